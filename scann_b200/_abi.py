@@ -1,0 +1,87 @@
+"""ctypes binding of ``libscann_b200.so`` (declared in ``include/scann_b200.h``).
+
+There is no CPU fallback: importing this module without the built library, or calling a
+compute entry point without a CUDA device, raises.  Build with ``python -m scann_b200.build``
+(or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libscann_b200.so")
+
+vp = C.c_void_p
+ci = C.c_int
+
+# name -> (restype, argtypes).  Mirrors include/scann_b200.h exactly; tests/test_abi.py checks
+# that every symbol declared in the header is exported and listed here.
+PROTOTYPES = {
+    "scann_last_error": (C.c_char_p, []),
+    "scann_version": (ci, []),
+    "scann_device_sm_count": (ci, []),
+    "scann_device_cc": (ci, []),
+    "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
+    "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp]),
+    "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp]),
+    "scann_geom_init_forward": (ci, [vp, ci] + [vp] * 10 + [vp]),
+    "scann_geom_init_backward": (ci, [vp, ci] + [vp] * 14 + [vp]),
+    "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
+    "scann_dense_wgrad": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp]),
+    "scann_layernorm_backward": (ci, [vp, vp, vp, ci, vp, vp, ci, vp, vp, vp]),
+    "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
+    "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
+    "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
+    "scann_la_backward": (ci, [ci] + [vp] * 30 + [vp]),
+    "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
+    "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),
+    "scann_adam_step": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
+    "scann_loss_value": (ci, [vp, vp, ci, vp, C.c_float, C.c_float, vp, vp]),
+}
+
+
+class ScannAbiError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the sm_100a extension has not been built "
+            "(run `python -m scann_b200.build`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return lib.scann_last_error().decode()
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        raise ScannAbiError(f"{what or 'scann'} failed (status {status}): {last_error()}")
+
+
+def require_gpu() -> int:
+    """Number of SMs of the current device; raises when no CUDA device is usable."""
+    sms = lib.scann_device_sm_count()
+    if sms <= 0:
+        raise ScannAbiError("scann_b200 needs a CUDA device (sm_100a); no CPU fallback exists: " + last_error())
+    return sms
+
+
+def ptr_array(ptrs):
+    """A C array of pointers (``const float* const*``) from ints / None."""
+    arr = (vp * len(ptrs))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p if p else None
+    return arr

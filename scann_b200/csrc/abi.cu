@@ -1,0 +1,50 @@
+// C-ABI plumbing shared by all translation units: error string, launch check, device info.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void scann_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int scann_check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        scann_set_error("%s: %s", what, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+
+extern "C" const char* scann_last_error(void) { return g_err; }
+
+extern "C" int scann_version(void) { return 100; }   // 0.1.0
+
+// Number of SMs of the current device, or -1 (with the error string set) when no CUDA device
+// is usable.  The product path calls this first and refuses to run without a GPU.
+extern "C" int scann_device_sm_count(void) {
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) {
+        scann_set_error("no usable CUDA device: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -1;
+    }
+    return sms;
+}
+
+extern "C" int scann_device_cc(void) {
+    int dev = 0, major = 0, minor = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    return major * 10 + minor;
+}

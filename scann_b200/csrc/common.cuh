@@ -1,0 +1,62 @@
+// Shared device helpers for the SCANN sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SCANN_D 128          // local_dim = global_dim = dense_out (every shipped config)
+#define SCANN_H 8            // attention heads
+#define SCANN_HD 16          // head dim
+#define SCANN_RBF 20         // Gaussian centres
+#define SCANN_TILE 128       // pair rows per tile (= UMMA M)
+#define SCANN_LN_EPS 1e-6f   // LayerNormalization(epsilon=1e-6), attention.py:35,111,113
+
+// error plumbing (abi.cu)
+void scann_set_error(const char* fmt, ...);
+int scann_check_launch(const char* what);
+
+// device-side status word shared by all kernels of one engine (bit flags)
+#define SCANN_ERR_TILE_OVERFLOW 1   // plan needed more tiles than the caller allocated
+#define SCANN_ERR_TOO_MANY_NBRS 2   // an atom has more than SCANN_TILE valid neighbours
+#define SCANN_ERR_BAD_ATOMIC 4      // atomic number outside the embedding table
+#define SCANN_ERR_BAD_NEIGHBOR 8    // neighbour index outside [0, M)
+
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
+// d/dx [x * sigmoid(x)] = s * (1 + x * (1 - s))
+__device__ __forceinline__ float swish_grad_f(float x) {
+    float s = sigmoid_f(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// reduce over the 16 lanes that share (lane & 16)
+__device__ __forceinline__ float half_warp_sum(float v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// reduce over groups of 4 consecutive lanes
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// vectorised fire-and-forget reduction into global memory (sm_90+)
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}

@@ -1,0 +1,76 @@
+// Optimiser step over the flat parameter arena: Keras-2.10 Adam(lr, decay=1e-5)
+// (scann/models/scann_model.py:212) fused with the loss-gradient scaling and the l2
+// regulariser gradient (kernel_regularizer=l2(1e-4): attention.py:27-28,95,97,108,260,262;
+// scann_model.py:428,441).
+//
+// Backward kernels produce  G = sum_b err_b * d y_b / d theta  (err_b = y_b - t_b).
+// loss = sqrt(SSE / B) + 1e-4 * sum_{l2 kernels} W^2   (scann/layers/losses.py:5-6), hence
+//   d loss / d theta = G / (B * sqrt(SSE / B)) + 2e-4 * W * [theta is an l2 kernel]
+// SSE sits right behind the gradients in the same arena so one all-reduce covers both.
+#include "common.cuh"
+
+struct AdamScalars {      // filled by the host every step (device copy)
+    float alpha;          // lr_t * sqrt(1 - b2^t) / (1 - b1^t)
+    float b1, b2, eps;
+    float l2;             // 1e-4
+    float batch;          // global batch size B
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   const float* __restrict__ l2mask, int n,
+                                                   const float* __restrict__ sse, const AdamScalars* __restrict__ hs,
+                                                   float* __restrict__ grad_out, int apply) {
+    const AdamScalars h = *hs;
+    const float rmse = sqrtf(sse[0] / h.batch);
+    const float scale = 1.0f / (h.batch * rmse);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float w = p[i];
+        float gr = fmaf(g[i], scale, 2.0f * h.l2 * l2mask[i] * w);
+        if (grad_out) grad_out[i] = gr;
+        if (apply) {
+            float mi = h.b1 * m[i] + (1.0f - h.b1) * gr;
+            float vi = h.b2 * v[i] + (1.0f - h.b2) * gr * gr;
+            m[i] = mi;
+            v[i] = vi;
+            p[i] = w - h.alpha * mi / (sqrtf(vi) + h.eps);
+        }
+    }
+}
+
+// out[0] = sqrt(SSE/B) + l2 * sum(mask * p^2) ; out[1] = sqrt(SSE/B) ; out[2] = sum|err| / B
+__global__ void __launch_bounds__(1024) loss_value_kernel(const float* __restrict__ p,
+                                                          const float* __restrict__ l2mask, int n,
+                                                          const float* __restrict__ sse, float batch, float l2,
+                                                          float* __restrict__ out) {
+    __shared__ float s_red[32];
+    float a = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmaf(l2mask[i] * p[i], p[i], a);
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t += s_red[w];
+        float rmse = sqrtf(sse[0] / batch);
+        out[0] = rmse + l2 * t;
+        out[1] = rmse;
+        out[2] = sse[1] / batch;
+    }
+}
+
+extern "C" int scann_adam_step(float* params, const float* grads, float* m, float* v, const float* l2mask, int n,
+                               const float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream) {
+    if (n <= 0) return 0;
+    int grid = (n + 255) / 256;
+    if (grid > 1184) grid = 1184;
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, l2mask, n, sse,
+                                                        (const AdamScalars*)scalars_dev, grad_out, apply);
+    return scann_check_launch("scann_adam_step");
+}
+
+extern "C" int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch,
+                                float l2, float* out3, void* stream) {
+    loss_value_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, l2mask, n, sse, batch, l2, out3);
+    return scann_check_launch("scann_loss_value");
+}

@@ -1,0 +1,145 @@
+// Batch plan: padded [B,M,N] neighbour lists -> tile-padded packed pair layout.
+//
+// The reference keeps every (atom, neighbour-slot) pair of the padded batch and masks
+// the invalid ones (scann/utils/datagenerator.py:80-101, scann/layers/attention.py:186-206).
+// Masked slots never reach a model output (their softmax weight is exactly 0 in fp32 and
+// the context sum multiplies by the mask again), so the kernels only materialise VALID
+// pairs.  Pairs of one centre atom stay contiguous (slot order preserved) and are grouped
+// into tiles of at most SCANN_TILE rows that never split an atom; tile t owns rows
+// [t*128, t*128+128) of every per-pair tensor, unused rows are padding (pair_c = -1).
+#include "common.cuh"
+
+#define PLAN_GSZ 128   // atom rows per greedy group (one thread walks one group)
+
+__global__ void plan_count_kernel(const uint8_t* __restrict__ nmask, const int32_t* __restrict__ nbr,
+                                  int R, int M, int N, int32_t* __restrict__ cnt, int32_t* __restrict__ status) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const uint8_t* m = nmask + (size_t)r * N;
+    const int32_t* j = nbr + (size_t)r * N;
+    int c = 0, bad = 0;
+    for (int n = 0; n < N; ++n) {
+        if (m[n]) {
+            ++c;
+            int v = j[n];
+            bad |= (v < 0) | (v >= M);
+        }
+    }
+    if (c > SCANN_TILE) { atomicOr(status, SCANN_ERR_TOO_MANY_NBRS); c = 0; }
+    if (bad) { atomicOr(status, SCANN_ERR_BAD_NEIGHBOR); c = 0; }
+    cnt[r] = c;
+}
+
+// One thread per group of PLAN_GSZ consecutive atom rows: greedy first-fit in order.
+// rowptr[r] <- local_tile*128 + offset (group-local); gtiles[g] <- tiles used by the group.
+__global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ngroups,
+                                  int32_t* __restrict__ rowptr, int32_t* __restrict__ gtiles) {
+    __shared__ int32_t s_cnt[32 * (PLAN_GSZ + 1)];
+    int g0 = blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * PLAN_GSZ; i += blockDim.x) {
+        int g = i / PLAN_GSZ, a = i % PLAN_GSZ;
+        int r = (g0 + g) * PLAN_GSZ + a;
+        s_cnt[g * (PLAN_GSZ + 1) + a] = (r < R) ? cnt[r] : 0;
+    }
+    __syncthreads();
+    int g = g0 + threadIdx.x;
+    if (threadIdx.x >= 32 || g >= ngroups) return;
+    int32_t* sc = s_cnt + threadIdx.x * (PLAN_GSZ + 1);
+    int tile = 0, fill = 0, any = 0;
+    for (int a = 0; a < PLAN_GSZ; ++a) {
+        int c = sc[a];
+        if (c == 0) { sc[a] = -1; continue; }
+        if (fill + c > SCANN_TILE) { ++tile; fill = 0; }
+        sc[a] = tile * SCANN_TILE + fill;
+        fill += c;
+        any = 1;
+    }
+    gtiles[g] = any ? tile + 1 : 0;
+    __syncwarp();
+    for (int a = 0; a < PLAN_GSZ; ++a) {
+        int r = g * PLAN_GSZ + a;
+        if (r < R) rowptr[r] = sc[a];
+    }
+}
+
+// Exclusive scan of gtiles (single CTA) -> gbase ; total -> ntiles.
+__global__ void plan_scan_kernel(const int32_t* __restrict__ gtiles, int ngroups, int tile_cap,
+                                 int32_t* __restrict__ gbase, int32_t* __restrict__ ntiles,
+                                 int32_t* __restrict__ status) {
+    __shared__ int32_t s_part[1024];
+    int per = (ngroups + blockDim.x - 1) / blockDim.x;
+    int lo = threadIdx.x * per, hi = min(lo + per, ngroups);
+    int sum = 0;
+    for (int g = lo; g < hi; ++g) sum += gtiles[g];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) { int v = s_part[i]; s_part[i] = run; run += v; }
+        if (run > tile_cap) { atomicOr(status, SCANN_ERR_TILE_OVERFLOW); run = 0; }
+        *ntiles = run;
+    }
+    __syncthreads();
+    int run = s_part[threadIdx.x];
+    for (int g = lo; g < hi; ++g) { gbase[g] = run; run += gtiles[g]; }
+}
+
+__global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_t* __restrict__ nbr,
+                                 const float* __restrict__ dist, const float* __restrict__ weight,
+                                 const int32_t* __restrict__ cnt, const int32_t* __restrict__ gbase,
+                                 const int32_t* __restrict__ ntiles, int R, int M, int N,
+                                 int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_a0,
+                                 int32_t* __restrict__ tile_a1, int32_t* __restrict__ pair_c,
+                                 int32_t* __restrict__ pair_j, int32_t* __restrict__ pair_slot,
+                                 float* __restrict__ pair_d, float* __restrict__ pair_w) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int c = cnt[r];
+    if (c == 0 || *ntiles == 0) { rowptr[r] = 0; return; }
+    int rp = gbase[r / PLAN_GSZ] * SCANN_TILE + rowptr[r];
+    rowptr[r] = rp;
+    int tile = rp / SCANN_TILE;
+    if (rp % SCANN_TILE == 0) tile_a0[tile] = r;
+    atomicMax(&tile_a1[tile], r + 1);
+    int b = r / M;
+    const uint8_t* m = nmask + (size_t)r * N;
+    int k = 0;
+    for (int n = 0; n < N; ++n) {
+        if (m[n]) {
+            size_t s = (size_t)r * N + n;
+            int p = rp + k++;
+            pair_c[p] = r;
+            pair_j[p] = b * M + nbr[s];
+            pair_slot[p] = (int32_t)s;
+            pair_d[p] = dist[s];
+            pair_w[p] = weight[s];
+        }
+    }
+}
+
+extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
+                                const float* weight, int B, int M, int N, int tile_cap, int32_t* cnt,
+                                int32_t* rowptr, int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles,
+                                int32_t* pair_c, int32_t* pair_j, int32_t* pair_slot, float* pair_d,
+                                float* pair_w, int32_t* scratch, int scratch_len, int32_t* status, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    long long Rll = (long long)B * M;
+    if (Rll <= 0 || N <= 0 || Rll * N > 0x7fffffffLL) { scann_set_error("plan: bad shape B=%d M=%d N=%d", B, M, N); return 1; }
+    int R = (int)Rll;
+    int ngroups = (R + PLAN_GSZ - 1) / PLAN_GSZ;
+    if (scratch_len < 2 * ngroups) { scann_set_error("plan: scratch too small (%d < %d)", scratch_len, 2 * ngroups); return 1; }
+    int32_t* gtiles = scratch;
+    int32_t* gbase = scratch + ngroups;
+    size_t rows = (size_t)tile_cap * SCANN_TILE;
+    // padding rows are recognised by pair_c < 0; every consumer guards on it, so the other
+    // per-pair arrays need no initialisation.  tile_a1 is built with atomicMax.
+    cudaMemsetAsync(pair_c, 0xFF, rows * sizeof(int32_t), st);
+    cudaMemsetAsync(tile_a1, 0, (size_t)tile_cap * sizeof(int32_t), st);
+    plan_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(neighbor_mask, neighbors, R, M, N, cnt, status);
+    plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, rowptr, gtiles);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(gtiles, ngroups, tile_cap, gbase, ntiles, status);
+    plan_fill_kernel<<<(R + 127) / 128, 128, 0, st>>>(neighbor_mask, neighbors, dist, weight, cnt, gbase, ntiles, R, M,
+                                                     N, rowptr, tile_a0, tile_a1, pair_c, pair_j, pair_slot, pair_d,
+                                                     pair_w);
+    return scann_check_launch("scann_plan_build");
+}

@@ -1,0 +1,446 @@
+"""Device engine: orchestrates the sm_100a kernels for one SCANN model on one GPU.
+
+Host logic only (Python): owns the flat parameter / gradient arenas and the per-shape
+workspaces, and issues the C-ABI kernel calls on the current torch CUDA stream.  torch is
+used for device memory, streams and host<->device copies -- never for arithmetic on the
+hot path.  Graph being executed: ``create_model`` of the reference
+(scann/models/scann_model.py:329-453); see DESIGN.md for the kernel schedule.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import check, lib, ptr_array
+from .config import ModelSpec, N_RBF, check_kernel_support
+from .params import ParamLayout, layer_name
+
+TILE = 128
+PLAN_GSZ = 128
+D = 128
+L2_COEF = 1e-4
+
+ERR_BITS = {1: "plan tile capacity exceeded", 2: "an atom has more than 128 valid neighbours",
+            4: "atomic number outside the embedding table", 8: "neighbour index outside [0, M)"}
+
+
+def _p(t: Optional[torch.Tensor], off_elems: int = 0) -> int:
+    if t is None:
+        return 0
+    return t.data_ptr() + off_elems * t.element_size()
+
+
+class Batch:
+    """Device-resident inputs of one padded batch plus its pair plan."""
+
+    def __init__(self):
+        self.B = self.M = self.N = self.R = 0
+        self.tile_cap = 0
+        self.P_host = None          # number of valid pairs when known on the host
+        self.A_host = None
+
+
+class Engine:
+    def __init__(self, spec: ModelSpec, arena: Optional[np.ndarray] = None, device: Optional[torch.device] = None,
+                 seed: int = 1):
+        check_kernel_support(spec)
+        if not spec.g_update:
+            raise NotImplementedError("g_update=False (SCANN without geometry update) is not on the accelerated path yet")
+        if spec.use_ring:
+            raise NotImplementedError("use_ring=True is not on the accelerated path yet")
+        self.sm_count = _abi.require_gpu()
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.spec = spec
+        self.layout = ParamLayout(spec)
+        n = self.layout.total
+        if arena is None:
+            arena = self.layout.init_arena(seed)
+        assert arena.shape == (n,)
+        dev = self.device
+        self.params = torch.from_numpy(np.ascontiguousarray(arena, np.float32)).to(dev)
+        self.paramsT = torch.zeros(n, dtype=torch.float32, device=dev)
+        # gradient arena: [0,n) gradients, [n] SSE, [n+1] sum |err|  (one all-reduce covers all)
+        self.grads = torch.zeros(n + 4, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.l2mask = torch.from_numpy(self.layout.l2_mask()).to(dev)
+        self.grad_out = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.adam_scalars = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._adam_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.step_count = 0
+        # RBF centres: np.linspace(0, gaussian_d, 20) / np.linspace(0, 2*pi, 20), float32 (scann_model.py:378,384)
+        self.centers_d = torch.from_numpy(np.linspace(0, spec.gaussian_d, N_RBF, dtype="float32")).to(dev)
+        self.centers_w = torch.from_numpy(np.linspace(0, np.pi * 2, N_RBF, dtype="float32")).to(dev)
+        # list of 128x128 weight blocks whose transpose the backward pass needs
+        offs = []
+        for e in self.layout:
+            if e.name.endswith("/kernel") and len(e.shape) == 2 and e.shape[1] == D and e.shape[0] % D == 0:
+                for blk in range(e.shape[0] // D):
+                    offs.append(e.offset + blk * D * D)
+        self.tblocks = torch.tensor(offs, dtype=torch.int32, device=dev)
+        self._ws: Dict[Tuple, dict] = {}
+        self._pinned: Dict[Tuple, dict] = {}
+        self.la_grid = self.sm_count
+        self.launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def w(self, name: str, off: int = 0) -> int:
+        return _p(self.params, self.layout[name].offset + off)
+
+    def wT(self, name: str, off: int = 0) -> int:
+        return _p(self.paramsT, self.layout[name].offset + off)
+
+    def gw(self, name: str, off: int = 0) -> int:
+        return _p(self.grads, self.layout[name].offset + off)
+
+    def check_status(self) -> None:
+        s = int(self.status.item())
+        if s:
+            self.status.zero_()
+            msgs = [m for b, m in ERR_BITS.items() if s & b]
+            raise _abi.ScannAbiError("device status: " + "; ".join(msgs))
+
+    def set_params(self, arena: np.ndarray) -> None:
+        self.params.copy_(torch.from_numpy(np.ascontiguousarray(arena, np.float32)))
+
+    def get_params(self) -> np.ndarray:
+        return self.params.cpu().numpy()
+
+    # ------------------------------------------------------------------ inputs
+    def load_batch(self, inputs: Dict[str, object]) -> Batch:
+        """Stage one padded batch (reference layout, scann/utils/datagenerator.py:123-135) on the
+        device and build its pair plan.  Host arrays go through pinned staging buffers; objects
+        that are already CUDA tensors (or export ``__dlpack__``) are used in place."""
+        b = Batch()
+        dev = self.device
+
+        def to_dev(x, dtype, key):
+            if isinstance(x, torch.Tensor):
+                t = x
+            elif hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
+                t = torch.from_dlpack(x)
+            else:
+                a = np.ascontiguousarray(x)
+                if a.dtype == np.bool_:
+                    a = a.view(np.uint8)
+                slot = self._pinned.get((key, a.shape, a.dtype.str))
+                if slot is None:
+                    pin = torch.empty(a.shape, dtype=torch.from_numpy(a.reshape(-1)[:0].copy()).dtype).pin_memory()
+                    slot = self._pinned[(key, a.shape, a.dtype.str)] = [pin, None]
+                pin, ev = slot
+                if ev is not None:
+                    ev.synchronize()            # the previous async copy out of this buffer has finished
+                pin.numpy()[...] = a
+                t = pin.to(dev, non_blocking=True)
+                slot[1] = torch.cuda.Event()
+                slot[1].record(torch.cuda.current_stream(dev))
+                b.h2d_bytes = getattr(b, "h2d_bytes", 0) + a.nbytes
+            if t.device != dev:
+                t = t.to(dev, non_blocking=True)
+            if dtype == torch.uint8:
+                if t.dtype == torch.bool:
+                    t = t.view(torch.uint8) if t.is_contiguous() else t.contiguous().view(torch.uint8)
+                elif t.dtype != torch.uint8:
+                    t = (t != 0).view(torch.uint8)
+            elif t.dtype != dtype:
+                t = t.to(dtype)
+            return t.contiguous()
+
+        nb = inputs["neighbors"]
+        B, M, N = (int(s) for s in nb.shape)
+        b.B, b.M, b.N, b.R = B, M, N, B * M
+        nmask_in = inputs["neighbor_mask"]
+        if isinstance(nmask_in, np.ndarray):
+            b.P_host = int(np.count_nonzero(nmask_in))
+        b.atomic = to_dev(inputs["atomic"], torch.int32, "atomic").view(-1)
+        b.atom_mask = to_dev(inputs["atom_mask"], torch.uint8, "atom_mask").view(-1)
+        b.nbr = to_dev(nb, torch.int32, "neighbors").view(-1)
+        b.nmask = to_dev(nmask_in, torch.uint8, "neighbor_mask").view(-1)
+        b.weight = to_dev(inputs["neighbor_weight"], torch.float32, "neighbor_weight").view(-1)
+        b.dist = to_dev(inputs["neighbor_distance"], torch.float32, "neighbor_distance").view(-1)
+        if b.atomic.numel() != b.R or b.atom_mask.numel() != b.R:
+            raise ValueError("atomic / atom_mask must be [B,M] / [B,M,1]")
+        # tile capacity: every non-final tile of a greedy group holds more than 128-N rows
+        P = b.P_host if b.P_host is not None else B * M * N
+        ngroups = (b.R + PLAN_GSZ - 1) // PLAN_GSZ
+        cap = P // (129 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2
+        b.tile_cap = max(64, (cap + 63) // 64 * 64)
+        b.ngroups = ngroups
+        self._plan(b)
+        return b
+
+    def _plan(self, b: Batch) -> None:
+        dev = self.device
+        rows = b.tile_cap * TILE
+        i32 = dict(dtype=torch.int32, device=dev)
+        b.cnt = torch.empty(b.R, **i32)
+        b.rowptr = torch.empty(b.R, **i32)
+        b.tile_a0 = torch.empty(b.tile_cap, **i32)
+        b.tile_a1 = torch.empty(b.tile_cap, **i32)
+        b.ntiles = torch.zeros(1, **i32)
+        b.pair_c = torch.empty(rows, **i32)
+        b.pair_j = torch.empty(rows, **i32)
+        b.pair_slot = torch.empty(rows, **i32)
+        b.pair_d = torch.empty(rows, dtype=torch.float32, device=dev)
+        b.pair_w = torch.empty(rows, dtype=torch.float32, device=dev)
+        b.scratch = torch.empty(2 * b.ngroups + 8, **i32)
+        check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
+                                   _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
+                                   _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
+                                   _p(b.scratch), b.scratch.numel(), _p(self.status), self._stream()), "plan_build")
+        self.launches += 4
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, b: Batch, training: bool) -> dict:
+        key = (b.R, b.B, b.tile_cap, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        dev = self.device
+        L = self.spec.n_attention
+        R, rows = b.R, b.tile_cap * TILE
+        f = dict(dtype=torch.float32, device=dev)
+        ws = {}
+        nsave = L + 1 if training else 2
+        ws["g"] = [torch.empty(rows, D, **f) for _ in range(nsave)]
+        ws["x"] = [torch.empty(R, D, **f) for _ in range(L + 1 if training else 2)]
+        nl = L if training else 1
+        ws["proj"] = [torch.empty(R, 3 * D, **f) for _ in range(nl)]
+        ws["h"] = [torch.empty(R, D, **f) for _ in range(nl)]
+        ws["h1"] = [torch.empty(R, D, **f) for _ in range(nl)]
+        if training:
+            ws["t0"] = torch.empty(R, D, **f)
+            ws["ctxpre"] = [torch.empty(R, D, **f) for _ in range(L)]
+            ws["t1"] = [torch.empty(R, D, **f) for _ in range(L)]
+            ws["v2"] = [torch.empty(R, D, **f) for _ in range(L)]
+            ws["ta"] = torch.empty(R, D, **f)
+            ws["ctxg"] = torch.empty(b.B, D, **f)
+            ws["tb"] = torch.empty(b.B, D, **f)
+            # backward temporaries
+            for k in ("dx", "d_v2", "d_t1", "d_h", "d_ctx", "dq", "d_ta"):
+                ws[k] = torch.empty(R, D, **f)
+            ws["scat"] = torch.empty(3, R, D, **f)           # s_pre, t_scatter, dx_scatter (zeroed together)
+            ws["dg"] = [torch.empty(rows, D, **f) for _ in range(2)]
+            ws["d_qk"] = torch.empty(R, 2 * D, **f)
+            ws["d_tb"] = torch.empty(b.B, D, **f)
+            ws["dy"] = torch.empty(b.B, **f)
+            ws["wpart"] = torch.empty(self.la_grid, 2, D, D, **f)
+            ws["G"] = torch.empty(self.spec.n_atoms + 3, D, **f)
+        ws["xa"] = torch.empty(R, D, **f)
+        ws["qk"] = torch.empty(R, 2 * D, **f)
+        ws["ga"] = torch.empty(R, **f)
+        ws["y"] = torch.empty(b.B, **f)
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ thin kernel wrappers
+    def _dense(self, A, lda, W, bias, kblk, nblk, R, C, ldc, mode=0, resid=None, ldres=D, pre_in=None, pre_out=None,
+               gamma=0, beta=0):
+        check(lib.scann_dense_forward(ptr_array(A), lda, ptr_array(W), ptr_array(bias) if bias else None, kblk, nblk,
+                                      R, C, ldc, mode, _p(resid), ldres, _p(pre_in), _p(pre_out), gamma, beta,
+                                      self._stream()), "dense_forward")
+        self.launches += 1
+
+    def _wgrad(self, A, lda, G, ldg, kblk, nblk, R, dW, db):
+        check(lib.scann_dense_wgrad(ptr_array(A), lda, ptr_array(G), ldg, kblk, nblk, R, ptr_array(dW),
+                                    ptr_array(db) if db else None, self._stream()), "dense_wgrad")
+        self.launches += 1
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, b: Batch, training: bool = False, attn_out: Optional[list] = None):
+        """Runs the whole graph; returns (y[B], ga[B*M]) device tensors (views of the workspace)."""
+        sp, st = self.spec, self._stream()
+        ws = self._workspace(b, training)
+        L, R = sp.n_attention, b.R
+        xs, gs = ws["x"], ws["g"]
+        E = sp.embedding_dim
+        check(lib.scann_embed_forward(_p(b.atomic), 0, R, E, sp.n_atoms, self.w("embed_atom/embeddings"), 0, 0,
+                                      self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
+                                      _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status), st), "embed_forward")
+        check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+                                          _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
+                                          self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
+                                          self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
+        self.launches += 2
+        for l in range(L):
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            li = l if training else 0
+            x_in = xs[l] if training else xs[l % 2]
+            x_out = xs[l + 1] if training else xs[(l + 1) % 2]
+            g_in = gs[l] if training else gs[l % 2]
+            g_out = gs[l + 1] if training else gs[(l + 1) % 2]
+            proj, h, h1 = ws["proj"][li], ws["h"][li], ws["h1"][li]
+            fg = f"{la}/filter_geo/kernel"
+            # per-atom projections [x@W1+bf | x@W3 | x@Wq+bq]
+            self._dense([_p(x_in)], D, [self.w(fg, 0), self.w(fg, 2 * D * D), self.w(f"{la}/query/kernel")],
+                        [self.w(f"{la}/filter_geo/bias"), 0, self.w(f"{la}/query/bias")], 1, 3, R, _p(proj), 3 * D)
+            ctxpre = ws["ctxpre"][l] if training else None
+            out = h if sp.use_attn_norm else x_out
+            check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
+                                              self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), st), "la_nopair")
+            attn = None
+            if attn_out is not None:
+                attn = torch.zeros(b.tile_cap * TILE, 8, dtype=torch.float32, device=self.device)
+                attn_out.append(attn)
+            check(lib.scann_la_forward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                                       _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),
+                                       self.w(fg, D * D), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                                       self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
+                                       self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
+                                       _p(g_out), _p(ctxpre), _p(out), _p(attn), st), "la_forward")
+            self.launches += 2
+            if sp.use_attn_norm:
+                # ResidualNorm: LN(h + Dense(swish(Dense(h))))  (attention.py:25-40)
+                self._dense([_p(h)], D, [self.w(f"{rn}/dense/kernel")], [self.w(f"{rn}/dense/bias")], 1, 1, R, _p(h1),
+                            D, mode=1, pre_out=ws["t1"][l] if training else None)
+                self._dense([_p(h1)], D, [self.w(f"{rn}/dense_1/kernel")], [self.w(f"{rn}/dense_1/bias")], 1, 1, R,
+                            _p(x_out), D, mode=3, resid=h, pre_out=ws["v2"][l] if training else None,
+                            gamma=self.w(f"{rn}/layer_norm/gamma"), beta=self.w(f"{rn}/layer_norm/beta"))
+        x_last = xs[L] if training else xs[L % 2]
+        self._dense([_p(x_last)], D, [self.w("after_Lc/kernel")], [self.w("after_Lc/bias")], 1, 1, R, _p(ws["xa"]), D,
+                    mode=1, pre_out=ws["ta"] if training else None)
+        self._dense([_p(ws["xa"])], D, [self.w("global_attention/query/kernel"), self.w("global_attention/key/kernel")],
+                    [self.w("global_attention/query/bias"), self.w("global_attention/key/bias")], 1, 2, R,
+                    _p(ws["qk"]), 2 * D)
+        check(lib.scann_ga_head_forward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
+                                        self.w("bf_property/kernel"), self.w("bf_property/bias"),
+                                        self.w("predict_property/kernel"), self.w("predict_property/bias"),
+                                        int(sp.mrelu_head), _p(ws["ga"]), _p(ws["y"]),
+                                        _p(ws["ctxg"]) if training else 0, _p(ws["tb"]) if training else 0, st),
+              "ga_head_forward")
+        self.launches += 1
+        return ws["y"], ws["ga"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, b: Batch, target: torch.Tensor) -> None:
+        """Accumulates G = sum_b (y_b - t_b) dy_b/dtheta into the (pre-zeroed) gradient arena and
+        the SSE into its tail.  ``forward(b, training=True)`` must have run on the same batch."""
+        sp, st = self.spec, self._stream()
+        ws = self._workspace(b, True)
+        L, R, n = sp.n_attention, b.R, self.layout.total
+        check(lib.scann_transpose_blocks(_p(self.params), _p(self.paramsT), _p(self.tblocks), self.tblocks.numel(), st),
+              "transpose_blocks")
+        check(lib.scann_rmse_prepare(_p(ws["y"]), _p(target), b.B, _p(ws["dy"]), _p(self.grads, n), st), "rmse_prepare")
+        check(lib.scann_ga_head_backward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
+                                         self.wT("bf_property/kernel"), self.w("predict_property/kernel"),
+                                         _p(ws["tb"]), _p(ws["dy"]), _p(ws["d_qk"]), _p(ws["d_tb"]),
+                                         self.gw("predict_property/kernel"), self.gw("predict_property/bias"), st),
+              "ga_head_backward")
+        self.launches += 3
+        self._wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
+                    [self.gw("bf_property/bias")])
+        dqk = ws["d_qk"]
+        self._wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
+                    [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
+                    [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
+        self._dense([_p(dqk), _p(dqk, D)], 2 * D,
+                    [self.wT("global_attention/query/kernel"), self.wT("global_attention/key/kernel")], None, 2, 1, R,
+                    _p(ws["d_ta"]), D, mode=2, pre_in=ws["ta"])
+        self._wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")],
+                    [self.gw("after_Lc/bias")])
+        dx = ws["dx"]
+        self._dense([_p(ws["d_ta"])], D, [self.wT("after_Lc/kernel")], None, 1, 1, R, _p(dx), D)
+        dg_up = None
+        for l in range(L - 1, -1, -1):
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            fg = f"{la}/filter_geo/kernel"
+            if sp.use_attn_norm:
+                check(lib.scann_layernorm_backward(_p(dx), _p(ws["v2"][l]), self.w(f"{rn}/layer_norm/gamma"), R,
+                                                   _p(ws["d_v2"]), 0, D, self.gw(f"{rn}/layer_norm/gamma"),
+                                                   self.gw(f"{rn}/layer_norm/beta"), st), "ln_bwd")
+                self._wgrad([_p(ws["h1"][l])], D, [_p(ws["d_v2"])], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
+                            [self.gw(f"{rn}/dense_1/bias")])
+                self._dense([_p(ws["d_v2"])], D, [self.wT(f"{rn}/dense_1/kernel")], None, 1, 1, R, _p(ws["d_t1"]), D,
+                            mode=2, pre_in=ws["t1"][l])
+                self._wgrad([_p(ws["h"][l])], D, [_p(ws["d_t1"])], D, 1, 1, R, [self.gw(f"{rn}/dense/kernel")],
+                            [self.gw(f"{rn}/dense/bias")])
+                self._dense([_p(ws["d_t1"])], D, [self.wT(f"{rn}/dense/kernel")], None, 1, 1, R, _p(ws["d_h"]), D,
+                            resid=ws["d_v2"])
+                d_h = ws["d_h"]
+                self.launches += 1
+            else:
+                d_h = dx
+            check(lib.scann_layernorm_backward(_p(d_h), _p(ws["ctxpre"][l]), self.w(f"{la}/layer_norm/gamma"), R,
+                                               _p(ws["d_ctx"]), _p(ws["dq"]), D, self.gw(f"{la}/layer_norm/gamma"),
+                                               self.gw(f"{la}/layer_norm/beta"), st), "ln_bwd")
+            ws["scat"].zero_()
+            s_pre, t_sc, dx_sc = ws["scat"][0], ws["scat"][1], ws["scat"][2]
+            dg_out = ws["dg"][l % 2]
+            check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                                        _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
+                                        _p(ws["g"][l]), self.w(fg, D * D), self.w(f"{la}/key/kernel"),
+                                        self.wT(fg, D * D), self.wT(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                                        self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
+                                        _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(ws["dq"]), _p(s_pre), _p(t_sc),
+                                        _p(dx_sc), _p(ws["wpart"]), self.gw(f"{la}/key/kernel"), self.gw(fg, D * D),
+                                        self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
+                                        self.gw(f"{la}/key/bias"), st), "la_backward")
+            self.launches += 4
+            self._wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(ws["dq"])], D, 1, 3, R,
+                        [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
+                        [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
+            self._dense([_p(s_pre), _p(t_sc), _p(ws["dq"])], D,
+                        [self.wT(fg, 0), self.wT(fg, 2 * D * D), self.wT(f"{la}/query/kernel")], None, 3, 1, R, _p(dx),
+                        D, resid=dx_sc)
+            dg_up = dg_out
+        check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+                                           _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
+                                           self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
+                                           self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),
+                                           self.gw("neighbor_d/bias"), self.gw("neighbor_w/kernel"),
+                                           self.gw("neighbor_w/bias"), st), "geom_init_backward")
+        E = sp.embedding_dim
+        check(lib.scann_embed_backward(_p(b.atomic), 0, R, E, sp.n_atoms, self.w("embed_atom/embeddings"), 0, 0,
+                                       self.w("dense_embed/kernel"), _p(ws["t0"]), _p(dx), _p(ws["G"]),
+                                       self.gw("embed_atom/embeddings"), 0, 0, self.gw("dense_embed/kernel"),
+                                       self.gw("dense_embed/bias"), st), "embed_backward")
+        self.launches += 4
+
+    # ------------------------------------------------------------------ optimiser
+    def _set_adam(self, lr: float, batch_global: int, decay: float = 1e-5, b1=0.9, b2=0.999, eps=1e-7):
+        t = self.step_count + 1
+        lr_t = lr / (1.0 + decay * (t - 1))                       # legacy Keras `decay`
+        alpha = lr_t * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
+        h = self._adam_host
+        h[0], h[1], h[2], h[3], h[4], h[5] = alpha, b1, b2, eps, L2_COEF, float(batch_global)
+        self.adam_scalars.copy_(h, non_blocking=True)
+
+    def apply_gradients(self, lr: float, batch_global: int, apply: bool = True, want_grads: bool = False) -> None:
+        self._set_adam(lr, batch_global)
+        n = self.layout.total
+        check(lib.scann_adam_step(_p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
+                                  _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
+                                  int(apply), self._stream()), "adam_step")
+        self.launches += 1
+        if apply:
+            self.step_count += 1
+
+    def loss_value(self, batch_global: int) -> torch.Tensor:
+        """[loss (RMSE + l2 terms), RMSE, MAE] of the batch whose SSE sits in the gradient arena."""
+        n = self.layout.total
+        check(lib.scann_loss_value(_p(self.params), _p(self.l2mask), n, _p(self.grads, n), float(batch_global),
+                                   L2_COEF, _p(self.loss_out), self._stream()), "loss_value")
+        self.launches += 1
+        return self.loss_out
+
+    def train_step(self, b: Batch, target: torch.Tensor, lr: float, allreduce=None, batch_global: Optional[int] = None,
+                   apply: bool = True, want_grads: bool = False) -> None:
+        """One Keras train_step (scann_model.py:232-241): forward, RMSE + l2 loss, backward, Adam.
+        ``allreduce(tensor)`` sums the gradient arena (+SSE) across data-parallel ranks."""
+        self.grads.zero_()
+        self.forward(b, training=True)
+        self.backward(b, target)
+        if allreduce is not None:
+            allreduce(self.grads)
+        self.apply_gradients(lr, batch_global or b.B, apply=apply, want_grads=want_grads)
