@@ -238,7 +238,7 @@ def loss_and_grads(w_np: Dict[str, np.ndarray], inputs_np: Dict[str, np.ndarray]
     loss = rmse_loss(torch.tensor(target, dtype=dtype), y) + l2_penalty(w, l2_names)
     loss.backward()
     grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in w.items()}
-    return float(loss), y.detach().numpy(), ga.detach().numpy(), grads
+    return float(loss.detach()), y.detach().numpy(), ga.detach().numpy(), grads
 
 
 def to_torch_inputs(inputs_np: Dict[str, np.ndarray], dtype=torch.float64) -> Dict[str, torch.Tensor]:
