@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the SCANN attention hot path on B200 (contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W            # our sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...   # reference restated on CPU
+
+Workload = BASELINE.json configs[1]: QM9 HOMO model (configs/model_qm9.yaml) train step
+(forward + backward + Adam), 128 structures per GPU, synthetic QM9-shaped padded batch
+(scann_b200/synth.py), random-init weights.  Weak scaling: every rank owns its own batch of 128;
+one NCCL all-reduce of the gradient arena per step.
+
+`value`   structures/s with the padded inputs already resident in HBM (plan + fwd + bwd + Adam).
+`e2e`     same metric through the public API ``model.train_on_batch(numpy inputs, targets)``:
+          host->device copies from pinned memory and a device->host read of the loss inside
+          the timed region.
+`roofline` the dominant kernel (local-attention backward) against measured HBM bandwidth.
+`cpu_baseline` the oracle (PyTorch-CPU restatement of the reference graph; TensorFlow is not
+          installable here) timed on the host cores for a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QM9_CONFIG = {
+    "model": {"n_atoms": 10, "embedding_dim": 48, "n_attention": 7, "local_dim": 128, "num_head": 8,
+              "global_dim": 128, "dense_out": 128, "scale": 0.5, "use_attn_norm": True, "use_ga_norm": True,
+              "use_ring": False, "g_update": True, "gaussian_d": 4.0, "feature": "atomic", "use_drop": False},
+    "hyper": {"batch_size": 128, "lr": 0.0005, "min_lr": 0.0001, "scheduler": "sgdr", "target": "homo"},
+}
+METRIC = "structures/sec (QM9 train step fwd+bwd+Adam, batch 128 per GPU)"
+UNIT = "structures/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference (oracle)
+def cpu_train_step_fn():
+    """One reference train step on the host: the oracle's fp32 restatement of the reference graph
+    with reverse-mode autodiff + Keras Adam.  Returns (step_fn, cores)."""
+    import torch
+    from oracle import scann_oracle as O
+    from scann_b200.config import model_spec
+    from scann_b200.params import ParamLayout
+    from scann_b200.synth import make_batch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec = model_spec(QM9_CONFIG)
+    lay = ParamLayout(spec)
+    w = lay.to_dict(lay.init_arena(1))
+    inp, tgt = make_batch("qm9", 0, B=128)
+    l2n = [e.name for e in lay if e.l2]
+    kw = dict(n_attention=spec.n_attention, g_update=True, gaussian_d=spec.gaussian_d, use_attn_norm=True,
+              use_ga_norm=True)
+    state = {"w": {k: v.copy() for k, v in w.items()}, "m": {k: np.zeros_like(v) for k, v in w.items()},
+             "v": {k: np.zeros_like(v) for k, v in w.items()}, "t": 0}
+
+    def step():
+        _, _, _, g = O.loss_and_grads(state["w"], inp, tgt, l2n, dtype=torch.float32, **kw)
+        state["t"] += 1
+        for k in state["w"]:
+            state["w"][k], state["m"][k], state["v"][k] = O.adam_legacy_step(
+                state["w"][k], g[k].astype(np.float32), state["m"][k], state["v"][k], state["t"], 5e-4)
+        return 128
+
+    return step, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores = cpu_train_step_fn()
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(args.steps):
+        n += step()
+    dt = time.perf_counter() - t0
+    v = n / dt
+    sample = f"{args.steps} train steps of one 128-structure QM9-shaped batch after {args.warmup} warm-up"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "qm9_train_step_b128", "note": "reference graph restated on CPU in PyTorch "
+                   "(TensorFlow 2.10 is not installable in this image); rank 0 only"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from scann_b200 import dist as sdist
+    from scann_b200.model import create_model
+    from scann_b200.synth import count_valid, make_batch
+
+    rank, local_rank, world = sdist.init()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    model = create_model(QM9_CONFIG, seed=1)
+    sdist.attach(model, world)
+    eng = model.engine
+    B = 128
+    inputs, target = make_batch("qm9", seed=rank, B=B)
+    A_valid, P_valid = count_valid(inputs)
+    lr = QM9_CONFIG["hyper"]["lr"]
+
+    # device-resident copies of the padded inputs (the `value` arm starts from HBM)
+    dev_inputs = {k: torch.from_numpy(np.ascontiguousarray(v.view(np.uint8) if v.dtype == np.bool_ else v)).to(dev)
+                  for k, v in inputs.items()}
+    tgt_dev = torch.from_numpy(target).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step_device():
+        b = eng.load_batch(dev_inputs)
+        eng.train_step(b, tgt_dev, lr, allreduce=model.allreduce, batch_global=B * world)
+        return b
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    eng.check_status()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: inputs resident in HBM
+    launches0 = eng.launches
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.fill_(1.0)                                   # L2 flush, outside the per-step events
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    launches = eng.launches - launches0
+    # ---- timed region 2: end to end through the public API (host buffers)
+    for _ in range(2):
+        model.train_on_batch(inputs, target)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.train_on_batch(inputs, target)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d, d2h = model.last_e2e_bytes
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- instrumented pass: CUDA events around the local-attention kernels
+    eng.prof = {}
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        step_device()
+    torch.cuda.synchronize()
+    prof = eng.prof_summary()
+    eng.prof = None
+    # ---- inference forward (reported beside the headline)
+    b = eng.load_batch(dev_inputs)
+    for _ in range(3):
+        eng.forward(b)
+    torch.cuda.synchronize()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
+    for _ in range(args.steps):
+        eng.forward(eng.load_batch(dev_inputs))
+    i1.record()
+    torch.cuda.synchronize()
+    infer_ms = i0.elapsed_time(i1)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, infer_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, infer_ms = (float(x) for x in t.cpu())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    L = QM9_CONFIG["model"]["n_attention"]
+    peaks, peak_kind = measured_peaks()
+    # algorithmic bytes per launch: valid pairs P and atoms A only
+    bytes_bwd = 1540.0 * P_valid + 1028.0 * A_valid
+    bytes_fwd = 1028.0 * P_valid + 1028.0 * A_valid
+    n_bwd, ms_bwd = prof.get("la_backward", (0, float("nan")))
+    n_fwd, ms_fwd = prof.get("la_forward", (0, float("nan")))
+    ach = bytes_bwd / (ms_bwd * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "la_bwd_simt_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+            "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
+            "share_of_step": n_bwd * ms_bwd / args.steps / (dev_ms / args.steps),
+            "la_forward": {"achieved": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "ms_per_launch": ms_fwd,
+                           "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+    # bounded CPU sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        step, cores = cpu_train_step_fn()
+        step()
+        t0 = time.perf_counter()
+        n = 0
+        while time.perf_counter() - t0 < args.cpu_seconds:
+            n += step()
+        cpu = {"value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n // 128} train steps of the same 128-structure batch (~{args.cpu_seconds:.0f} s), "
+                         "PyTorch-CPU restatement of the reference graph (TensorFlow not installable)"}
+    out = {
+        "metric": METRIC, "value": B * world * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "qm9_train_step_b128", "structures_per_gpu": B, "M": 29, "N": 16, "layers": L,
+                   "valid_atoms_per_gpu": A_valid, "valid_pairs_per_gpu": P_valid, "parallelism": f"dp{world}",
+                   "l2": "flushed between steps (256 MiB write outside the timed events)",
+                   "engine": "fp32 SIMT"},
+        "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "infer": {"value": B * world * args.steps / (infer_ms * 1e-3), "unit": UNIT,
+                  "note": "forward incl. ga_score, inputs resident in HBM"},
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,145 @@
+/* scann_b200.h -- C ABI of libscann_b200.so (sm_100a only, no CPU fallback).
+ *
+ * Drop-in boundary for the SCANN attention hot path.  The reference has no FFI: the path sits
+ * behind Keras Layer objects (scann/layers/attention.py, scann/layers/custom_layers.py) wired by
+ * create_model (scann/models/scann_model.py:329-453).  Each entry point below names the reference
+ * code it replaces.  Host code (Python, scann_b200/) binds these with ctypes and exchanges
+ * tensors with the caller via DLPack; see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *  - every function returns 0 on success; non-zero -> scann_last_error() holds a message;
+ *  - all pointers are DEVICE pointers unless stated; arguments are borrowed, outputs are
+ *    caller-allocated, nothing is allocated or freed inside the library;
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and re-entrant across
+ *    streams; the only global state is the per-thread error string;
+ *  - per-atom tensors are [R,128] fp32 row-major with R = B*M (row r = b*M + m);
+ *    per-pair tensors use the tile-padded packed layout built by scann_plan_build:
+ *    tile t owns rows [128 t, 128 t + 128), rows with pair_c < 0 are padding;
+ *  - weight blocks are [128,128] fp32 row-major (Keras Dense kernels, [in,out]);
+ *  - `status` is a device int32 of SCANN_ERR_* bits set by kernels on malformed input.
+ */
+#ifndef SCANN_B200_H
+#define SCANN_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCANN_ERR_TILE_OVERFLOW 1
+#define SCANN_ERR_TOO_MANY_NBRS 2
+#define SCANN_ERR_BAD_ATOMIC 4
+#define SCANN_ERR_BAD_NEIGHBOR 8
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* scann_last_error(void);
+int scann_version(void);
+/* SM count of the current device, -1 when no CUDA device is usable (callers must refuse to run). */
+int scann_device_sm_count(void);
+int scann_device_cc(void);
+
+/* ---- batch plan ---------------------------------------------------------------------------
+ * Replaces the mask / index bookkeeping the reference does with dense padded tensors:
+ * gather_shape (scann/layers/custom_layers.py:18-28), the (1-mask)*-1e9 additive mask and the
+ * mask multiply of LocalAttention.call (scann/layers/attention.py:186-187, :206).  Inputs are the
+ * padded arrays of DataIterator.__getitem__ (scann/utils/datagenerator.py:80-101):
+ * neighbor_mask [B,M,N] uint8, neighbors [B,M,N] int32, dist/weight [B,M,N] fp32.
+ * Outputs: cnt[R], rowptr[R], tile_a0/tile_a1[tile_cap] (atom range of each tile), ntiles[1],
+ * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*128].  scratch: >= 2*ceil(R/128) int32. */
+int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
+                     const float* weight, int B, int M, int N, int tile_cap, int32_t* cnt, int32_t* rowptr,
+                     int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles, int32_t* pair_c, int32_t* pair_j,
+                     int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* scratch, int scratch_len,
+                     int32_t* status, void* stream);
+
+/* ---- input embedding: Embedding + (extra_embed) + dense_embed swish -----------------------
+ * scann/models/scann_model.py:361-374.  ring may be NULL (use_ring False). t0 (pre-activation,
+ * saved for backward) may be NULL. */
+int scann_embed_forward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
+                        const float* Wr, const float* br, const float* We, const float* be, float* t0, float* x0,
+                        int32_t* status, void* stream);
+/* Gradients are ACCUMULATED into d_emb, dWr, dbr, dWe, dbe.  G_ws: (n_atoms+3)*128 floats. */
+int scann_embed_backward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
+                         const float* Wr, const float* br, const float* We, const float* t0, const float* dx0,
+                         float* G_ws, float* d_emb, float* dWr, float* dbr, float* dWe, float* dbe, void* stream);
+
+/* ---- geometry initialisation: GaussianExpansion x2 + neighbor_d/neighbor_w Dense + Multiply --
+ * scann/layers/custom_layers.py:55-65, scann/models/scann_model.py:378-389. */
+int scann_geom_init_forward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+                            const float* pair_w, const float* centers_d, const float* centers_w, const float* Wd,
+                            const float* bd, const float* Ww, const float* bw, float* g0, void* stream);
+int scann_geom_init_backward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+                             const float* pair_w, const float* centers_d, const float* centers_w, const float* Wd,
+                             const float* bd, const float* Ww, const float* bw, const float* dg0, float* dWd,
+                             float* dbd, float* dWw, float* dbw, void* stream);
+
+/* ---- per-atom Dense layers ------------------------------------------------------------------
+ * C[r, nb*128+c] = epi(sum_kb A[kb][r,:] @ W[kb*nblk+nb] + bias[nb] (+ resid)); A/W/bias are HOST
+ * arrays of device pointers.  mode: 0 none, 1 swish (pre_out <- pre-activation), 2 multiply by
+ * swish'(pre_in), 3 LayerNorm(eps 1e-6) (pre_out <- pre-LN value).  Replaces keras Dense /
+ * LayerNormalization calls of LocalAttention (attention.py:95-113,160), ResidualNorm (:25-40),
+ * after_Lc and the GlobalAttention projections (scann_model.py:424-429, attention.py:269-272),
+ * and, with transposed weight blocks, their input gradients. */
+int scann_dense_forward(const float* const* A, int lda, const float* const* W, const float* const* bias, int kblk,
+                        int nblk, int R, float* C, int ldc, int mode, const float* resid, int ldres,
+                        const float* pre_in, float* pre_out, const float* gamma, const float* beta, void* stream);
+/* dW[kb*nblk+nb] += A[kb]^T @ G[nb] ; db[nb] += colsum(G[nb])  (TF autodiff of Dense). */
+int scann_dense_wgrad(const float* const* A, int lda, const float* const* G, int ldg, int kblk, int nblk, int R,
+                      float* const* dW, float* const* db, void* stream);
+/* LayerNormalization backward; dv2 (row stride ld2) optionally receives a second copy of dv. */
+int scann_layernorm_backward(const float* dy, const float* v, const float* gamma, int R, float* dv, float* dv2,
+                             int ld2, float* dgamma, float* dbeta, void* stream);
+/* Atoms with no valid neighbour: context = q, out = LN(q) (attention.py:206-214). */
+int scann_la_nopair_forward(const int32_t* cnt, const float* proj, int R, const float* gamma, const float* beta,
+                            float* ctx_pre, float* out, void* stream);
+/* dst[off..] = transpose(src[off..]) for each listed 128x128 block (offsets: device int32). */
+int scann_transpose_blocks(const float* src, float* dst, const int32_t* offsets, int nblocks, void* stream);
+
+/* ---- local attention (the hot kernel) ---------------------------------------------------------
+ * LocalAttention.call, g_update=True, v_proj=False, kq_proj=True (scann/layers/attention.py:118-216).
+ * proj = [x@W1+bf | x@W3 | x@Wq+bq] ([R,384]); W2 = rows 128..255 of filter_geo/kernel.
+ * Outputs: g_out (geometry'), out = LN(context) [R,128], ctx_pre (nullable, pre-LN context),
+ * attn (nullable) [rows,8] softmax weights.  grid: number of CTAs (<= SM count is sensible). */
+int scann_la_forward(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                     const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
+                     const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
+                     const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
+                     const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, void* stream);
+/* Reverse-mode of the above (TF autodiff inside keras fit, scann_model.py:232-241).  d_ctx is the
+ * gradient w.r.t. the pre-LN context; dq/s_pre are written for atoms with pairs, t_scatter /
+ * dx_scatter are accumulated with atomics (pre-zero them); wpart: grid*2*128*128 floats. */
+int scann_la_backward(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                      const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
+                      const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
+                      const float* W2T, const float* WkT, const float* bk, const float* gamma_g,
+                      const float* beta_g, const float* d_ctx, const float* dg_up, float* dg_out, float* dq,
+                      float* s_pre, float* t_scatter, float* dx_scatter, float* wpart, float* dgamma_g,
+                      float* dbeta_g, float* dbk, void* stream);
+/* dWk += sum_cta wpart[cta][0] ; dW2 += sum_cta wpart[cta][1]  (per-CTA partial weight gradients). */
+int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2, void* stream);
+
+/* ---- global attention + property head ---------------------------------------------------------
+ * GlobalAttention.call (scann/layers/attention.py:267-318) + bf_property / predict_property / mrelu
+ * (scann/models/scann_model.py:437-447, scann/layers/custom_layers.py:6-15).  qk = [q | k] [R,256].
+ * Outputs ga [R] (ga_score), y [B]; ctx_out / tb_out [B,128] nullable (saved for backward). */
+int scann_ga_head_forward(const float* qk, const uint8_t* atom_mask, int B, int M, int norm, const float* Wb,
+                          const float* bb, const float* wp, const float* bp, int mrelu, float* ga, float* y,
+                          float* ctx_out, float* tb_out, void* stream);
+int scann_ga_head_backward(const float* qk, const uint8_t* atom_mask, int B, int M, int norm, const float* WbT,
+                           const float* wp, const float* tb, const float* dy, float* d_qk, float* d_tb, float* dwp,
+                           float* dbp, void* stream);
+
+/* ---- loss and optimiser -----------------------------------------------------------------------
+ * root_mean_squared_error (scann/layers/losses.py:5-6): dy_b = y_b - t_b, sse[0] += sum err^2,
+ * sse[1] += sum |err|; the 1/(B*RMSE) factor is applied in scann_adam_step after the gradient
+ * all-reduce.  Adam(lr, decay=1e-5) + l2(1e-4) regulariser gradient (scann_model.py:212). */
+int scann_rmse_prepare(const float* y, const float* target, int B, float* dy, float* sse, void* stream);
+int scann_adam_step(float* params, const float* grads, float* m, float* v, const float* l2mask, int n,
+                    const float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream);
+int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch, float l2,
+                     float* out3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -33,7 +33,8 @@ PROTOTYPES = {
     "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
-    "scann_la_backward": (ci, [ci] + [vp] * 30 + [vp]),
+    "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
+    "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),

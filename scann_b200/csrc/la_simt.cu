@@ -570,8 +570,7 @@ extern "C" int scann_la_backward(int grid, const int32_t* ntiles, const int32_t*
                                  const float* W2, const float* Wk, const float* W2T, const float* WkT, const float* bk,
                                  const float* gamma_g, const float* beta_g, const float* d_ctx, const float* dg_up,
                                  float* dg_out, float* dq, float* s_pre, float* t_scatter, float* dx_scatter,
-                                 float* wpart, float* dWk, float* dW2, float* dgamma_g, float* dbeta_g, float* dbk,
-                                 void* stream) {
+                                 float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(la_bwd_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -584,7 +583,13 @@ extern "C" int scann_la_backward(int grid, const int32_t* ntiles, const int32_t*
                 gamma_g, beta_g, d_ctx, dg_up, dg_out, dq, s_pre, t_scatter, dx_scatter, wpart,
                 dgamma_g, dbeta_g, dbk};
     la_bwd_simt_kernel<<<grid, LA_THREADS, LA_BWD_SMEM, (cudaStream_t)stream>>>(a);
+    return scann_check_launch("scann_la_backward");
+}
+
+// dWk += sum over CTAs of wpart[cta][0], dW2 += sum of wpart[cta][1]; `grid` as in scann_la_backward.
+extern "C" int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2,
+                                     void* stream) {
     la_wpart_reduce_kernel<<<(2 * SCANN_D * SCANN_D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wpart, ntiles, grid,
                                                                                                dWk, dW2);
-    return scann_check_launch("scann_la_backward");
+    return scann_check_launch("scann_la_wpart_reduce");
 }

@@ -88,8 +88,29 @@ class Engine:
         self._pinned: Dict[Tuple, dict] = {}
         self.la_grid = self.sm_count
         self.launches = 0
+        self.prof: Optional[dict] = None
 
     # ------------------------------------------------------------------ helpers
+    def _ev(self, name: str, begin: bool) -> None:
+        """CUDA-event bracket around one kernel launch (only when ``self.prof`` is a dict)."""
+        if self.prof is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        if begin:
+            self.prof.setdefault(name, []).append([ev, None])
+        else:
+            self.prof[name][-1][1] = ev
+
+    def prof_summary(self) -> Dict[str, Tuple[int, float]]:
+        """name -> (launches, mean milliseconds); call after a synchronize."""
+        out = {}
+        for k, evs in (self.prof or {}).items():
+            ms = [a.elapsed_time(b) for a, b in evs if b is not None]
+            if ms:
+                out[k] = (len(ms), float(np.mean(ms)))
+        return out
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -292,12 +313,14 @@ class Engine:
             if attn_out is not None:
                 attn = torch.zeros(b.tile_cap * TILE, 8, dtype=torch.float32, device=self.device)
                 attn_out.append(attn)
+            self._ev("la_forward", True)
             check(lib.scann_la_forward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                                        _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),
                                        self.w(fg, D * D), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                                        self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
                                        self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
                                        _p(g_out), _p(ctxpre), _p(out), _p(attn), st), "la_forward")
+            self._ev("la_forward", False)
             self.launches += 2
             if sp.use_attn_norm:
                 # ResidualNorm: LN(h + Dense(swish(Dense(h))))  (attention.py:25-40)
@@ -377,15 +400,19 @@ class Engine:
             ws["scat"].zero_()
             s_pre, t_sc, dx_sc = ws["scat"][0], ws["scat"][1], ws["scat"][2]
             dg_out = ws["dg"][l % 2]
+            self._ev("la_backward", True)
             check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                                         _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
                                         _p(ws["g"][l]), self.w(fg, D * D), self.w(f"{la}/key/kernel"),
                                         self.wT(fg, D * D), self.wT(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                                         self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
                                         _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(ws["dq"]), _p(s_pre), _p(t_sc),
-                                        _p(dx_sc), _p(ws["wpart"]), self.gw(f"{la}/key/kernel"), self.gw(fg, D * D),
+                                        _p(dx_sc), _p(ws["wpart"]),
                                         self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
                                         self.gw(f"{la}/key/bias"), st), "la_backward")
+            self._ev("la_backward", False)
+            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, self.gw(f"{la}/key/kernel"),
+                                            self.gw(fg, D * D), st), "la_wpart_reduce")
             self.launches += 4
             self._wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(ws["dq"])], D, 1, 3, R,
                         [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],

@@ -1,0 +1,233 @@
+"""Drop-in surface of the reference for the accelerated path.
+
+``SCANN(config, pretrained=..., mode=...)`` mirrors scann/models/scann_model.py:42-96 and
+``SCANN.model`` mirrors the subset of ``tf.keras.Model`` the reference calls:
+``predict`` (:266, :316), ``compile`` (:210-214), ``fit`` (:232-241), ``get_layer`` (:81),
+``summary`` (:324, :451) plus ``train_on_batch`` / ``save_weights`` / ``load_weights``.
+Arithmetic runs in the sm_100a kernels behind ``libscann_b200.so``; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Dict, Iterable, Optional
+
+import numpy as np
+import torch
+
+from .config import ModelSpec, fill_cli_defaults, model_spec
+from .engine import Engine
+from .params import ParamLayout
+
+
+# --------------------------------------------------------------------------- lr schedules
+class CosineDecay:
+    """tf.keras.optimizers.schedules.CosineDecay(lr, decay_steps, alpha) (scann_model.py:203-208)."""
+
+    def __init__(self, initial_learning_rate: float, decay_steps: float, alpha: float = 0.0):
+        self.lr0, self.decay_steps, self.alpha = float(initial_learning_rate), float(decay_steps), float(alpha)
+
+    def __call__(self, step: int) -> float:
+        s = min(float(step), self.decay_steps)
+        cos = 0.5 * (1.0 + math.cos(math.pi * s / self.decay_steps))
+        return self.lr0 * ((1.0 - self.alpha) * cos + self.alpha)
+
+
+class History:
+    def __init__(self):
+        self.history: Dict[str, list] = {}
+
+    def add(self, key: str, v: float) -> None:
+        self.history.setdefault(key, []).append(float(v))
+
+
+# --------------------------------------------------------------------------- keras-like model
+class ScannKerasModel:
+    """What ``SCANN.model`` exposes.  ``infer=True`` is the re-wrapped model of
+    scann_model.py:79-83 whose ``predict`` returns ``[target, ga_score]``."""
+
+    input_names = ["atomic", "atom_mask", "neighbors", "neighbor_mask", "neighbor_weight", "neighbor_distance"]
+
+    def __init__(self, spec: ModelSpec, arena: Optional[np.ndarray] = None, infer: bool = False, seed: int = 1,
+                 device: Optional[torch.device] = None):
+        self.spec = spec
+        self.infer = infer
+        self.engine = Engine(spec, arena, device=device, seed=seed)
+        self.layout: ParamLayout = self.engine.layout
+        self.lr = 1e-3
+        self.allreduce = None
+        self.world_size = 1
+        self._y_host = None
+        self.last_e2e_bytes = (0, 0)
+
+    # ---- inference -------------------------------------------------------------------------
+    def predict(self, inputs: Dict[str, object], batch_size: Optional[int] = None, verbose: int = 0):
+        """Keras ``Model.predict``: numpy in, numpy out.  Keras would split the batch into
+        sub-batches of 32; structures are independent so one pass gives identical results."""
+        eng = self.engine
+        b = eng.load_batch(inputs)
+        y, ga = eng.forward(b, training=False)
+        y_h = y.cpu().numpy().reshape(b.B, 1)          # synchronises the stream
+        eng.check_status()
+        self.last_e2e_bytes = (getattr(b, "h2d_bytes", 0), y.numel() * 4)
+        if self.infer:
+            ga_h = ga.cpu().numpy().reshape(b.B, b.M, 1)
+            self.last_e2e_bytes = (self.last_e2e_bytes[0], self.last_e2e_bytes[1] + ga.numel() * 4)
+            return [y_h, ga_h]
+        return y_h
+
+    def __call__(self, inputs, training: bool = False):
+        return self.predict(inputs)
+
+    # ---- training --------------------------------------------------------------------------
+    def compile(self, loss=None, optimizer=None, metrics=None, learning_rate=None):
+        """``compile(loss=root_mean_squared_error, optimizer=Adam(lr, decay=1e-5), metrics=[...])``
+        (scann_model.py:210-214).  The loss is fixed to RMSE + l2 terms, the optimiser to the
+        Keras-2.10 Adam with decay=1e-5; ``optimizer`` / ``learning_rate`` may be a float or a schedule."""
+        lr = learning_rate if learning_rate is not None else optimizer
+        if lr is not None:
+            self.lr = lr
+
+    def _lr_now(self) -> float:
+        return float(self.lr(self.engine.step_count)) if callable(self.lr) else float(self.lr)
+
+    def train_on_batch(self, inputs: Dict[str, object], y_true, return_dict: bool = False):
+        """One Keras ``train_step``: returns the loss (RMSE + l2 penalties) of the batch."""
+        eng = self.engine
+        b = eng.load_batch(inputs)
+        t = torch.as_tensor(np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1)))
+        t = t.pin_memory().to(eng.device, non_blocking=True)
+        if t.numel() != b.B:
+            raise ValueError("target must have one value per structure")
+        batch_global = b.B * self.world_size
+        eng.train_step(b, t, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global)
+        out = eng.loss_value(batch_global).cpu().numpy()       # synchronises the stream
+        eng.check_status()
+        self.last_e2e_bytes = (getattr(b, "h2d_bytes", 0) + t.numel() * 4, 16)
+        if return_dict:
+            return {"loss": float(out[0]), "rmse": float(out[1]), "mae": float(out[2])}
+        return float(out[0])
+
+    def evaluate_batch(self, inputs, y_true) -> Dict[str, float]:
+        y = self.predict(inputs)
+        y = (y[0] if isinstance(y, list) else y).reshape(-1)
+        t = np.asarray(y_true, np.float32).reshape(-1)
+        return {"mae": float(np.abs(y - t).mean()), "rmse": float(np.sqrt(((y - t) ** 2).mean()))}
+
+    def fit(self, x, epochs: int = 1, validation_data=None, callbacks=None, verbose: int = 2, shuffle: bool = False,
+            **_ignored) -> History:
+        """``model.fit(trainIter, epochs, validation_data=validIter, ...)`` (scann_model.py:232-241) over a
+        ``Sequence``-like iterator (``len``, ``__getitem__`` -> (inputs, target), ``on_epoch_end``)."""
+        hist = History()
+        for ep in range(epochs):
+            losses, maes = [], []
+            for i in range(len(x)):
+                inputs, target = x[i]
+                out = self.train_on_batch(inputs, target, return_dict=True)
+                losses.append(out["loss"])
+                maes.append(out["mae"])
+            hist.add("loss", float(np.mean(losses)))
+            hist.add("mae", float(np.mean(maes)))
+            if validation_data is not None:
+                v = [self.evaluate_batch(*validation_data[i]) for i in range(len(validation_data))]
+                hist.add("val_mae", float(np.mean([m["mae"] for m in v])))
+            if hasattr(x, "on_epoch_end"):
+                x.on_epoch_end()
+            if verbose:
+                print(f"Epoch {ep + 1}/{epochs} - " + " - ".join(f"{k}: {vals[-1]:.6f}" for k, vals in hist.history.items()))
+            for cb in callbacks or []:
+                if hasattr(cb, "on_epoch_end"):
+                    cb.on_epoch_end(ep, {k: vals[-1] for k, vals in hist.history.items()})
+        return hist
+
+    # ---- weights ---------------------------------------------------------------------------
+    def get_weights(self):
+        """Weights in the reference's Keras order (see params.ParamLayout)."""
+        d = self.layout.to_dict(self.engine.get_params())
+        return [d[e.name].copy() for e in self.layout]
+
+    def set_weights(self, weights: Iterable[np.ndarray]) -> None:
+        weights = list(weights)
+        if len(weights) != len(self.layout.entries):
+            raise ValueError(f"expected {len(self.layout.entries)} arrays, got {len(weights)}")
+        self.engine.set_params(self.layout.from_dict({e.name: w for e, w in zip(self.layout, weights)}))
+
+    def save_weights(self, path: str) -> None:
+        d = self.layout.to_dict(self.engine.get_params())
+        np.savez(path, **{k.replace("/", "__"): v for k, v in d.items()})
+
+    def load_weights(self, path: str) -> None:
+        with np.load(path) as z:
+            d = {k.replace("__", "/"): z[k] for k in z.files}
+        self.engine.set_params(self.layout.from_dict(d))
+
+    def count_params(self) -> int:
+        return self.layout.n_params
+
+    def summary(self) -> None:
+        print(f"Model: SCANN ({'SCANN+' if self.spec.g_update else 'SCANN'}), {self.spec.n_attention} local-attention layers")
+        for e in self.layout:
+            print(f"  {e.name:50s} {str(e.shape):14s} {e.size}")
+        print(f"Total params: {self.layout.n_params}")
+
+    def get_layer(self, name: str):
+        if name != "global_attention":
+            raise ValueError(f"No such layer: {name}")
+        return self
+
+
+def create_model(config: dict, seed: int = 1, infer: bool = False, arena: Optional[np.ndarray] = None) -> ScannKerasModel:
+    """Counterpart of ``create_model(config)`` (scann_model.py:329-453)."""
+    return ScannKerasModel(model_spec(config), arena=arena, infer=infer, seed=seed)
+
+
+class SCANN:
+    """Same constructor and methods as the reference facade (scann_model.py:42-96, 315-319)."""
+
+    def __init__(self, config=None, pretrained: str = "", mode: str = "train"):
+        self.config = config
+        self.model = None
+        self.mean, self.std = 0, 1
+        if "target_mean" in self.config["hyper"]:                       # scann_model.py:66-68
+            self.mean = float(self.config["hyper"]["target_mean"])
+            self.std = float(self.config["hyper"]["target_std"])
+        if mode in ("train", "eval"):                                   # :70-77
+            self.model = create_model(self.config)
+            if pretrained:
+                print("load pretrained model from ", pretrained, "\n")
+                self.model.load_weights(pretrained)
+                self.config["hyper"]["pretrained"] = pretrained
+        else:                                                           # :78-83
+            if not pretrained:
+                raise ValueError("mode='infer' needs pretrained weights (the reference calls load_model(pretrained))")
+            self.model = create_model(self.config, infer=True)
+            self.model.load_weights(pretrained)
+
+    @classmethod
+    def load_model_infer(cls, path: str, config: dict):
+        m = create_model(config, infer=True)
+        m.load_weights(path)
+        return m
+
+    @classmethod
+    def load_model(cls, path: str, config: dict):
+        m = create_model(config)
+        m.load_weights(path)
+        return m
+
+    def predict_data(self, ip):                                         # :315-319
+        out = self.model.predict(ip)
+        if len(out) == 2:
+            return out[0] * self.std + self.mean, out[1]
+        return out * self.std + self.mean
+
+    def train_iterators(self, train_iter, valid_iter=None, epochs: int = 1000, callbacks=None):
+        """``train`` (scann_model.py:199-241) minus dataset loading: lr schedule + compile + fit."""
+        hy = self.config["hyper"]
+        if hy.get("scheduler") == "sgdr":
+            lr = hy["lr"]
+        else:
+            lr = CosineDecay(hy["lr"], 0.5 * len(train_iter) * epochs, alpha=hy["min_lr"] / hy["lr"])
+        self.model.compile(optimizer=lr)
+        self.hist = self.model.fit(train_iter, epochs=epochs, validation_data=valid_iter, callbacks=callbacks)
+        return self.hist

@@ -1,0 +1,357 @@
+"""GPU parity tests: the sm_100a path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): gathers and masks bit-exact; fp32 outputs and ga_score
+within 1e-5, gradients within 1e-4 -- both measured as max|err| / max|ref| against the fp64
+oracle (an elementwise |err|/|ref| bound fails for exact fp32 arithmetic as well, SURVEY.md
+appendix B)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import scann_oracle as O                               # noqa: E402
+from scann_b200.config import model_spec                           # noqa: E402
+from scann_b200.configs import get_config                          # noqa: E402
+from scann_b200.params import ParamLayout                          # noqa: E402
+from scann_b200.synth import SHAPES, count_valid, make_batch       # noqa: E402
+from tests.golden.make_golden import CASES, build_case, oracle_kwargs   # noqa: E402
+
+TOL_OUT = 1e-5
+TOL_GRAD = 1e-4
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def engine_for(spec, arena):
+    from scann_b200.engine import Engine
+    return Engine(spec, arena)
+
+
+def run_forward(spec, arena, inputs):
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    y, ga = eng.forward(b)
+    torch.cuda.synchronize()
+    eng.check_status()
+    return eng, b, y.cpu().numpy(), ga.cpu().numpy().reshape(b.B, b.M)
+
+
+def small(cfg_name="qm9", L=2, seed=2):
+    cfg = get_config(cfg_name)
+    cfg["model"]["n_attention"] = L
+    spec = model_spec(cfg)
+    lay = ParamLayout(spec)
+    return spec, lay, lay.randomize_arena(seed)
+
+
+def test_native_library_is_loaded_on_gpu():
+    from scann_b200 import _abi
+    assert _abi.require_gpu() >= 100
+    assert _abi.lib.scann_device_cc() >= 100
+
+
+@pytest.mark.parametrize("shape,B", [("qm9", 16), ("mp2018", 6), ("fullerene", 3)])
+def test_plan_gathers_and_masks_bit_exact(shape, B):
+    spec, lay, arena = small(shape if shape != "fullerene" else "fullerene")
+    inputs, _ = make_batch(shape, 1, B=B)
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    torch.cuda.synchronize()
+    eng.check_status()
+    pc, pj, slot = b.pair_c.cpu().numpy(), b.pair_j.cpu().numpy(), b.pair_slot.cpu().numpy()
+    nt = int(b.ntiles.item())
+    valid = pc >= 0
+    assert not valid[nt * 128:].any()
+    nm = inputs["neighbor_mask"].reshape(-1)
+    assert valid.sum() == nm.sum()
+    assert np.array_equal(np.sort(slot[valid]), np.flatnonzero(nm))           # every valid slot exactly once
+    flat_j = (np.arange(b.B)[:, None, None] * b.M + inputs["neighbors"]).reshape(-1)
+    assert np.array_equal(pj[valid], flat_j[slot[valid]])                      # gather indices bit-exact
+    assert np.array_equal(pc[valid], slot[valid] // b.N)
+    assert np.array_equal(b.pair_d.cpu().numpy()[valid], inputs["neighbor_distance"].reshape(-1)[slot[valid]])
+    assert np.array_equal(b.pair_w.cpu().numpy()[valid], inputs["neighbor_weight"].reshape(-1)[slot[valid]])
+    cnt = b.cnt.cpu().numpy()
+    assert np.array_equal(cnt, inputs["neighbor_mask"].reshape(b.R, -1).sum(1))
+    # pairs of one atom are contiguous, in slot order, inside one tile
+    rp = b.rowptr.cpu().numpy()
+    for r in np.flatnonzero(cnt)[:200]:
+        rows = np.arange(rp[r], rp[r] + cnt[r])
+        assert rows[0] // 128 == rows[-1] // 128
+        assert (pc[rows] == r).all() and (np.diff(slot[rows]) > 0).all()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_golden(name):
+    cfg, spec, lay, arena, inputs, target = build_case(name)
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    _, b, y, ga = run_forward(spec, arena, inputs)
+    assert rel(y, z["y"].ravel()) <= TOL_OUT
+    assert rel(ga, z["ga"][..., 0]) <= TOL_OUT
+    assert (ga[~inputs["atom_mask"][..., 0]] == 0).all()
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_gradients_match_golden(name):
+    cfg, spec, lay, arena, inputs, target = build_case(name)
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = eng.grad_out.cpu().numpy().astype(np.float64)
+    loss = eng.loss_value(b.B).cpu().numpy()
+    assert abs(loss[0] - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    assert rel(g[z["grad_idx"]], z["grad_sample"]) <= TOL_GRAD
+    assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
+
+
+@pytest.mark.parametrize("shape,cfg_name,B,L", [("qm9", "qm9", 24, 7), ("mp2018", "mp2018", 8, 4)])
+def test_per_tensor_gradient_parity_against_oracle(shape, cfg_name, B, L):
+    spec, lay, arena = small(cfg_name, L=L, seed=5)
+    inputs, target = make_batch(shape, 3, B=B)
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, y_ref, ga_ref, grads = O.loss_and_grads(w, inputs, target, l2n, **oracle_kwargs(spec))
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        # per-tensor bound, with a floor for tensors whose gradient is tiny compared to the model's
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+    ws = eng._workspace(b, True)
+    assert rel(ws["y"].cpu().numpy(), y_ref.ravel()) <= TOL_OUT
+
+
+def test_edge_cases_isolated_atoms_duplicates_self_neighbours():
+    """Atoms without any valid neighbour, duplicate and self neighbours (periodic images), a
+    non-prefix mask pattern and an atom using every slot."""
+    spec, lay, arena = small("mp2018", L=3, seed=6)
+    inputs, target = make_batch("mp2018", 9, B=4)
+    nm = inputs["neighbor_mask"]
+    nm[0, 1, :] = False                                   # isolated atom
+    nm[1, 0, ::2] = False                                 # holes in the slot pattern
+    inputs["neighbors"][2, 0, :] = 0                      # all neighbours = the same atom (itself)
+    inputs["neighbors"] = np.where(nm, inputs["neighbors"], 0).astype(np.int32)
+    inputs["neighbor_weight"] = np.where(nm, inputs["neighbor_weight"], 0).astype(np.float32)
+    inputs["neighbor_distance"] = np.where(nm, inputs["neighbor_distance"], 0).astype(np.float32)
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, y_ref, ga_ref, grads = O.loss_and_grads(w, inputs, target, l2n, **oracle_kwargs(spec))
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    ws = eng._workspace(b, True)
+    assert rel(ws["y"].cpu().numpy(), y_ref.ravel()) <= TOL_OUT
+    assert rel(ws["ga"].cpu().numpy(), ga_ref.ravel()) <= TOL_OUT
+    g = eng.grad_out.cpu().numpy().astype(np.float64)
+    ref = np.zeros(lay.total)
+    for e in lay:
+        ref[e.offset:e.offset + e.size] = grads[e.name].reshape(-1)
+    assert rel(g, ref) <= TOL_GRAD
+
+
+def test_single_atom_structure_nan_like_reference():
+    spec, lay, arena = small("qm9", L=2)
+    inputs, _ = make_batch("qm9", 7, B=3)
+    inputs["atomic"][0, 1:] = 0
+    inputs["atom_mask"] = (inputs["atomic"] != 0)[..., None]
+    inputs["neighbor_mask"][0, 1:] = False
+    inputs["neighbors"][0] = 0
+    y_ref, ga_ref = O.predict(lay.to_dict(arena), inputs, **oracle_kwargs(spec))
+    _, b, y, ga = run_forward(spec, arena, inputs)
+    assert np.isnan(y_ref[0]).all() and np.isnan(y[0])
+    assert np.isnan(ga[0]).all()
+    assert rel(y[1:], y_ref[1:].ravel()) <= TOL_OUT
+
+
+def test_ga_norm_false_fullerene_config():
+    spec, lay, arena = small("fullerene", L=2, seed=8)
+    assert not spec.use_ga_norm
+    inputs, _ = make_batch("fullerene", 2, B=3)
+    y_ref, ga_ref = O.predict(lay.to_dict(arena), inputs, **oracle_kwargs(spec))
+    _, b, y, ga = run_forward(spec, arena, inputs)
+    assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= TOL_OUT
+
+
+def test_malformed_input_is_reported():
+    from scann_b200._abi import ScannAbiError
+    spec, lay, arena = small("qm9", L=1)
+    inputs, _ = make_batch("qm9", 1, B=2)
+    inputs["neighbors"][0, 0, 0] = 29 + 5                 # out of [0, M) on a valid slot
+    inputs["neighbor_mask"][0, 0, 0] = True
+    eng = engine_for(spec, arena)
+    eng.load_batch(inputs)
+    torch.cuda.synchronize()
+    with pytest.raises(ScannAbiError):
+        eng.check_status()
+
+
+# ----------------------------------------------------------------------------- full-size properties
+@pytest.mark.parametrize("shape", ["qm9", "mp2018"])
+def test_full_size_properties(shape):
+    """At BASELINE.json's full batch sizes: sum(ga)=1, padded atoms exactly 0, batch-split and
+    padding invariance (size-independent properties; the oracle is too slow here)."""
+    cfg = get_config(shape)
+    spec = model_spec(cfg)
+    lay = ParamLayout(spec)
+    arena = lay.randomize_arena(11)
+    inputs, _ = make_batch(shape, 5)
+    eng, b, y, ga = run_forward(spec, arena, inputs)
+    am = inputs["atom_mask"][..., 0]
+    assert np.isfinite(y).all()
+    np.testing.assert_allclose(ga.sum(1), 1.0, rtol=2e-6)
+    assert (ga[~am] == 0).all()
+    # batch split: second half alone
+    h = b.B // 2
+    b2 = eng.load_batch({k: v[h:] for k, v in inputs.items()})
+    y2, ga2 = eng.forward(b2)
+    torch.cuda.synchronize()
+    assert rel(y2.cpu().numpy(), y[h:]) <= 2e-6           # tiles differ, so summation order differs slightly
+    # padding invariance: two more padded atoms and neighbour slots
+    pad = {}
+    N = inputs["neighbors"].shape[2]
+    for k, v in inputs.items():
+        if v.ndim == 3 and v.shape[2] == N:
+            pad[k] = np.pad(v, ((0, 0), (0, 2), (0, 2)))
+        elif v.ndim == 3:
+            pad[k] = np.pad(v, ((0, 0), (0, 2), (0, 0)))
+        else:
+            pad[k] = np.pad(v, ((0, 0), (0, 2)))
+    b3 = eng.load_batch(pad)
+    y3, ga3 = eng.forward(b3)
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert np.array_equal(y3.cpu().numpy(), y)            # same pairs, same tiles -> bitwise identical
+    assert np.array_equal(ga3.cpu().numpy().reshape(b.B, -1)[:, :b.M], ga)
+
+
+# ----------------------------------------------------------------------------- optimiser and public API
+def test_adam_step_matches_oracle():
+    spec, lay, arena = small("qm9", L=2, seed=9)
+    inputs, target = make_batch("qm9", 4, B=8)
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    m = {k: np.zeros_like(v, np.float64) for k, v in w.items()}
+    v = {k: np.zeros_like(x, np.float64) for k, x in w.items()}
+    w64 = {k: x.astype(np.float64) for k, x in w.items()}
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    t = torch.from_numpy(target).cuda()
+    for step in (1, 2, 3):
+        _, _, _, g = O.loss_and_grads(w64, inputs, target, l2n, **oracle_kwargs(spec))
+        for k in w64:
+            w64[k], m[k], v[k] = O.adam_legacy_step(w64[k], g[k], m[k], v[k], step, 5e-4)
+        eng.train_step(b, t, lr=5e-4)
+    torch.cuda.synchronize()
+    got = lay.to_dict(eng.get_params())
+    for e in lay:
+        # three Adam steps move each weight by ~1.5e-3; compare the MOVEMENT, not the weight
+        moved_ref = w64[e.name] - w[e.name]
+        moved = got[e.name].astype(np.float64) - w[e.name]
+        assert np.abs(moved - moved_ref).max() <= 2e-2 * max(np.abs(moved_ref).max(), 1e-6), e.name
+
+
+def test_public_api_predict_and_train(tmp_path):
+    """SCANN(config, pretrained, mode='infer').model.predict(inputs) -> (target[B,1], ga_score[B,M,1])."""
+    from scann.models import SCANN
+    cfg = get_config("qm9")
+    cfg["model"]["n_attention"] = 2
+    cfg["hyper"]["target_mean"], cfg["hyper"]["target_std"] = "0.5", "2.0"
+    spec = model_spec(cfg)
+    lay = ParamLayout(spec)
+    trainer = SCANN(cfg, mode="train")
+    inputs, target = make_batch("qm9", 2, B=8)
+    l0 = trainer.model.train_on_batch(inputs, target)
+    for _ in range(5):
+        l1 = trainer.model.train_on_batch(inputs, target)
+    assert np.isfinite(l0) and l1 < l0
+    path = str(tmp_path / "weights.npz")
+    trainer.model.save_weights(path)
+    infer = SCANN(cfg, pretrained=path, mode="infer")
+    out = infer.model.predict(inputs)
+    assert len(out) == 2 and out[0].shape == (8, 1) and out[1].shape == (8, 29, 1)
+    w = lay.to_dict(trainer.model.engine.get_params())
+    y_ref, ga_ref = O.predict(w, inputs, **oracle_kwargs(spec))
+    assert rel(out[0], y_ref) <= TOL_OUT and rel(out[1], ga_ref) <= TOL_OUT
+    yd, gad = infer.predict_data(inputs)
+    np.testing.assert_allclose(yd, out[0] * 2.0 + 0.5, rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------- layer-level drop-ins
+def test_local_attention_layer_matches_reference_layer():
+    from scann.layers import LocalAttention, gather_shape
+    rng = np.random.default_rng(0)
+    B, M, N = 3, 11, 7
+    x = rng.standard_normal((B, M, 128)).astype(np.float32)
+    geom = rng.standard_normal((B, M, N, 128)).astype(np.float32)
+    nbrs = rng.integers(0, M, (B, M, N)).astype(np.int32)
+    mask = rng.random((B, M, N)) > 0.35
+    mask[0, 0] = False                                     # an atom without neighbours
+    names = ["query/kernel", "query/bias", "key/kernel", "key/bias", "filter_geo/kernel", "filter_geo/bias",
+             "layer_norm/gamma", "layer_norm/beta", "layer_norm_g/gamma", "layer_norm_g/beta"]
+    shapes = [(128, 128), (128,), (128, 128), (128,), (384, 128), (128,), (128,), (128,), (128,), (128,)]
+    ws = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in shapes]
+    ws[6] += 1
+    ws[8] += 1
+    layer = LocalAttention(v_proj=False, kq_proj=True, dim=128, num_head=8, activation="swish", dropout=False,
+                           g_update=True)
+    layer.set_weights(ws)
+    idx = gather_shape(nbrs)
+    attn, ctx, g_new = layer(x, idx, geom, mask.astype(np.float32))
+    w = {f"la/{n}": torch.tensor(v, dtype=torch.float64) for n, v in zip(names, ws)}
+    a_ref, c_ref, g_ref = O.local_attention(w, "la", torch.tensor(x, dtype=torch.float64),
+                                            O.gather_shape(torch.tensor(nbrs.astype(np.int64))),
+                                            torch.tensor(geom, dtype=torch.float64),
+                                            torch.tensor(mask.astype(np.float64)), g_update=True)
+    assert rel(ctx.cpu().numpy(), c_ref.numpy()) <= TOL_OUT
+    assert rel(attn.cpu().numpy(), a_ref.numpy()) <= TOL_OUT
+    g_ref = g_ref.numpy()
+    assert rel(g_new.cpu().numpy()[mask], g_ref[mask]) <= TOL_OUT     # masked slots are don't-care
+    assert layer.get_config()["g_update"] is True
+
+
+def test_global_attention_and_residual_norm_layers():
+    from scann.layers import GlobalAttention, ResidualNorm
+    rng = np.random.default_rng(1)
+    B, M = 4, 13
+    x = rng.standard_normal((B, M, 128)).astype(np.float32)
+    mask = (rng.random((B, M, 1)) > 0.3).astype(np.float32)
+    mask[:, :2] = 1
+    for norm in (True, False):
+        ga_l = GlobalAttention(v_proj=False, kq_proj=True, dim=128, norm=norm)
+        ws = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in [(128, 128), (128,), (128, 128), (128,)]]
+        ga_l.set_weights(ws)
+        attn, ctx = ga_l(x, mask)
+        w = {f"ga/{n}": torch.tensor(v, dtype=torch.float64)
+             for n, v in zip(["query/kernel", "query/bias", "key/kernel", "key/bias"], ws)}
+        a_ref, c_ref = O.global_attention(w, "ga", torch.tensor(x, dtype=torch.float64),
+                                          torch.tensor(mask, dtype=torch.float64), norm=norm)
+        assert rel(attn.cpu().numpy(), a_ref.numpy()) <= TOL_OUT
+        assert rel(ctx.cpu().numpy(), c_ref.numpy()) <= TOL_OUT
+    rn = ResidualNorm(128)
+    ws = [(0.1 * rng.standard_normal(s)).astype(np.float32) for s in [(128, 128), (128,), (128, 128), (128,), (128,), (128,)]]
+    ws[4] += 1
+    rn.set_weights(ws)
+    out = rn(x)
+    w = {f"rn/{n}": torch.tensor(v, dtype=torch.float64)
+         for n, v in zip(["dense/kernel", "dense/bias", "dense_1/kernel", "dense_1/bias", "layer_norm/gamma",
+                          "layer_norm/beta"], ws)}
+    ref = O.residual_norm(w, "rn", torch.tensor(x, dtype=torch.float64))
+    assert rel(out.cpu().numpy(), ref.numpy()) <= TOL_OUT
+    assert rn.get_config() == {"dim": 128, "dropout": 0.1}

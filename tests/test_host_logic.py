@@ -1,0 +1,89 @@
+"""CPU tests of the host logic: parameter layout, configs, synthetic batches, lr schedules."""
+import numpy as np
+import pytest
+import yaml
+
+from scann_b200.config import fill_cli_defaults, load_yaml, model_spec
+from scann_b200.configs import CONFIGS, get_config
+from scann_b200.params import ParamLayout
+from scann_b200.synth import SHAPES, count_valid, make_batch
+
+
+@pytest.mark.parametrize("name,expected", [("qm9", 890977), ("mp2018", 1145089), ("fullerene", 890977)])
+def test_param_counts_match_reference_models(name, expected):
+    """Trainable-parameter totals of the reference graphs."""
+    lay = ParamLayout(model_spec(get_config(name)))
+    assert lay.n_params == expected
+    assert all(e.offset % 4 == 0 for e in lay)
+
+
+def test_l2_kernels_are_the_regularised_ones():
+    """5 per LA+ResidualNorm block + after_Lc + GA query/key + bf_property."""
+    spec = model_spec(get_config("qm9"))
+    lay = ParamLayout(spec)
+    l2 = [e.name for e in lay if e.l2]
+    assert len(l2) == 5 * spec.n_attention + 4
+    assert "dense_embed/kernel" not in l2 and "predict_property/kernel" not in l2
+    assert "neighbor_d/kernel" not in l2 and "embed_atom/embeddings" not in l2
+
+
+def test_keras_weight_order_of_local_attention():
+    lay = ParamLayout(model_spec(get_config("qm9")))
+    names = [e.name for e in lay if e.name.startswith("local_attention/")]
+    assert names == ["local_attention/query/kernel", "local_attention/query/bias", "local_attention/key/kernel",
+                     "local_attention/key/bias", "local_attention/filter_geo/kernel",
+                     "local_attention/filter_geo/bias", "local_attention/layer_norm/gamma",
+                     "local_attention/layer_norm/beta", "local_attention/layer_norm_g/gamma",
+                     "local_attention/layer_norm_g/beta"]
+    assert lay["local_attention/filter_geo/kernel"].shape == (384, 128)
+    assert "local_attention_6/key/kernel" in lay and "local_attention_7/key/kernel" not in lay
+
+
+def test_yaml_roundtrip_and_missing_keys(tmp_path):
+    cfg = get_config("qm9")
+    p = tmp_path / "model_qm9.yaml"
+    p.write_text(yaml.safe_dump({"model": {k: v for k, v in cfg["model"].items() if k not in ("feature", "use_drop")},
+                                 "hyper": {k: v for k, v in cfg["hyper"].items() if k not in ("target", "use_ref")}}))
+    raw = load_yaml(str(p))
+    with pytest.raises(KeyError):            # feature/target come from the CLI in the reference (train.py:37-43)
+        model_spec(raw)
+    spec = model_spec(fill_cli_defaults(raw))
+    assert spec.n_attention == 7 and spec.g_update and spec.gaussian_d == 4.0
+    with pytest.raises(KeyError):            # model_ptgp.yaml lacks g_update, as shipped
+        model_spec(get_config("ptgp"))
+
+
+def test_arena_roundtrip():
+    lay = ParamLayout(model_spec(get_config("mp2018")))
+    arena = lay.randomize_arena(5)
+    d = lay.to_dict(arena)
+    assert np.array_equal(lay.from_dict(d), arena)
+    assert abs(d["local_attention_3/layer_norm/gamma"].mean() - 1.0) < 0.2
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_synthetic_batch_layout(shape):
+    inputs, target = make_batch(shape, 0, B=4)
+    s = SHAPES[shape]
+    assert inputs["atomic"].shape == (4, s.M) and inputs["atomic"].dtype == np.int32
+    assert inputs["atom_mask"].shape == (4, s.M, 1) and inputs["atom_mask"].dtype == bool
+    assert inputs["neighbors"].shape == (4, s.M, s.N)
+    nm = inputs["neighbor_mask"]
+    # padded slots are reset to index 0 and carry zero weight/distance (datagenerator.py:82-101)
+    assert (inputs["neighbors"][~nm] == 0).all()
+    assert (inputs["neighbor_weight"][~nm] == 0).all() and (inputs["neighbor_distance"][~nm] == 0).all()
+    # neighbours only point at real atoms of the same structure
+    n_at = inputs["atom_mask"].sum((1, 2))
+    assert (inputs["neighbors"] < n_at[:, None, None]).all()
+    assert not nm[~inputs["atom_mask"][..., 0]].any()
+    A, P = count_valid(inputs)
+    assert A == inputs["atom_mask"].sum() and P == nm.sum() and target.shape == (4,)
+
+
+def test_cosine_decay_matches_keras_formula():
+    from scann_b200.model import CosineDecay
+    sch = CosineDecay(1e-4, 100, alpha=0.5)
+    assert sch(0) == pytest.approx(1e-4)
+    assert sch(100) == pytest.approx(0.5e-4)
+    assert sch(1000) == pytest.approx(0.5e-4)
+    assert sch(50) == pytest.approx(1e-4 * (0.5 * 0.5 + 0.5))
