@@ -43,6 +43,18 @@ def run_forward(spec, arena, inputs):
     return eng, b, y.cpu().numpy(), ga.cpu().numpy().reshape(b.B, b.M)
 
 
+def ga_tolerance(spec, lay, arena, inputs):
+    """1e-5, except for use_ga_norm=False (model_fullerene.yaml): un-normalised scores reach O(100), so
+    the softmax amplifies fp32 rounding of the logits and the REFERENCE's own fp32 arithmetic sits
+    ~4e-5 from fp64 truth (measured with the fp32 oracle).  There the bound is 3x that noise floor."""
+    if spec.use_ga_norm:
+        return TOL_OUT
+    w = lay.to_dict(arena)
+    _, ga64 = O.predict(w, inputs, torch.float64, **oracle_kwargs(spec))
+    _, ga32 = O.predict(w, inputs, torch.float32, **oracle_kwargs(spec))
+    return max(TOL_OUT, 3.0 * rel(ga32, ga64))
+
+
 def small(cfg_name="qm9", L=2, seed=2):
     cfg = get_config(cfg_name)
     cfg["model"]["n_attention"] = L
@@ -93,7 +105,7 @@ def test_forward_matches_golden(name):
     z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
     _, b, y, ga = run_forward(spec, arena, inputs)
     assert rel(y, z["y"].ravel()) <= TOL_OUT
-    assert rel(ga, z["ga"][..., 0]) <= TOL_OUT
+    assert rel(ga, z["ga"][..., 0]) <= ga_tolerance(spec, lay, arena, inputs)
     assert (ga[~inputs["atom_mask"][..., 0]] == 0).all()
 
 
@@ -186,7 +198,7 @@ def test_ga_norm_false_fullerene_config():
     inputs, _ = make_batch("fullerene", 2, B=3)
     y_ref, ga_ref = O.predict(lay.to_dict(arena), inputs, **oracle_kwargs(spec))
     _, b, y, ga = run_forward(spec, arena, inputs)
-    assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= TOL_OUT
+    assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= ga_tolerance(spec, lay, arena, inputs)
 
 
 def test_malformed_input_is_reported():
@@ -320,7 +332,17 @@ def test_local_attention_layer_matches_reference_layer():
                                             torch.tensor(geom, dtype=torch.float64),
                                             torch.tensor(mask.astype(np.float64)), g_update=True)
     assert rel(ctx.cpu().numpy(), c_ref.numpy()) <= TOL_OUT
-    assert rel(attn.cpu().numpy(), a_ref.numpy()) <= TOL_OUT
+    # Rows without a valid slot: in the reference's fp32 arithmetic e + (-1e9) == -1e9 exactly, so the
+    # softmax is uniform 1/N (the fp64 oracle keeps the differences of e; irrelevant, the mask zeroes the row)
+    empty = ~mask.any(-1)                                              # [B,M]
+    a_gpu, a_ref = attn.cpu().numpy(), a_ref.numpy()
+    assert rel(a_gpu.transpose(0, 2, 1, 3)[~empty], a_ref.transpose(0, 2, 1, 3)[~empty]) <= TOL_OUT
+    assert np.array_equal(a_gpu.transpose(0, 2, 1, 3)[empty],
+                          np.full_like(a_gpu.transpose(0, 2, 1, 3)[empty], np.float32(1.0) / N))
+    a32, _, _ = O.local_attention({k: v.float() for k, v in w.items()}, "la", torch.tensor(x),
+                                  O.gather_shape(torch.tensor(nbrs.astype(np.int64))), torch.tensor(geom),
+                                  torch.tensor(mask.astype(np.float32)), g_update=True)
+    assert np.allclose(a32.numpy().transpose(0, 2, 1, 3)[empty], 1.0 / N, rtol=1e-6)   # the fp32 reference agrees
     g_ref = g_ref.numpy()
     assert rel(g_new.cpu().numpy()[mask], g_ref[mask]) <= TOL_OUT     # masked slots are don't-care
     assert layer.get_config()["g_update"] is True
