@@ -139,6 +139,11 @@ int scann_adam_step(float* params, const float* grads, float* m, float* v, const
 int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch, float l2,
                      float* out3, void* stream);
 
+/* ---- diagnostics --------------------------------------------------------------------------------
+ * One 128x128x128 tile product on the tcgen05 tensor cores (self-test of descriptors / layouts).
+ * layout 0: A@W, 1: A^T@W, 2: A@W^T, 3: A@W with A in tensor memory; nprod 1 (TF32) or 3 (3xTF32). */
+int scann_tc_probe(const float* A, const float* W, float* D, int layout, int nprod, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,7 @@ PROTOTYPES = {
     "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_adam_step": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
     "scann_loss_value": (ci, [vp, vp, ci, vp, C.c_float, C.c_float, vp, vp]),
+    "scann_tc_probe": (ci, [vp, vp, vp, ci, ci, vp]),
 }
 
 
