@@ -83,6 +83,11 @@ int scann_geom_init_backward(const int32_t* ntiles, int grid, const int32_t* pai
 int scann_dense_forward(const float* const* A, int lda, const float* const* W, const float* const* bias, int kblk,
                         int nblk, int R, float* C, int ldc, int mode, const float* resid, int ldres,
                         const float* pre_in, float* pre_out, const float* gamma, const float* beta, void* stream);
+/* Same contract on the tcgen05 tensor cores (3xTF32, weights stationary in tensor memory). */
+int scann_dense_forward_tc(const float* const* A, int lda, const float* const* W, const float* const* bias,
+                           int kblk, int nblk, int R, float* C, int ldc, int mode, const float* resid, int ldres,
+                           const float* pre_in, float* pre_out, const float* gamma, const float* beta,
+                           void* stream);
 /* dW[kb*nblk+nb] += A[kb]^T @ G[nb] ; db[nb] += colsum(G[nb])  (TF autodiff of Dense). */
 int scann_dense_wgrad(const float* const* A, int lda, const float* const* G, int ldg, int kblk, int nblk, int R,
                       float* const* dW, float* const* db, void* stream);
@@ -105,6 +110,14 @@ int scann_la_forward(int grid, const int32_t* ntiles, const int32_t* tile_a0, co
                      const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
                      const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
                      const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, void* stream);
+/* Same forward on the tcgen05 tensor cores (3xTF32; two kernels: geometry update, attention).
+ * pre_out / k_out ([rows,128], nullable) save the filter_geo pre-activation and the keys. */
+int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                        const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
+                        const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
+                        const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
+                        const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out,
+                        float* k_out, void* stream);
 /* Reverse-mode of the above (TF autodiff inside keras fit, scann_model.py:232-241).  d_ctx is the
  * gradient w.r.t. the pre-LN context; dq/s_pre are written for atoms with pairs, t_scatter /
  * dx_scatter are accumulated with atomics (pre-zero them); wpart: grid*2*128*128 floats. */

@@ -28,11 +28,13 @@ PROTOTYPES = {
     "scann_geom_init_forward": (ci, [vp, ci] + [vp] * 10 + [vp]),
     "scann_geom_init_backward": (ci, [vp, ci] + [vp] * 14 + [vp]),
     "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
+    "scann_dense_forward_tc": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_wgrad": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp]),
     "scann_layernorm_backward": (ci, [vp, vp, vp, ci, vp, vp, ci, vp, vp, vp]),
     "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
+    "scann_la_forward_tc": (ci, [ci] + [vp] * 23 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),

@@ -1,0 +1,202 @@
+// Per-atom Dense layers on the 5th-generation tensor cores (tcgen05, kind::tf32, 3xTF32).
+//
+//   C[r, nb*128 + c] = epi( sum_kb A_kb[r,:] @ W[kb*nblk+nb] + bias[nb] (+ resid) )
+//
+// Same contract as scann_dense_forward (atom.cu).  One CTA = 128 rows x one 128-column block:
+//   * the weight block is the STATIONARY operand: W^T (hi and lo tf32 parts) lives in tensor
+//     memory as the M x K "A" operand (lane = output feature n, column = input feature k),
+//   * the activation tile is the "B" operand: its canonical K-major image (tc_common.cuh) is staged
+//     in shared memory by the threads (coalesced loads, hi/lo split, no transposition needed),
+//   * D^T = W^T @ X^T accumulates in tensor memory (lane = n, column = row r), the main term
+//     hi*hi and the correction lo*hi + hi*lo in separate accumulators (single-accumulator
+//     3xTF32 loses the small terms to the tensor core's truncating adds: 1.5e-5 vs 3.4e-6),
+//   * epilogue: TMEM -> registers -> shared (transposing) -> warp-per-row bias / swish /
+//     residual / LayerNorm -> coalesced global stores.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#define DTC_THREADS 256
+
+struct DenseTcArgs {
+    const float* A[3];
+    int lda;
+    const float* W[9];
+    const float* bias[3];
+    int kblk, nblk, R;
+    float* C;
+    int ldc, mode;
+    const float* resid;
+    int ldres;
+    const float* pre_in;
+    float* pre_out;
+    const float* gamma;
+    const float* beta;
+};
+
+__global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sXhi = smem;
+    uint8_t* sXlo = smem + TC_TILE_BYTES;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r0 = blockIdx.x * 128, nb = blockIdx.y;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
+    uint32_t phase = 0;
+
+    for (int kb = 0; kb < a.kblk; ++kb) {
+        // (b) activation tile: issue all global loads first (16 x LDG.128 in flight per thread)
+        const float* A = a.A[kb];
+        float4 xv[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int i = tid + it * DTC_THREADS, r = i >> 5, c4 = i & 31;
+            xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < a.R) xv[it] = ld4(A + (size_t)(r0 + r) * a.lda + c4 * 4);
+        }
+        // (a) weight block -> tensor memory: thread = output feature n, columns = k; warps 0-3 take
+        //     k in [0,64), warps 4-7 take k in [64,128)
+        {
+            const float* W = a.W[kb * a.nblk + nb];
+            const int n = (warp & 3) * 32 + lane, kbase = (warp >> 2) * 64;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float w[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) w[q] = __ldg(W + (size_t)(kbase + h * 32 + q) * SCANN_D + n);
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) tf32_split(w[g * 16 + q], hi[q], lo[q]);
+                    tmem_st16(t_whi + lane_base + kbase + h * 32 + g * 16, hi);
+                    tmem_st16(t_wlo + lane_base + kbase + h * 32 + g * 16, lo);
+                }
+            }
+        }
+        // activation tile -> K-major images (hi, lo)
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int i = tid + it * DTC_THREADS, r = i >> 5, c4 = i & 31;
+            float4 v = xv[it], h, l;
+            tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y);
+            tf32_split(v.z, h.z, l.z); tf32_split(v.w, h.w, l.w);
+            const uint32_t off = tc_off4(r, c4);
+            *reinterpret_cast<float4*>(sXhi + off) = h;
+            *reinterpret_cast<float4*>(sXlo + off) = l;
+        }
+        tmem_st_wait();
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t xh = smem_u32(sXhi), xl = smem_u32(sXlo);
+#pragma unroll 1
+            for (int ks = 0; ks < 16; ++ks)
+                tc_mma_ts(t_dm, t_whi + ks * 8, tc_desc_kmajor(xh, ks), idesc, (kb | ks) != 0);
+#pragma unroll 1
+            for (int ks = 0; ks < 16; ++ks)
+                tc_mma_ts(t_dc, t_wlo + ks * 8, tc_desc_kmajor(xh, ks), idesc, (kb | ks) != 0);
+#pragma unroll 1
+            for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, tc_desc_kmajor(xl, ks), idesc, true);
+            tc_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        __syncthreads();
+    }
+    // epilogue 1: D^T (lane = n, column = r) -> shared image S[r][n]  (S aliases the hi image)
+    {
+        const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 64;
+#pragma unroll 1
+        for (int rr = rbase; rr < rbase + 64; rr += 16) {
+            float m[16], c[16];
+            tmem_ld16(t_dm + lane_base + rr, m);
+            tmem_ld16(t_dc + lane_base + rr, c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(sXhi + tc_off(rr + q, n)) = m[q] + c[q];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+    // epilogue 2: one warp per row, lane = 4 consecutive columns
+    const int c0 = lane * 4;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.bias[nb]) bias = ldg4(a.bias[nb] + c0);
+    float4 gam = bias, bet = bias;
+    if (a.mode == 3) { gam = ldg4(a.gamma + c0); bet = ldg4(a.beta + c0); }
+    // all global loads of the warp's 16 rows are issued before the first use (no 16-deep latency chain)
+    constexpr int RPW = 128 / (DTC_THREADS / 32);
+    float4 rv[RPW], pv[RPW];
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int r = r0 + warp + i * (DTC_THREADS / 32);
+        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pv[i] = rv[i];
+        if (r < a.R) {
+            if (a.resid) rv[i] = ld4(a.resid + (size_t)r * a.ldres + nb * SCANN_D + c0);
+            if (a.mode == 2) pv[i] = ld4(a.pre_in + (size_t)r * a.ldc + nb * SCANN_D + c0);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+        const int rr = warp + i * (DTC_THREADS / 32), r = r0 + rr;
+        const bool ok = r < a.R;                     // warp-uniform
+        float4 acc = *reinterpret_cast<const float4*>(sXhi + tc_off4(rr, lane));
+        float v[4] = {acc.x + bias.x + rv[i].x, acc.y + bias.y + rv[i].y, acc.z + bias.z + rv[i].z,
+                      acc.w + bias.w + rv[i].w};
+        if (a.mode == 1) {
+            if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + nb * SCANN_D + c0, make_float4(v[0], v[1], v[2], v[3]));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = swish_f(v[j]);
+        } else if (a.mode == 2) {
+            v[0] *= swish_grad_f(pv[i].x); v[1] *= swish_grad_f(pv[i].y);
+            v[2] *= swish_grad_f(pv[i].z); v[3] *= swish_grad_f(pv[i].w);
+        } else if (a.mode == 3) {
+            if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + c0, make_float4(v[0], v[1], v[2], v[3]));
+            float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / SCANN_D);
+            float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean, d3 = v[3] - mean;
+            float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / SCANN_D);
+            float inv = rsqrtf(var + SCANN_LN_EPS);
+            v[0] = d0 * inv * gam.x + bet.x; v[1] = d1 * inv * gam.y + bet.y;
+            v[2] = d2 * inv * gam.z + bet.z; v[3] = d3 * inv * gam.w + bet.w;
+        }
+        if (ok) st4(a.C + (size_t)r * a.ldc + nb * SCANN_D + c0, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
+extern "C" int scann_dense_forward_tc(const float* const* A, int lda, const float* const* W, const float* const* bias,
+                                      int kblk, int nblk, int R, float* C, int ldc, int mode, const float* resid,
+                                      int ldres, const float* pre_in, float* pre_out, const float* gamma,
+                                      const float* beta, void* stream) {
+    if (kblk < 1 || kblk > 3 || nblk < 1 || nblk > 3) { scann_set_error("dense_tc: kblk/nblk must be in 1..3"); return 1; }
+    if (mode == 3 && nblk != 1) { scann_set_error("dense_tc: LayerNorm epilogue needs nblk == 1"); return 1; }
+    if (R <= 0) return 0;
+    static bool configured = false;
+    const size_t smem = 2 * TC_TILE_BYTES;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { scann_set_error("dense_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    DenseTcArgs a;
+    for (int i = 0; i < 3; ++i) { a.A[i] = i < kblk ? A[i] : nullptr; a.bias[i] = (bias && i < nblk) ? bias[i] : nullptr; }
+    for (int i = 0; i < 9; ++i) a.W[i] = i < kblk * nblk ? W[i] : nullptr;
+    a.lda = lda; a.kblk = kblk; a.nblk = nblk; a.R = R; a.C = C; a.ldc = ldc; a.mode = mode;
+    a.resid = resid; a.ldres = ldres; a.pre_in = pre_in; a.pre_out = pre_out; a.gamma = gamma; a.beta = beta;
+    dim3 grid((R + 127) / 128, nblk);
+    dense_tc_kernel<<<grid, DTC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    return scann_check_launch("scann_dense_forward_tc");
+}

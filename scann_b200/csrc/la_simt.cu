@@ -87,9 +87,16 @@ __device__ __forceinline__ void zero_acc(float (&acc)[8][8]) {
 __device__ __forceinline__ int col_of(int tx, int j) { return (j < 4) ? tx * 4 + j : 64 + tx * 4 + (j - 4); }
 
 __device__ __forceinline__ void load_tile(float* S, const float* __restrict__ src, size_t rowbase, int tid) {
-    for (int i = tid; i < SCANN_TILE * 32; i += LA_THREADS) {
-        int row = i >> 5, c4 = (i & 31) * 4;
-        st4(S + row * LA_LDS + c4, ld4(src + (rowbase + row) * SCANN_D + c4));
+    float4 v[16];                       // all 16 loads in flight before the first store
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        int i = tid + it * LA_THREADS;
+        v[it] = ld4(src + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
+    }
+#pragma unroll
+    for (int it = 0; it < 16; ++it) {
+        int i = tid + it * LA_THREADS;
+        st4(S + (i >> 5) * LA_LDS + (i & 31) * 4, v[it]);
     }
 }
 

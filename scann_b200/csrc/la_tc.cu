@@ -1,0 +1,351 @@
+// Local attention forward on the tcgen05 tensor cores (g_update = True), two persistent kernels:
+//
+//   la_geom_fwd_tc : g' = LN_g(swish(xw1[c] + g @ W2 + xw3[j]) + g)          (attention.py:141-153)
+//   la_attn_fwd_tc : k = (x[j] * g') @ Wk + bk ; softmax over the atom's pairs ; out = LN(sum p k + q)
+//                                                                           (attention.py:157-214)
+//
+// Each kernel keeps ONE 128x128 weight block stationary in tensor memory as the M x K operand
+// (W^T: lane = output feature, column = input feature; hi and lo tf32 parts, 256 columns) and streams
+// 128-pair tiles through shared memory as the N x K operand (canonical K-major image, tc_common.cuh).
+// D^T = W^T @ X^T lands in tensor memory (lane = feature, column = pair row); main (hi*hi) and
+// correction (lo*hi + hi*lo) terms use separate accumulators (256 columns).  The accumulator is moved to
+// shared memory transposed and the row-wise epilogue runs warp-per-row with coalesced gathers that
+// were prefetched into registers while the tensor core was busy.
+//
+// Both weights of a layer (4 x 64 KB as hi/lo tf32) exceed one SM's shared + tensor memory next to the
+// tile operands, hence two kernels; g' makes one extra round trip through L2/HBM.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+#define LTC_THREADS 512
+#define LTC_WARPS 16
+#define LTC_RPW 8                          // rows per warp in the row-wise epilogue
+
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// W[k][n] (row-major, ld 128) -> tensor memory as A[M = n][K = k], hi and lo parts.
+// warp w: lane quarter w%4 (features 32*(w%4)..), k range 32*(w/4)..+31
+__device__ __forceinline__ void weightT_to_tmem(const float* __restrict__ W, uint32_t t_hi, uint32_t t_lo, int warp,
+                                                int lane) {
+    const int n = (warp & 3) * 32 + lane, kbase = (warp >> 2) * 32;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float w[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) w[q] = __ldg(W + (size_t)(kbase + q) * SCANN_D + n);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) tf32_split(w[g * 16 + q], hi[q], lo[q]);
+        tmem_st16(t_hi + lane_base + kbase + g * 16, hi);
+        tmem_st16(t_lo + lane_base + kbase + g * 16, lo);
+    }
+    tmem_st_wait();
+}
+
+// D_main = W_hi X_hi^T ; D_corr = W_lo X_hi^T + W_hi X_lo^T   (one thread)
+__device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
+                                             uint32_t t_dc, uint64_t* bar) {
+    const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
+#pragma unroll 1
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, tc_desc_kmajor(xh, ks), idesc, ks != 0);
+#pragma unroll 1
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_wlo + ks * 8, tc_desc_kmajor(xh, ks), idesc, ks != 0);
+#pragma unroll 1
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, tc_desc_kmajor(xl, ks), idesc, true);
+    tc_commit(bar);
+}
+
+// accumulators (lane = feature n, column = row r) -> S[r][n] (+ bias[n]); warp w: lanes 32*(w%4).., rows 32*(w/4)..
+__device__ __forceinline__ void tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8_t* S, const float* __restrict__ bias,
+                                             int warp, int lane) {
+    const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 32;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const float b = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float m[16], c[16];
+        tmem_ld16(t_dm + lane_base + rbase + h * 16, m);
+        tmem_ld16(t_dc + lane_base + rbase + h * 16, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(S + tc_off(rbase + h * 16 + q, n)) = m[q] + c[q] + b;
+    }
+}
+
+// =============================================================================================
+// Geometry update
+// =============================================================================================
+struct LaGeomArgs {
+    const int32_t* ntiles; const int32_t* pair_c; const int32_t* pair_j;
+    const float* proj;       // [R,384] = [x@W1+bf | x@W3 | x@Wq+bq]
+    const float* g_in;       // [rows,128]
+    const float* W2;         // rows 128..255 of filter_geo/kernel, [k][n]
+    const float* gamma_g; const float* beta_g;
+    float* g_out;            // [rows,128]
+    float* pre_out;          // [rows,128] pre-activation of filter_geo (nullable; saved for backward)
+};
+
+__global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const LaGeomArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sHi = smem;
+    uint8_t* sLo = smem + TC_TILE_BYTES;
+    uint8_t* sS = smem + 2 * TC_TILE_BYTES;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = *a.ntiles;
+    if ((int)blockIdx.x >= nt) return;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);
+    const float4 gam = ldg4(a.gamma_g + lane * 4), bet = ldg4(a.beta_g + lane * 4);
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const size_t rowbase = (size_t)t * SCANN_TILE;
+        // ---- stage the geometry tile: coalesced loads, hi/lo split, K-major images
+        {
+            float4 v[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int i = tid + it * LTC_THREADS;
+                v[it] = ld4(a.g_in + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int i = tid + it * LTC_THREADS;
+                float4 h, l;
+                tf32_split(v[it].x, h.x, l.x); tf32_split(v[it].y, h.y, l.y);
+                tf32_split(v[it].z, h.z, l.z); tf32_split(v[it].w, h.w, l.w);
+                const uint32_t off = tc_off4(i >> 5, i & 31);
+                *reinterpret_cast<float4*>(sHi + off) = h;
+                *reinterpret_cast<float4*>(sLo + off) = l;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
+        }
+        // ---- while the tensor core works: indices and gathered projections of this warp's rows
+        int pc[LTC_RPW];
+        float4 p13[LTC_RPW];
+#pragma unroll
+        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+#pragma unroll
+        for (int i = 0; i < LTC_RPW; ++i) {
+            p13[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pc[i] >= 0) {
+                const int j = a.pair_j[rowbase + warp + LTC_WARPS * i];
+                p13[i] = f4add(ld4(a.proj + (size_t)pc[i] * 3 * SCANN_D + lane * 4),
+                               ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + lane * 4));
+            }
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        tmem_to_rows(t_dm, t_dc, sS, nullptr, warp, lane);
+        tc_fence_before();
+        __syncthreads();
+        // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
+#pragma unroll
+        for (int i = 0; i < LTC_RPW; ++i) {
+            const int r = warp + LTC_WARPS * i;
+            const uint32_t off = tc_off4(r, lane);
+            float4 acc = *reinterpret_cast<const float4*>(sS + off);
+            float4 gh = *reinterpret_cast<const float4*>(sHi + off), gl = *reinterpret_cast<const float4*>(sLo + off);
+            float pre[4] = {acc.x + p13[i].x, acc.y + p13[i].y, acc.z + p13[i].z, acc.w + p13[i].w};
+            float g[4] = {gh.x + gl.x, gh.y + gl.y, gh.z + gl.z, gh.w + gl.w};
+            float z[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[q] = swish_f(pre[q]) + g[q];
+            float mean = warp_sum(z[0] + z[1] + z[2] + z[3]) * (1.0f / SCANN_D);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) z[q] -= mean;
+            float inv = rsqrtf(warp_sum(z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3]) * (1.0f / SCANN_D) +
+                               SCANN_LN_EPS);
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
+            if (pc[i] >= 0) {
+                o = make_float4(z[0] * inv * gam.x + bet.x, z[1] * inv * gam.y + bet.y, z[2] * inv * gam.z + bet.z,
+                                z[3] * inv * gam.w + bet.w);
+                po = make_float4(pre[0], pre[1], pre[2], pre[3]);
+            }
+            st4(a.g_out + (rowbase + r) * SCANN_D + lane * 4, o);
+            if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + lane * 4, po);
+        }
+        __syncthreads();                 // images and S are rewritten by the next tile
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// =============================================================================================
+// Attention
+// =============================================================================================
+struct LaAttnArgs {
+    const int32_t* ntiles; const int32_t* tile_a0; const int32_t* tile_a1;
+    const int32_t* cnt; const int32_t* rowptr; const int32_t* pair_c; const int32_t* pair_j;
+    const float* x;          // [R,128]
+    const float* proj;       // [R,384]; q = columns 256..383
+    const float* g_new;      // [rows,128] updated geometry g'
+    const float* Wk; const float* bk; const float* gamma; const float* beta;
+    float* ctx_pre;          // [R,128] nullable
+    float* out;              // [R,128]
+    float* attn;             // [rows,8] nullable
+    float* k_out;            // [rows,128] nullable (keys, saved for backward)
+};
+
+__global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const LaAttnArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* sHi = smem;
+    uint8_t* sLo = smem + TC_TILE_BYTES;
+    uint8_t* sS = smem + 2 * TC_TILE_BYTES;
+    float* Es = reinterpret_cast<float*>(smem + 3 * TC_TILE_BYTES);      // [128][8]
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = *a.ntiles;
+    if ((int)blockIdx.x >= nt) return;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    weightT_to_tmem(a.Wk, t_whi, t_wlo, warp, lane);
+    const float4 gam = ldg4(a.gamma + lane * 4), bet = ldg4(a.beta + lane * 4);
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const size_t rowbase = (size_t)t * SCANN_TILE;
+        int pc[LTC_RPW];
+        // ---- stage a = x[j] * g' (warp per row: coalesced row loads and gathers), hi/lo images
+        {
+            float4 gv[LTC_RPW], xv[LTC_RPW];
+#pragma unroll
+            for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+#pragma unroll
+            for (int i = 0; i < LTC_RPW; ++i) {
+                const int r = warp + LTC_WARPS * i;
+                gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[i] = gv[i];
+                if (pc[i] >= 0) {
+                    const int j = a.pair_j[rowbase + r];
+                    gv[i] = ld4(a.g_new + (rowbase + r) * SCANN_D + lane * 4);
+                    xv[i] = ld4(a.x + (size_t)j * SCANN_D + lane * 4);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < LTC_RPW; ++i) {
+                const int r = warp + LTC_WARPS * i;
+                float4 h, l;
+                tf32_split(gv[i].x * xv[i].x, h.x, l.x); tf32_split(gv[i].y * xv[i].y, h.y, l.y);
+                tf32_split(gv[i].z * xv[i].z, h.z, l.z); tf32_split(gv[i].w * xv[i].w, h.w, l.w);
+                const uint32_t off = tc_off4(r, lane);
+                *reinterpret_cast<float4*>(sHi + off) = h;
+                *reinterpret_cast<float4*>(sLo + off) = l;
+            }
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
+        }
+        // ---- prefetch the queries of this warp's rows while the tensor core works
+        float4 qv[LTC_RPW];
+#pragma unroll
+        for (int i = 0; i < LTC_RPW; ++i) {
+            qv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pc[i] >= 0) qv[i] = ld4(a.proj + (size_t)pc[i] * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        tmem_to_rows(t_dm, t_dc, sS, a.bk, warp, lane);          // keys k = a @ Wk + bk
+        tc_fence_before();
+        __syncthreads();
+        // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = 4 lanes)
+#pragma unroll
+        for (int i = 0; i < LTC_RPW; ++i) {
+            const int r = warp + LTC_WARPS * i;
+            float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
+            float e = quad_sum(kv.x * qv[i].x + kv.y * qv[i].y + kv.z * qv[i].z + kv.w * qv[i].w) * 0.25f;
+            if ((lane & 3) == 0) Es[r * 8 + (lane >> 2)] = e;
+            if (a.k_out) st4(a.k_out + (rowbase + r) * SCANN_D + lane * 4, pc[i] >= 0 ? kv : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        __syncthreads();
+        // ---- per atom: softmax over its rows, context, residual q, LayerNorm (one warp per atom)
+        const int a0 = a.tile_a0[t], a1 = a.tile_a1[t];
+        for (int atom = a0 + warp; atom < a1; atom += LTC_WARPS) {
+            const int n = a.cnt[atom];
+            if (n == 0) continue;
+            const int r0 = a.rowptr[atom] - (int)rowbase;
+            const int h = lane >> 2;
+            float4 q = ld4(a.proj + (size_t)atom * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+            float m = -INFINITY;
+            for (int r = 0; r < n; ++r) m = fmaxf(m, Es[(r0 + r) * 8 + h]);
+            float s = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+            for (int r = 0; r < n; ++r) {
+                float p = expf(Es[(r0 + r) * 8 + h] - m);
+                float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r0 + r, lane));
+                s += p;
+                c0 = fmaf(p, kv.x, c0); c1 = fmaf(p, kv.y, c1); c2 = fmaf(p, kv.z, c2); c3 = fmaf(p, kv.w, c3);
+            }
+            const float is = 1.0f / s;
+            if (a.attn && (lane & 3) == 0)
+                for (int r = 0; r < n; ++r) a.attn[(rowbase + r0 + r) * 8 + h] = expf(Es[(r0 + r) * 8 + h] - m) * is;
+            c0 = c0 * is + q.x; c1 = c1 * is + q.y; c2 = c2 * is + q.z; c3 = c3 * is + q.w;
+            if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
+            float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
+            c0 -= mean; c1 -= mean; c2 -= mean; c3 -= mean;
+            float inv = rsqrtf(warp_sum(c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3) * (1.0f / SCANN_D) + SCANN_LN_EPS);
+            st4(a.out + (size_t)atom * SCANN_D + lane * 4,
+                make_float4(c0 * inv * gam.x + bet.x, c1 * inv * gam.y + bet.y, c2 * inv * gam.z + bet.z,
+                            c3 * inv * gam.w + bet.w));
+        }
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+#define LA_GEOM_SMEM (3 * TC_TILE_BYTES)
+#define LA_ATTN_SMEM (3 * TC_TILE_BYTES + SCANN_TILE * 8 * sizeof(float))
+
+// Tensor-core forward of LocalAttention.call (attention.py:118-216); same data contract as
+// scann_la_forward plus the optional training saves pre_out / k_out ([rows,128] each).
+extern "C" int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                                   const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
+                                   const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
+                                   const float* W2, const float* Wk, const float* bk, const float* gamma_g,
+                                   const float* beta_g, const float* gamma, const float* beta, float* g_out,
+                                   float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
+                                   void* stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(la_geom_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)LA_GEOM_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
+        if (e != cudaSuccess) { scann_set_error("la_forward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    if (grid <= 0) return 0;
+    LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
+    la_geom_fwd_tc_kernel<<<grid, LTC_THREADS, LA_GEOM_SMEM, (cudaStream_t)stream>>>(ga);
+    LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
+                  ctx_pre, out, attn, k_out};
+    la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
+    return scann_check_launch("scann_la_forward_tc");
+}

@@ -9,6 +9,7 @@ hot path.  Graph being executed: ``create_model`` of the reference
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional, Tuple
 
 import numpy as np
@@ -73,6 +74,7 @@ class Engine:
         self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
         self.adam_scalars = torch.zeros(8, dtype=torch.float32, device=dev)
         self._adam_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self._adam_ev = None
         self.step_count = 0
         # RBF centres: np.linspace(0, gaussian_d, 20) / np.linspace(0, 2*pi, 20), float32 (scann_model.py:378,384)
         self.centers_d = torch.from_numpy(np.linspace(0, spec.gaussian_d, N_RBF, dtype="float32")).to(dev)
@@ -85,10 +87,16 @@ class Engine:
                     offs.append(e.offset + blk * D * D)
         self.tblocks = torch.tensor(offs, dtype=torch.int32, device=dev)
         self._ws: Dict[Tuple, dict] = {}
-        self._pinned: Dict[Tuple, dict] = {}
+        self._pinned: Dict[Tuple, list] = {}
+        self._batches: Dict[Tuple, Batch] = {}
+        self.use_graphs = os.environ.get("SCANN_GRAPHS", "1") == "1"
         self.la_grid = self.sm_count
         self.launches = 0
         self.prof: Optional[dict] = None
+        # engine selection (tensor-core kernels are the default; SCANN_ENGINE=simt keeps the fp32 SIMT path)
+        eng = os.environ.get("SCANN_ENGINE", "tc")
+        self.tc_dense = eng != "simt" and os.environ.get("SCANN_DENSE", "tc") == "tc"
+        self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -137,14 +145,31 @@ class Engine:
         return self.params.cpu().numpy()
 
     # ------------------------------------------------------------------ inputs
-    def load_batch(self, inputs: Dict[str, object]) -> Batch:
-        """Stage one padded batch (reference layout, scann/utils/datagenerator.py:123-135) on the
-        device and build its pair plan.  Host arrays go through pinned staging buffers; objects
-        that are already CUDA tensors (or export ``__dlpack__``) are used in place."""
-        b = Batch()
+    def load_batch(self, inputs: Dict[str, object], plan: bool = True) -> Batch:
+        """Stage one padded batch (reference layout, scann/utils/datagenerator.py:123-135) in the
+        persistent device buffers of its shape class and build its pair plan.  Host arrays go through
+        pinned staging buffers; CUDA tensors / ``__dlpack__`` objects are copied device-to-device.
+        Buffers are persistent per (B, M, N, tile capacity) so that a captured CUDA graph can be
+        replayed on every batch of that shape."""
         dev = self.device
+        nb = inputs["neighbors"]
+        B, M, N = (int(s) for s in nb.shape)
+        R = B * M
+        nmask_in = inputs["neighbor_mask"]
+        P_host = int(np.count_nonzero(nmask_in)) if isinstance(nmask_in, np.ndarray) else None
+        # tile capacity: every non-final tile of a greedy group holds more than 128-N rows
+        P = P_host if P_host is not None else B * M * N
+        ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
+        cap = P // (129 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2
+        tile_cap = max(64, (cap + 63) // 64 * 64)
+        key = (B, M, N, tile_cap)
+        b = self._batches.get(key)
+        if b is None:
+            b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups)
+        b.P_host = P_host
+        b.h2d_bytes = 0
 
-        def to_dev(x, dtype, key):
+        def put(dst: torch.Tensor, x, name):
             if isinstance(x, torch.Tensor):
                 t = x
             elif hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
@@ -153,67 +178,86 @@ class Engine:
                 a = np.ascontiguousarray(x)
                 if a.dtype == np.bool_:
                     a = a.view(np.uint8)
-                slot = self._pinned.get((key, a.shape, a.dtype.str))
+                want = {torch.int32: np.int32, torch.uint8: np.uint8, torch.float32: np.float32}[dst.dtype]
+                if a.dtype != want:
+                    a = (a != 0).astype(np.uint8) if want is np.uint8 else a.astype(want)
+                slot = self._pinned.get((name, key))
                 if slot is None:
-                    pin = torch.empty(a.shape, dtype=torch.from_numpy(a.reshape(-1)[:0].copy()).dtype).pin_memory()
-                    slot = self._pinned[(key, a.shape, a.dtype.str)] = [pin, None]
+                    slot = self._pinned[(name, key)] = [torch.empty(dst.shape, dtype=dst.dtype).pin_memory(), None]
                 pin, ev = slot
                 if ev is not None:
                     ev.synchronize()            # the previous async copy out of this buffer has finished
-                pin.numpy()[...] = a
-                t = pin.to(dev, non_blocking=True)
+                pin.numpy()[...] = a.reshape(pin.shape)
+                dst.copy_(pin, non_blocking=True)
                 slot[1] = torch.cuda.Event()
                 slot[1].record(torch.cuda.current_stream(dev))
-                b.h2d_bytes = getattr(b, "h2d_bytes", 0) + a.nbytes
-            if t.device != dev:
-                t = t.to(dev, non_blocking=True)
-            if dtype == torch.uint8:
-                if t.dtype == torch.bool:
-                    t = t.view(torch.uint8) if t.is_contiguous() else t.contiguous().view(torch.uint8)
-                elif t.dtype != torch.uint8:
-                    t = (t != 0).view(torch.uint8)
-            elif t.dtype != dtype:
-                t = t.to(dtype)
-            return t.contiguous()
+                b.h2d_bytes += a.nbytes
+                return
+            if t.numel() != dst.numel():
+                raise ValueError(f"{name}: expected {dst.numel()} elements, got {t.numel()}")
+            if dst.dtype == torch.uint8 and t.dtype not in (torch.uint8, torch.bool):
+                t = t != 0
+            dst.copy_(t.reshape(dst.shape), non_blocking=True)
 
-        nb = inputs["neighbors"]
-        B, M, N = (int(s) for s in nb.shape)
-        b.B, b.M, b.N, b.R = B, M, N, B * M
-        nmask_in = inputs["neighbor_mask"]
-        if isinstance(nmask_in, np.ndarray):
-            b.P_host = int(np.count_nonzero(nmask_in))
-        b.atomic = to_dev(inputs["atomic"], torch.int32, "atomic").view(-1)
-        b.atom_mask = to_dev(inputs["atom_mask"], torch.uint8, "atom_mask").view(-1)
-        b.nbr = to_dev(nb, torch.int32, "neighbors").view(-1)
-        b.nmask = to_dev(nmask_in, torch.uint8, "neighbor_mask").view(-1)
-        b.weight = to_dev(inputs["neighbor_weight"], torch.float32, "neighbor_weight").view(-1)
-        b.dist = to_dev(inputs["neighbor_distance"], torch.float32, "neighbor_distance").view(-1)
-        if b.atomic.numel() != b.R or b.atom_mask.numel() != b.R:
-            raise ValueError("atomic / atom_mask must be [B,M] / [B,M,1]")
-        # tile capacity: every non-final tile of a greedy group holds more than 128-N rows
-        P = b.P_host if b.P_host is not None else B * M * N
-        ngroups = (b.R + PLAN_GSZ - 1) // PLAN_GSZ
-        cap = P // (129 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2
-        b.tile_cap = max(64, (cap + 63) // 64 * 64)
-        b.ngroups = ngroups
-        self._plan(b)
+        put(b.atomic, inputs["atomic"], "atomic")
+        put(b.atom_mask, inputs["atom_mask"], "atom_mask")
+        put(b.nbr, nb, "neighbors")
+        put(b.nmask, nmask_in, "neighbor_mask")
+        put(b.weight, inputs["neighbor_weight"], "neighbor_weight")
+        put(b.dist, inputs["neighbor_distance"], "neighbor_distance")
+        if plan:
+            self._plan(b)
         return b
 
-    def _plan(self, b: Batch) -> None:
+    def _new_batch(self, B: int, M: int, N: int, tile_cap: int, ngroups: int) -> Batch:
         dev = self.device
-        rows = b.tile_cap * TILE
+        b = Batch()
+        b.B, b.M, b.N, b.R, b.tile_cap, b.ngroups = B, M, N, B * M, tile_cap, ngroups
+        rows = tile_cap * TILE
         i32 = dict(dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        b.atomic = torch.zeros(b.R, **i32)
+        b.atom_mask = torch.zeros(b.R, dtype=torch.uint8, device=dev)
+        b.nbr = torch.zeros(b.R * N, **i32)
+        b.nmask = torch.zeros(b.R * N, dtype=torch.uint8, device=dev)
+        b.weight = torch.zeros(b.R * N, **f32)
+        b.dist = torch.zeros(b.R * N, **f32)
+        b.target = torch.zeros(B, **f32)
         b.cnt = torch.empty(b.R, **i32)
         b.rowptr = torch.empty(b.R, **i32)
-        b.tile_a0 = torch.empty(b.tile_cap, **i32)
-        b.tile_a1 = torch.empty(b.tile_cap, **i32)
+        b.tile_a0 = torch.empty(tile_cap, **i32)
+        b.tile_a1 = torch.empty(tile_cap, **i32)
         b.ntiles = torch.zeros(1, **i32)
         b.pair_c = torch.empty(rows, **i32)
         b.pair_j = torch.empty(rows, **i32)
         b.pair_slot = torch.empty(rows, **i32)
-        b.pair_d = torch.empty(rows, dtype=torch.float32, device=dev)
-        b.pair_w = torch.empty(rows, dtype=torch.float32, device=dev)
-        b.scratch = torch.empty(2 * b.ngroups + 8, **i32)
+        b.pair_d = torch.empty(rows, **f32)
+        b.pair_w = torch.empty(rows, **f32)
+        b.scratch = torch.empty(2 * ngroups + 8, **i32)
+        b.graphs = {}
+        return b
+
+    def set_target(self, b: Batch, y_true) -> None:
+        if isinstance(y_true, torch.Tensor):
+            b.target.copy_(y_true.reshape(-1), non_blocking=True)
+            return
+        a = np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1))
+        if a.size != b.B:
+            raise ValueError("target must have one value per structure")
+        key = (b.B, b.M, b.N, b.tile_cap)
+        slot = self._pinned.get(("target", key))
+        if slot is None:
+            slot = self._pinned[("target", key)] = [torch.empty(b.B, dtype=torch.float32).pin_memory(), None]
+        pin, ev = slot
+        if ev is not None:
+            ev.synchronize()
+        pin.numpy()[...] = a
+        b.target.copy_(pin, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record(torch.cuda.current_stream(self.device))
+        b.h2d_bytes += a.nbytes
+
+    def _plan(self, b: Batch) -> None:
         check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
                                    _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
@@ -266,7 +310,8 @@ class Engine:
     # ------------------------------------------------------------------ thin kernel wrappers
     def _dense(self, A, lda, W, bias, kblk, nblk, R, C, ldc, mode=0, resid=None, ldres=D, pre_in=None, pre_out=None,
                gamma=0, beta=0):
-        check(lib.scann_dense_forward(ptr_array(A), lda, ptr_array(W), ptr_array(bias) if bias else None, kblk, nblk,
+        fn = lib.scann_dense_forward_tc if self.tc_dense else lib.scann_dense_forward
+        check(fn(ptr_array(A), lda, ptr_array(W), ptr_array(bias) if bias else None, kblk, nblk,
                                       R, C, ldc, mode, _p(resid), ldres, _p(pre_in), _p(pre_out), gamma, beta,
                                       self._stream()), "dense_forward")
         self.launches += 1
@@ -314,12 +359,17 @@ class Engine:
                 attn = torch.zeros(b.tile_cap * TILE, 8, dtype=torch.float32, device=self.device)
                 attn_out.append(attn)
             self._ev("la_forward", True)
-            check(lib.scann_la_forward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
-                                       _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),
-                                       self.w(fg, D * D), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
-                                       self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
-                                       self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
-                                       _p(g_out), _p(ctxpre), _p(out), _p(attn), st), "la_forward")
+            la_args = (self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                       _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),
+                       self.w(fg, D * D), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                       self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
+                       self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
+                       _p(g_out), _p(ctxpre), _p(out), _p(attn))
+            if self.tc_la_fwd:
+                check(lib.scann_la_forward_tc(*la_args, 0, 0, st), "la_forward_tc")
+                self.launches += 1
+            else:
+                check(lib.scann_la_forward(*la_args, st), "la_forward")
             self._ev("la_forward", False)
             self.launches += 2
             if sp.use_attn_norm:
@@ -440,18 +490,12 @@ class Engine:
         lr_t = lr / (1.0 + decay * (t - 1))                       # legacy Keras `decay`
         alpha = lr_t * np.sqrt(1.0 - b2 ** t) / (1.0 - b1 ** t)
         h = self._adam_host
+        if self._adam_ev is not None:
+            self._adam_ev.synchronize()
         h[0], h[1], h[2], h[3], h[4], h[5] = alpha, b1, b2, eps, L2_COEF, float(batch_global)
         self.adam_scalars.copy_(h, non_blocking=True)
-
-    def apply_gradients(self, lr: float, batch_global: int, apply: bool = True, want_grads: bool = False) -> None:
-        self._set_adam(lr, batch_global)
-        n = self.layout.total
-        check(lib.scann_adam_step(_p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
-                                  _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
-                                  int(apply), self._stream()), "adam_step")
-        self.launches += 1
-        if apply:
-            self.step_count += 1
+        self._adam_ev = torch.cuda.Event()
+        self._adam_ev.record(torch.cuda.current_stream(self.device))
 
     def loss_value(self, batch_global: int) -> torch.Tensor:
         """[loss (RMSE + l2 terms), RMSE, MAE] of the batch whose SSE sits in the gradient arena."""
@@ -461,13 +505,73 @@ class Engine:
         self.launches += 1
         return self.loss_out
 
-    def train_step(self, b: Batch, target: torch.Tensor, lr: float, allreduce=None, batch_global: Optional[int] = None,
-                   apply: bool = True, want_grads: bool = False) -> None:
+    def train_step(self, b: Batch, target, lr: float, allreduce=None, batch_global: Optional[int] = None,
+                   apply: bool = True, want_grads: bool = False, replan: bool = False) -> None:
         """One Keras train_step (scann_model.py:232-241): forward, RMSE + l2 loss, backward, Adam.
-        ``allreduce(tensor)`` sums the gradient arena (+SSE) across data-parallel ranks."""
+        ``allreduce(tensor)`` sums the gradient arena (+SSE) across data-parallel ranks.  With
+        ``replan`` the pair plan is rebuilt from the (freshly loaded) inputs as part of the step.
+        The kernel sequence of a shape class is captured once into a CUDA graph and replayed."""
+        if target is not None and target is not b.target:
+            self.set_target(b, target)
+        self._set_adam(lr, batch_global or b.B)
+        key = ("train", replan, apply, want_grads, allreduce is not None)
+        if not self.use_graphs or self.prof is not None:
+            self._train_body(b, allreduce, apply, want_grads, replan)
+        else:
+            g = b.graphs.get(key)
+            if g is None:
+                # one eager pass allocates workspaces / warms up, then capture on a side stream
+                self._train_body(b, allreduce, apply=False, want_grads=False, replan=replan)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                n0 = self.launches
+                with torch.cuda.graph(g):
+                    self._train_body(b, allreduce, apply, want_grads, replan)
+                g.n_launches = self.launches - n0
+                b.graphs[key] = g
+            else:
+                self.launches += g.n_launches
+            g.replay()
+        if apply:
+            self.step_count += 1
+
+    def _train_body(self, b: Batch, allreduce, apply: bool, want_grads: bool, replan: bool) -> None:
+        if replan:
+            self._plan(b)
         self.grads.zero_()
         self.forward(b, training=True)
-        self.backward(b, target)
+        self.backward(b, b.target)
         if allreduce is not None:
             allreduce(self.grads)
-        self.apply_gradients(lr, batch_global or b.B, apply=apply, want_grads=want_grads)
+        n = self.layout.total
+        check(lib.scann_adam_step(_p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
+                                  _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
+                                  int(apply), self._stream()), "adam_step")
+        self.launches += 1
+
+    def predict_step(self, b: Batch, replan: bool = False):
+        """Inference forward (plan + graph of kernels) -> (y[B], ga[B*M]) device tensors."""
+        key = ("infer", replan)
+        if not self.use_graphs or self.prof is not None:
+            if replan:
+                self._plan(b)
+            return self.forward(b, training=False)
+        g = b.graphs.get(key)
+        if g is None:
+            if replan:
+                self._plan(b)
+            self.forward(b, training=False)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = self.launches
+            with torch.cuda.graph(g):
+                if replan:
+                    self._plan(b)
+                self.forward(b, training=False)
+            g.n_launches = self.launches - n0
+            b.graphs[key] = g
+        else:
+            self.launches += g.n_launches
+        g.replay()
+        ws = self._workspace(b, False)
+        return ws["y"], ws["ga"]

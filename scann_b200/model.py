@@ -65,11 +65,11 @@ class ScannKerasModel:
         """Keras ``Model.predict``: numpy in, numpy out.  Keras would split the batch into
         sub-batches of 32; structures are independent so one pass gives identical results."""
         eng = self.engine
-        b = eng.load_batch(inputs)
-        y, ga = eng.forward(b, training=False)
+        b = eng.load_batch(inputs, plan=False)
+        y, ga = eng.predict_step(b, replan=True)
         y_h = y.cpu().numpy().reshape(b.B, 1)          # synchronises the stream
         eng.check_status()
-        self.last_e2e_bytes = (getattr(b, "h2d_bytes", 0), y.numel() * 4)
+        self.last_e2e_bytes = (b.h2d_bytes, y.numel() * 4)
         if self.infer:
             ga_h = ga.cpu().numpy().reshape(b.B, b.M, 1)
             self.last_e2e_bytes = (self.last_e2e_bytes[0], self.last_e2e_bytes[1] + ga.numel() * 4)
@@ -94,16 +94,12 @@ class ScannKerasModel:
     def train_on_batch(self, inputs: Dict[str, object], y_true, return_dict: bool = False):
         """One Keras ``train_step``: returns the loss (RMSE + l2 penalties) of the batch."""
         eng = self.engine
-        b = eng.load_batch(inputs)
-        t = torch.as_tensor(np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1)))
-        t = t.pin_memory().to(eng.device, non_blocking=True)
-        if t.numel() != b.B:
-            raise ValueError("target must have one value per structure")
+        b = eng.load_batch(inputs, plan=False)
         batch_global = b.B * self.world_size
-        eng.train_step(b, t, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global)
+        eng.train_step(b, y_true, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global, replan=True)
         out = eng.loss_value(batch_global).cpu().numpy()       # synchronises the stream
         eng.check_status()
-        self.last_e2e_bytes = (getattr(b, "h2d_bytes", 0) + t.numel() * 4, 16)
+        self.last_e2e_bytes = (b.h2d_bytes, 16)
         if return_dict:
             return {"loss": float(out[0]), "rmse": float(out[1]), "mae": float(out[2])}
         return float(out[0])
