@@ -128,6 +128,15 @@ int scann_la_backward(int grid, const int32_t* ntiles, const int32_t* tile_a0, c
                       const float* beta_g, const float* d_ctx, const float* dg_up, float* dg_out, float* dq,
                       float* s_pre, float* t_scatter, float* dx_scatter, float* wpart, float* dgamma_g,
                       float* dbeta_g, float* dbk, void* stream);
+/* Same backward on the tcgen05 tensor cores (three kernels: attention, geometry, pair weight gradients).
+ * kbuf / prebuf: in = keys / filter_geo pre-activation saved by scann_la_forward_tc, out = d_k / d_pre.
+ * dg: gradient w.r.t. g' from the next layer (dg_has_up != 0, updated in place) or scratch. */
+int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                         const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
+                         const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
+                         float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
+                         float* dg, int dg_has_up, float* dg_out, float* dq, float* s_pre, float* t_scatter,
+                         float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream);
 /* dWk += sum_cta wpart[cta][0] ; dW2 += sum_cta wpart[cta][1]  (per-CTA partial weight gradients). */
 int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2, void* stream);
 
@@ -156,6 +165,11 @@ int scann_loss_value(const float* params, const float* l2mask, int n, const floa
  * One 128x128x128 tile product on the tcgen05 tensor cores (self-test of descriptors / layouts).
  * layout 0: A@W, 1: A^T@W, 2: A@W^T, 3: A@W with A in tensor memory; nprod 1 (TF32) or 3 (3xTF32). */
 int scann_tc_probe(const float* A, const float* W, float* D, int layout, int nprod, void* stream);
+/* out[0] = cycles per tcgen05.mma (128 x ncols x 8, tf32) in a chain of nmma accumulating MMAs.
+ * mode bit 0: A from tensor memory; mode bit 1: core-matrix stride 128 B instead of 144 B. */
+int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream);
+/* Phase timestamps (clock64) of CTA 0 of the last la_geom_fwd_tc launch; host_out32: 32 int64 (HOST). */
+int scann_debug_clocks(long long* host_out32);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,7 @@ PROTOTYPES = {
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
     "scann_la_forward_tc": (ci, [ci] + [vp] * 23 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
+    "scann_la_backward_tc": (ci, [ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -43,6 +44,8 @@ PROTOTYPES = {
     "scann_adam_step": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
     "scann_loss_value": (ci, [vp, vp, ci, vp, C.c_float, C.c_float, vp, vp]),
     "scann_tc_probe": (ci, [vp, vp, vp, ci, ci, vp]),
+    "scann_tc_time": (ci, [vp, ci, ci, ci, vp]),
+    "scann_debug_clocks": (ci, [vp]),
 }
 
 

@@ -28,6 +28,23 @@ __device__ __forceinline__ float swish_grad_f(float x) {
     return s * (1.0f + x * (1.0f - s));
 }
 
+// Fast variants for the tensor-core kernels, whose row-wise epilogues are instruction-issue bound:
+// ex2.approx + rcp.approx (2 ulp each) instead of the ~25-instruction expf / IEEE division.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float swish_fast(float x) { return x * sigmoid_fast(x); }
+__device__ __forceinline__ float swish_grad_fast(float x) {
+    float s = sigmoid_fast(x);
+    return s * (1.0f + x * (1.0f - s));
+}
+// sum of two values over the warp in one shuffle sequence
+__device__ __forceinline__ void warp_sum2(float& a, float& b) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

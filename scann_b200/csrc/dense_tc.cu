@@ -99,15 +99,16 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint32_t xh = smem_u32(sXhi), xl = smem_u32(sXlo);
-#pragma unroll 1
+            const uint64_t dh = tc_desc_kmajor(smem_u32(sXhi), 0), dl = tc_desc_kmajor(smem_u32(sXlo), 0);
+            const bool first = kb == 0;
+#pragma unroll
             for (int ks = 0; ks < 16; ++ks)
-                tc_mma_ts(t_dm, t_whi + ks * 8, tc_desc_kmajor(xh, ks), idesc, (kb | ks) != 0);
-#pragma unroll 1
+                tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
+#pragma unroll
             for (int ks = 0; ks < 16; ++ks)
-                tc_mma_ts(t_dc, t_wlo + ks * 8, tc_desc_kmajor(xh, ks), idesc, (kb | ks) != 0);
-#pragma unroll 1
-            for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, tc_desc_kmajor(xl, ks), idesc, true);
+                tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
+#pragma unroll
+            for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
             tc_commit(&bar);
         }
         mbar_wait(&bar, phase);
@@ -160,10 +161,10 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         if (a.mode == 1) {
             if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + nb * SCANN_D + c0, make_float4(v[0], v[1], v[2], v[3]));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = swish_f(v[j]);
+            for (int j = 0; j < 4; ++j) v[j] = swish_fast(v[j]);
         } else if (a.mode == 2) {
-            v[0] *= swish_grad_f(pv[i].x); v[1] *= swish_grad_f(pv[i].y);
-            v[2] *= swish_grad_f(pv[i].z); v[3] *= swish_grad_f(pv[i].w);
+            v[0] *= swish_grad_fast(pv[i].x); v[1] *= swish_grad_fast(pv[i].y);
+            v[2] *= swish_grad_fast(pv[i].z); v[3] *= swish_grad_fast(pv[i].w);
         } else if (a.mode == 3) {
             if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + c0, make_float4(v[0], v[1], v[2], v[3]));
             float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / SCANN_D);

@@ -21,6 +21,10 @@
 #define LTC_WARPS 16
 #define LTC_RPW 8                          // rows per warp in the row-wise epilogue
 
+// phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks: development aid
+__device__ long long g_dbg_clk[32];
+#define DBG_CLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_clk[i] = clock64(); } while (0)
+
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // W[k][n] (row-major, ld 128) -> tensor memory as A[M = n][K = k], hi and lo parts.
@@ -43,16 +47,20 @@ __device__ __forceinline__ void weightT_to_tmem(const float* __restrict__ W, uin
     tmem_st_wait();
 }
 
-// D_main = W_hi X_hi^T ; D_corr = W_lo X_hi^T + W_hi X_lo^T   (one thread)
+// D_main = W_hi X_hi^T ; D_corr = W_lo X_hi^T + W_hi X_lo^T   (one thread).
+// Fully unrolled with the descriptors advanced by immediates: a single thread issues all MMAs, so
+// every extra instruction per MMA shows up as tensor-pipe idle time (measured: 107 cycles per MMA
+// with descriptors rebuilt in the loop vs the 64-cycle math floor of a 128x128x8 tf32 MMA).
 __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
                                              uint32_t t_dc, uint64_t* bar) {
     const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
-#pragma unroll 1
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, tc_desc_kmajor(xh, ks), idesc, ks != 0);
-#pragma unroll 1
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_wlo + ks * 8, tc_desc_kmajor(xh, ks), idesc, ks != 0);
-#pragma unroll 1
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, tc_desc_kmajor(xl, ks), idesc, true);
+    const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+#pragma unroll
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
     tc_commit(bar);
 }
 
@@ -103,7 +111,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    DBG_CLK(0);
     weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);
+    DBG_CLK(1);
     const float4 gam = ldg4(a.gamma_g + lane * 4), bet = ldg4(a.beta_g + lane * 4);
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -130,10 +140,12 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (t == (int)blockIdx.x) DBG_CLK(2);
         if (tid == 0) {
             tc_fence_after();
             issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
         }
+        if (t == (int)blockIdx.x) DBG_CLK(3);
         // ---- while the tensor core works: indices and gathered projections of this warp's rows
         int pc[LTC_RPW];
         float4 p13[LTC_RPW];
@@ -148,12 +160,15 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
                                ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + lane * 4));
             }
         }
+        if (t == (int)blockIdx.x) DBG_CLK(4);
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t == (int)blockIdx.x) DBG_CLK(5);
         tmem_to_rows(t_dm, t_dc, sS, nullptr, warp, lane);
         tc_fence_before();
         __syncthreads();
+        if (t == (int)blockIdx.x) DBG_CLK(6);
         // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i) {
@@ -165,12 +180,17 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
             float g[4] = {gh.x + gl.x, gh.y + gl.y, gh.z + gl.z, gh.w + gl.w};
             float z[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) z[q] = swish_f(pre[q]) + g[q];
-            float mean = warp_sum(z[0] + z[1] + z[2] + z[3]) * (1.0f / SCANN_D);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) z[q] -= mean;
-            float inv = rsqrtf(warp_sum(z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3]) * (1.0f / SCANN_D) +
-                               SCANN_LN_EPS);
+            for (int q = 0; q < 4; ++q) z[q] = swish_fast(pre[q]) + g[q];
+            // one-pass moments around the lane's own partial mean (numerically safe: shifted data)
+            float s1 = z[0] + z[1] + z[2] + z[3];
+            float sh = __shfl_sync(0xffffffffu, s1, 0) * 0.25f;     // common shift ~ row mean estimate
+            float d0 = z[0] - sh, d1 = z[1] - sh, d2 = z[2] - sh, d3 = z[3] - sh;
+            float m1 = d0 + d1 + d2 + d3, m2 = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+            warp_sum2(m1, m2);
+            m1 *= (1.0f / SCANN_D);
+            float var = fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f);
+            float inv = rsqrtf(var + SCANN_LN_EPS);
+            z[0] = d0 - m1; z[1] = d1 - m1; z[2] = d2 - m1; z[3] = d3 - m1;
             float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
             if (pc[i] >= 0) {
                 o = make_float4(z[0] * inv * gam.x + bet.x, z[1] * inv * gam.y + bet.y, z[2] * inv * gam.z + bet.z,
@@ -181,7 +201,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
             if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + lane * 4, po);
         }
         __syncthreads();                 // images and S are rewritten by the next tile
+        if (t == (int)blockIdx.x) DBG_CLK(7);
     }
+    DBG_CLK(8);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -296,14 +318,14 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
             for (int r = 0; r < n; ++r) m = fmaxf(m, Es[(r0 + r) * 8 + h]);
             float s = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
             for (int r = 0; r < n; ++r) {
-                float p = expf(Es[(r0 + r) * 8 + h] - m);
+                float p = __expf(Es[(r0 + r) * 8 + h] - m);
                 float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r0 + r, lane));
                 s += p;
                 c0 = fmaf(p, kv.x, c0); c1 = fmaf(p, kv.y, c1); c2 = fmaf(p, kv.z, c2); c3 = fmaf(p, kv.w, c3);
             }
             const float is = 1.0f / s;
             if (a.attn && (lane & 3) == 0)
-                for (int r = 0; r < n; ++r) a.attn[(rowbase + r0 + r) * 8 + h] = expf(Es[(r0 + r) * 8 + h] - m) * is;
+                for (int r = 0; r < n; ++r) a.attn[(rowbase + r0 + r) * 8 + h] = __expf(Es[(r0 + r) * 8 + h] - m) * is;
             c0 = c0 * is + q.x; c1 = c1 * is + q.y; c2 = c2 * is + q.z; c3 = c3 * is + q.w;
             if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
             float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
@@ -348,4 +370,10 @@ extern "C" int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_
                   ctx_pre, out, attn, k_out};
     la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
     return scann_check_launch("scann_la_forward_tc");
+}
+
+extern "C" int scann_debug_clocks(long long* host_out32) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out32, g_dbg_clk, sizeof(long long) * 32);
+    if (e != cudaSuccess) { scann_set_error("debug_clocks: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
 }

@@ -46,6 +46,9 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 __device__ __forceinline__ uint64_t tc_desc_kmajor(uint32_t tile_saddr, int ks) {
     return tc_desc(tile_saddr + (uint32_t)ks * 2u * TC_CG_STRIDE, TC_CG_STRIDE, TC_RG_STRIDE);
 }
+// descriptor of K-step ks = descriptor of K-step 0 + ks * TC_KSTEP_DESC (start-address field, 16-byte units)
+#define TC_KSTEP_DESC ((uint64_t)((2u * TC_CG_STRIDE) >> 4))
+
 // ---- MN-major tf32 operands: the only layout the hardware accepts is SWIZZLE_128B_BASE32B
 // (cutlass sm100_common.inl:92): column blocks of [128 rows x 128 B], row pitch 128 B, 32-byte
 // chunks XOR-swizzled with (r % 4) (Swizzle<2,5,2>), K atom = 4 rows.

@@ -134,3 +134,59 @@ extern "C" int scann_tc_probe(const float* A, const float* W, float* D, int layo
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(A, W, D, layout, nprod);
     return scann_check_launch("scann_tc_probe");
 }
+
+// ---- timing probe: cycles per tcgen05.mma for a chain of `nmma` accumulating MMAs ----
+// mode 0: SS, B K-major image with TC_CG_STRIDE; mode 1: TS (A in TMEM); mode 2: SS with cg stride 128;
+// mode 3: TS with cg stride 128 ; N = n_cols (multiple of 16)
+__global__ void __launch_bounds__(128, 1) tc_time_kernel(float* out, int mode, int nmma, int ncols) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (2 * (int)TC_TILE_BYTES) / 4; i += 128) reinterpret_cast<float*>(smem)[i] = 0.5f;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t cg = (mode & 2) ? 128u : TC_CG_STRIDE;
+        const uint32_t rg = 32u * cg;
+        const uint32_t idesc = tc_idesc_tf32(128, ncols, false, false);
+        const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + TC_TILE_BYTES);
+        long long t0 = clock64();
+        if (mode & 4) {           // fast issue: descriptors advanced by immediates, 16 MMAs per unrolled group
+            const uint64_t bd0 = tc_desc(sb, cg, rg), ad0 = tc_desc(sa, cg, rg);
+            const uint64_t step = (uint64_t)((2u * cg) >> 4);
+            for (int i = 0; i < nmma; i += 16) {
+#pragma unroll
+                for (int ks = 0; ks < 16; ++ks) {
+                    if (mode & 1) tc_mma_ts(tmem + 256, tmem + ks * 8, bd0 + ks * step, idesc, (i | ks) != 0);
+                    else tc_mma_ss(tmem + 256, ad0 + ks * step, bd0 + ks * step, idesc, (i | ks) != 0);
+                }
+            }
+        } else
+        for (int i = 0; i < nmma; ++i) {
+            const int ks = i & 15;
+            uint64_t bd = tc_desc(sb + (uint32_t)ks * 2u * cg, cg, rg);
+            if (mode & 1) tc_mma_ts(tmem + 256, tmem + ks * 8, bd, idesc, i != 0);
+            else tc_mma_ss(tmem + 256, tc_desc(sa + (uint32_t)ks * 2u * cg, cg, rg), bd, idesc, i != 0);
+        }
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        out[0] = (float)(t1 - t0) / (float)nmma;
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+extern "C" int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream) {
+    size_t smem = 2 * TC_TILE_BYTES;
+    cudaError_t e = cudaFuncSetAttribute(tc_time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { scann_set_error("tc_time: %s", cudaGetErrorString(e)); return 1; }
+    tc_time_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, mode, nmma, ncols);
+    return scann_check_launch("scann_tc_time");
+}

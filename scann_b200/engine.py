@@ -97,6 +97,7 @@ class Engine:
         eng = os.environ.get("SCANN_ENGINE", "tc")
         self.tc_dense = eng != "simt" and os.environ.get("SCANN_DENSE", "tc") == "tc"
         self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
+        self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -288,6 +289,9 @@ class Engine:
             ws["t1"] = [torch.empty(R, D, **f) for _ in range(L)]
             ws["v2"] = [torch.empty(R, D, **f) for _ in range(L)]
             ws["ta"] = torch.empty(R, D, **f)
+            if self.tc_la_bwd:
+                ws["pre"] = [torch.empty(rows, D, **f) for _ in range(L)]     # filter_geo pre-activation -> d_pre
+                ws["kk"] = [torch.empty(rows, D, **f) for _ in range(L)]      # keys -> d_k
             ws["ctxg"] = torch.empty(b.B, D, **f)
             ws["tb"] = torch.empty(b.B, D, **f)
             # backward temporaries
@@ -366,7 +370,9 @@ class Engine:
                        self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
                        _p(g_out), _p(ctxpre), _p(out), _p(attn))
             if self.tc_la_fwd:
-                check(lib.scann_la_forward_tc(*la_args, 0, 0, st), "la_forward_tc")
+                save = training and self.tc_la_bwd
+                check(lib.scann_la_forward_tc(*la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
+                                              st), "la_forward_tc")
                 self.launches += 1
             else:
                 check(lib.scann_la_forward(*la_args, st), "la_forward")
@@ -449,17 +455,31 @@ class Engine:
                                                self.gw(f"{la}/layer_norm/beta"), st), "ln_bwd")
             ws["scat"].zero_()
             s_pre, t_sc, dx_sc = ws["scat"][0], ws["scat"][1], ws["scat"][2]
-            dg_out = ws["dg"][l % 2]
+            dg_out = ws["dg"][(L - l) % 2]
             self._ev("la_backward", True)
-            check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
-                                        _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
-                                        _p(ws["g"][l]), self.w(fg, D * D), self.w(f"{la}/key/kernel"),
-                                        self.wT(fg, D * D), self.wT(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
-                                        self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
-                                        _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(ws["dq"]), _p(s_pre), _p(t_sc),
-                                        _p(dx_sc), _p(ws["wpart"]),
-                                        self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
-                                        self.gw(f"{la}/key/bias"), st), "la_backward")
+            if self.tc_la_bwd:
+                dg_buf = ws["dg"][(L - 1 - l) % 2]
+                check(lib.scann_la_backward_tc(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                                               _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
+                                               _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
+                                               _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
+                                               self.wT(f"{la}/key/kernel"), self.w(f"{la}/layer_norm_g/gamma"),
+                                               _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
+                                               _p(ws["dq"]), _p(s_pre), _p(t_sc), _p(dx_sc), _p(ws["wpart"]),
+                                               self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
+                                               self.gw(f"{la}/key/bias"), st), "la_backward_tc")
+                self.launches += 3
+            else:
+              if True:
+                check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                                            _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
+                                            _p(ws["g"][l]), self.w(fg, D * D), self.w(f"{la}/key/kernel"),
+                                            self.wT(fg, D * D), self.wT(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                                            self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
+                                            _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(ws["dq"]), _p(s_pre), _p(t_sc),
+                                            _p(dx_sc), _p(ws["wpart"]),
+                                            self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
+                                            self.gw(f"{la}/key/bias"), st), "la_backward")
             self._ev("la_backward", False)
             check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, self.gw(f"{la}/key/kernel"),
                                             self.gw(fg, D * D), st), "la_wpart_reduce")
