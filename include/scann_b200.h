@@ -154,10 +154,10 @@ int scann_ga_head_backward(const float* qk, const uint8_t* atom_mask, int B, int
 /* ---- loss and optimiser -----------------------------------------------------------------------
  * root_mean_squared_error (scann/layers/losses.py:5-6): dy_b = y_b - t_b, sse[0] += sum err^2,
  * sse[1] += sum |err|; the 1/(B*RMSE) factor is applied in scann_adam_step after the gradient
- * all-reduce.  Adam(lr, decay=1e-5) + l2(1e-4) regulariser gradient (scann_model.py:212). */
+ * all-reduce; scann_adam_step also accumulates sse[2] += sum(l2mask * w^2) for scann_loss_value.  Adam(lr, decay=1e-5) + l2(1e-4) regulariser gradient (scann_model.py:212). */
 int scann_rmse_prepare(const float* y, const float* target, int B, float* dy, float* sse, void* stream);
 int scann_adam_step(float* params, const float* grads, float* m, float* v, const float* l2mask, int n,
-                    const float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream);
+                    float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream);
 int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch, float l2,
                      float* out3, void* stream);
 

@@ -19,13 +19,16 @@ struct AdamScalars {      // filled by the host every step (device copy)
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    const float* __restrict__ l2mask, int n,
-                                                   const float* __restrict__ sse, const AdamScalars* __restrict__ hs,
+                                                   float* __restrict__ sse_rw, const AdamScalars* __restrict__ hs,
                                                    float* __restrict__ grad_out, int apply) {
+    const float* sse = sse_rw;
     const AdamScalars h = *hs;
     const float rmse = sqrtf(sse[0] / h.batch);
     const float scale = 1.0f / (h.batch * rmse);
+    float reg = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float w = p[i];
+        reg = fmaf(l2mask[i] * w, w, reg);          // l2 penalty of the weights the loss was evaluated with
         float gr = fmaf(g[i], scale, 2.0f * h.l2 * l2mask[i] * w);
         if (grad_out) grad_out[i] = gr;
         if (apply) {
@@ -36,31 +39,21 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
             p[i] = w - h.alpha * mi / (sqrtf(vi) + h.eps);
         }
     }
+    reg = warp_sum(reg);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sse_rw + 2, reg);
 }
 
-// out[0] = sqrt(SSE/B) + l2 * sum(mask * p^2) ; out[1] = sqrt(SSE/B) ; out[2] = sum|err| / B
-__global__ void __launch_bounds__(1024) loss_value_kernel(const float* __restrict__ p,
-                                                          const float* __restrict__ l2mask, int n,
-                                                          const float* __restrict__ sse, float batch, float l2,
-                                                          float* __restrict__ out) {
-    __shared__ float s_red[32];
-    float a = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmaf(l2mask[i] * p[i], p[i], a);
-    a = warp_sum(a);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 32; ++w) t += s_red[w];
-        float rmse = sqrtf(sse[0] / batch);
-        out[0] = rmse + l2 * t;
-        out[1] = rmse;
-        out[2] = sse[1] / batch;
-    }
+// out[0] = sqrt(SSE/B) + l2 * sum(mask * p^2) ; out[1] = sqrt(SSE/B) ; out[2] = sum|err| / B.
+// sse[0] = SSE, sse[1] = sum |err| (scann_rmse_prepare), sse[2] = sum(mask * p^2) (scann_adam_step).
+__global__ void loss_value_kernel(const float* __restrict__ sse, float batch, float l2, float* __restrict__ out) {
+    float rmse = sqrtf(sse[0] / batch);
+    out[0] = rmse + l2 * sse[2];
+    out[1] = rmse;
+    out[2] = sse[1] / batch;
 }
 
 extern "C" int scann_adam_step(float* params, const float* grads, float* m, float* v, const float* l2mask, int n,
-                               const float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream) {
+                               float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream) {
     if (n <= 0) return 0;
     int grid = (n + 255) / 256;
     if (grid > 1184) grid = 1184;
@@ -71,6 +64,7 @@ extern "C" int scann_adam_step(float* params, const float* grads, float* m, floa
 
 extern "C" int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch,
                                 float l2, float* out3, void* stream) {
-    loss_value_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, l2mask, n, sse, batch, l2, out3);
+    (void)params; (void)l2mask; (void)n;
+    loss_value_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sse, batch, l2, out3);
     return scann_check_launch("scann_loss_value");
 }
