@@ -259,7 +259,9 @@ def run_ours(args):
     n_bwd, ms_bwd = prof.get("la_backward", (0, float("nan")))
     n_fwd, ms_fwd = prof.get("la_forward", (0, float("nan")))
     ach = bytes_bwd / (ms_bwd * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "la_bwd_simt_kernel", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+    kern = ("la_attn_bwd_tc + la_geom_bwd_tc + 2 x la_wgrad_tc (one layer of local-attention backward)"
+            if eng.tc_la_bwd else "la_bwd_simt_kernel")
+    roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
             "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
             "share_of_step": n_bwd * ms_bwd / args.steps / (dev_ms / args.steps),
@@ -284,7 +286,8 @@ def run_ours(args):
         "config": {"workload": "qm9_train_step_b128", "structures_per_gpu": B, "M": 29, "N": 16, "layers": L,
                    "valid_atoms_per_gpu": A_valid, "valid_pairs_per_gpu": P_valid, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB write outside the timed events)",
-                   "engine": "fp32 SIMT"},
+                   "engine": "tcgen05 3xTF32 (fp32-accurate)" if eng.tc_la_bwd else "fp32 SIMT",
+                   "cuda_graphs": bool(eng.use_graphs)},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
