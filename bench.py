@@ -246,9 +246,18 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms, infer_ms = (float(x) for x in t.cpu())
-    if rank != 0:
+
+    def finish():
+        # Captured CUDA graphs hold NCCL work; tearing the communicator down under them can hang at
+        # interpreter exit, so every rank synchronises, meets at a barrier and leaves without destructors.
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            dist.barrier()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     L = QM9_CONFIG["model"]["n_attention"]
@@ -298,8 +307,7 @@ def run_ours(args):
                   "note": "forward incl. ga_score, inputs resident in HBM"},
     }
     print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 def main():
