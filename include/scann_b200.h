@@ -118,6 +118,14 @@ int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0,
                         const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
                         const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out,
                         float* k_out, void* stream);
+/* LocalAttention.call with g_update=False (attention.py:155): geometry' = swish(rbf(d) @ Wf + bf) * w is
+ * recomputed per layer from pair_d / pair_w; proj needs only its query block.  Inference only. */
+int scann_la_forward_noupdate_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                                 const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
+                                 const int32_t* pair_j, const float* x, const float* proj, const float* pair_d,
+                                 const float* pair_w, const float* centers, const float* Wf, const float* bf,
+                                 const float* Wk, const float* bk, const float* gamma, const float* beta,
+                                 float* ctx_pre, float* out, float* attn, void* stream);
 /* Reverse-mode of the above (TF autodiff inside keras fit, scann_model.py:232-241).  d_ctx is the
  * gradient w.r.t. the pre-LN context; dq/s_pre are written for atoms with pairs, t_scatter /
  * dx_scatter are accumulated with atomics (pre-zero them); wpart: grid*2*128*128 floats. */

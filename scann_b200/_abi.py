@@ -35,6 +35,7 @@ PROTOTYPES = {
     "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
     "scann_la_forward_tc": (ci, [ci] + [vp] * 23 + [vp]),
+    "scann_la_forward_noupdate_tc": (ci, [ci] + [vp] * 21 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),

@@ -223,6 +223,8 @@ struct LaAttnArgs {
     float* out;              // [R,128]
     float* attn;             // [rows,8] nullable
     float* k_out;            // [rows,128] nullable (keys, saved for backward)
+    // g_update = False (attention.py:155): g' = swish(rbf(d) @ Wf[20,128] + bf) * w, computed on the fly
+    const float* pair_d; const float* pair_w; const float* centers; const float* Wf; const float* bf;
 };
 
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const LaAttnArgs a) {
@@ -261,8 +263,33 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
                 xv[i] = gv[i];
                 if (pc[i] >= 0) {
                     const int j = a.pair_j[rowbase + r];
-                    gv[i] = ld4(a.g_new + (rowbase + r) * SCANN_D + lane * 4);
+                    if (a.g_new) gv[i] = ld4(a.g_new + (rowbase + r) * SCANN_D + lane * 4);
                     xv[i] = ld4(a.x + (size_t)j * SCANN_D + lane * 4);
+                }
+            }
+            if (!a.g_new) {
+                // SCANN without geometry update: the 20 Gaussians of the distance are computed by lanes
+                // 0..19 and broadcast; Wf (10 KB) is read through L1
+                const float cen = lane < SCANN_RBF ? __ldg(a.centers + lane) : 0.f;
+                const float4 bfv = ldg4(a.bf + lane * 4);
+#pragma unroll
+                for (int i = 0; i < LTC_RPW; ++i) {
+                    const int r = warp + LTC_WARPS * i;
+                    float d = 0.f, wgt = 0.f;
+                    if (pc[i] >= 0) { d = a.pair_d[rowbase + r]; wgt = a.pair_w[rowbase + r]; }
+                    const float df = d - cen;
+                    const float rb = expf(-(df * df) / 0.25f);
+                    float4 acc = bfv;
+#pragma unroll
+                    for (int k = 0; k < SCANN_RBF; ++k) {
+                        const float rk = __shfl_sync(0xffffffffu, rb, k);
+                        const float4 wv = ldg4(a.Wf + k * SCANN_D + lane * 4);
+                        acc.x = fmaf(rk, wv.x, acc.x); acc.y = fmaf(rk, wv.y, acc.y);
+                        acc.z = fmaf(rk, wv.z, acc.z); acc.w = fmaf(rk, wv.w, acc.w);
+                    }
+                    gv[i] = pc[i] >= 0 ? make_float4(swish_f(acc.x) * wgt, swish_f(acc.y) * wgt, swish_f(acc.z) * wgt,
+                                                     swish_f(acc.w) * wgt)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
 #pragma unroll
@@ -367,9 +394,33 @@ extern "C" int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_
     LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
     la_geom_fwd_tc_kernel<<<grid, LTC_THREADS, LA_GEOM_SMEM, (cudaStream_t)stream>>>(ga);
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out};
+                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr};
     la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
     return scann_check_launch("scann_la_forward_tc");
+}
+
+// LocalAttention.call with g_update = False (attention.py:155-216): neighbor_geometry' =
+// swish(rbf(distance) @ Wf + bf) * weight is recomputed per layer from the 8 bytes/pair of raw geometry;
+// proj needs only its query block (columns 256..383).  Inference path (no saves for backward).
+extern "C" int scann_la_forward_noupdate_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0,
+                                            const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
+                                            const int32_t* pair_c, const int32_t* pair_j, const float* x,
+                                            const float* proj, const float* pair_d, const float* pair_w,
+                                            const float* centers, const float* Wf, const float* bf, const float* Wk,
+                                            const float* bk, const float* gamma, const float* beta, float* ctx_pre,
+                                            float* out, float* attn, void* stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)LA_ATTN_SMEM);
+        if (e != cudaSuccess) { scann_set_error("la_forward_noupdate_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    if (grid <= 0) return 0;
+    LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
+                  ctx_pre, out, attn, nullptr, pair_d, pair_w, centers, Wf, bf};
+    la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
+    return scann_check_launch("scann_la_forward_noupdate_tc");
 }
 
 extern "C" int scann_debug_clocks(long long* host_out32) {

@@ -49,10 +49,6 @@ class Engine:
     def __init__(self, spec: ModelSpec, arena: Optional[np.ndarray] = None, device: Optional[torch.device] = None,
                  seed: int = 1):
         check_kernel_support(spec)
-        if not spec.g_update:
-            raise NotImplementedError("g_update=False (SCANN without geometry update) is not on the accelerated path yet")
-        if spec.use_ring:
-            raise NotImplementedError("use_ring=True is not on the accelerated path yet")
         self.sm_count = _abi.require_gpu()
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.spec = spec
@@ -206,6 +202,10 @@ class Engine:
         put(b.nmask, nmask_in, "neighbor_mask")
         put(b.weight, inputs["neighbor_weight"], "neighbor_weight")
         put(b.dist, inputs["neighbor_distance"], "neighbor_distance")
+        if self.spec.use_ring:
+            if b.ring is None:
+                b.ring = torch.zeros(b.R * 2, dtype=torch.float32, device=dev)
+            put(b.ring, inputs["ring_aromatic"], "ring_aromatic")
         if plan:
             self._plan(b)
         return b
@@ -224,6 +224,7 @@ class Engine:
         b.weight = torch.zeros(b.R * N, **f32)
         b.dist = torch.zeros(b.R * N, **f32)
         b.target = torch.zeros(B, **f32)
+        b.ring = None
         b.cnt = torch.empty(b.R, **i32)
         b.rowptr = torch.empty(b.R, **i32)
         b.tile_a0 = torch.empty(tile_cap, **i32)
@@ -277,7 +278,7 @@ class Engine:
         f = dict(dtype=torch.float32, device=dev)
         ws = {}
         nsave = L + 1 if training else 2
-        ws["g"] = [torch.empty(rows, D, **f) for _ in range(nsave)]
+        ws["g"] = [torch.empty(rows, D, **f) for _ in range(nsave)] if self.spec.g_update else []
         ws["x"] = [torch.empty(R, D, **f) for _ in range(L + 1 if training else 2)]
         nl = L if training else 1
         ws["proj"] = [torch.empty(R, 3 * D, **f) for _ in range(nl)]
@@ -333,35 +334,63 @@ class Engine:
         L, R = sp.n_attention, b.R
         xs, gs = ws["x"], ws["g"]
         E = sp.embedding_dim
-        check(lib.scann_embed_forward(_p(b.atomic), 0, R, E, sp.n_atoms, self.w("embed_atom/embeddings"), 0, 0,
+        if training and (not sp.g_update or sp.use_ring):
+            raise NotImplementedError("training is accelerated for g_update=True, use_ring=False models only; "
+                                      "g_update=False / use_ring=True run the inference path")
+        ring = sp.use_ring
+        check(lib.scann_embed_forward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
+                                      self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
+                                      self.w("extra_embed/bias") if ring else 0,
                                       self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
                                       _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status), st), "embed_forward")
-        check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
-                                          _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
-                                          self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
-                                          self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
-        self.launches += 2
+        self.launches += 1
+        if sp.g_update:
+            check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+                                              _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
+                                              self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
+                                              self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
+            self.launches += 1
         for l in range(L):
             la = layer_name("local_attention", l)
             rn = layer_name("residual_norm", l)
             li = l if training else 0
             x_in = xs[l] if training else xs[l % 2]
             x_out = xs[l + 1] if training else xs[(l + 1) % 2]
-            g_in = gs[l] if training else gs[l % 2]
-            g_out = gs[l + 1] if training else gs[(l + 1) % 2]
             proj, h, h1 = ws["proj"][li], ws["h"][li], ws["h1"][li]
             fg = f"{la}/filter_geo/kernel"
-            # per-atom projections [x@W1+bf | x@W3 | x@Wq+bq]
-            self._dense([_p(x_in)], D, [self.w(fg, 0), self.w(fg, 2 * D * D), self.w(f"{la}/query/kernel")],
-                        [self.w(f"{la}/filter_geo/bias"), 0, self.w(f"{la}/query/bias")], 1, 3, R, _p(proj), 3 * D)
             ctxpre = ws["ctxpre"][l] if training else None
             out = h if sp.use_attn_norm else x_out
-            check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
-                                              self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), st), "la_nopair")
             attn = None
             if attn_out is not None:
                 attn = torch.zeros(b.tile_cap * TILE, 8, dtype=torch.float32, device=self.device)
                 attn_out.append(attn)
+            if not sp.g_update:
+                # SCANN without geometry update (attention.py:155): only the query block of proj is needed
+                self._dense([_p(x_in)], D, [self.w(f"{la}/query/kernel")], [self.w(f"{la}/query/bias")], 1, 1, R,
+                            _p(proj, 2 * D), 3 * D)
+                check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
+                                                  self.w(f"{la}/layer_norm/beta"), 0, _p(out), st), "la_nopair")
+                check(lib.scann_la_forward_noupdate_tc(
+                    self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
+                    _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d), self.w(fg),
+                    self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), st),
+                    "la_forward_noupdate_tc")
+                self.launches += 2
+                if sp.use_attn_norm:
+                    self._dense([_p(h)], D, [self.w(f"{rn}/dense/kernel")], [self.w(f"{rn}/dense/bias")], 1, 1, R,
+                                _p(h1), D, mode=1)
+                    self._dense([_p(h1)], D, [self.w(f"{rn}/dense_1/kernel")], [self.w(f"{rn}/dense_1/bias")], 1, 1, R,
+                                _p(x_out), D, mode=3, resid=h, gamma=self.w(f"{rn}/layer_norm/gamma"),
+                                beta=self.w(f"{rn}/layer_norm/beta"))
+                continue
+            g_in = gs[l] if training else gs[l % 2]
+            g_out = gs[l + 1] if training else gs[(l + 1) % 2]
+            # per-atom projections [x@W1+bf | x@W3 | x@Wq+bq]
+            self._dense([_p(x_in)], D, [self.w(fg, 0), self.w(fg, 2 * D * D), self.w(f"{la}/query/kernel")],
+                        [self.w(f"{la}/filter_geo/bias"), 0, self.w(f"{la}/query/bias")], 1, 3, R, _p(proj), 3 * D)
+            check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
+                                              self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), st), "la_nopair")
             self._ev("la_forward", True)
             la_args = (self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                        _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),

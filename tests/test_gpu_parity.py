@@ -201,6 +201,24 @@ def test_ga_norm_false_fullerene_config():
     assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= ga_tolerance(spec, lay, arena, inputs)
 
 
+def test_scann_without_geometry_update_and_ring_features():
+    """model_ptgp.yaml family: g_update=False (attention.py:155) + use_ring=True (scann_model.py:367-371).
+    The yaml lacks g_update / gaussian_d (KeyError in the reference as shipped), so they are supplied."""
+    cfg = get_config("ptgp")
+    cfg["model"].update(g_update=False, gaussian_d=4.0, n_attention=3)
+    spec = model_spec(cfg)
+    lay = ParamLayout(spec)
+    arena = lay.randomize_arena(12)
+    inputs, target = make_batch("ptgp", 4, B=2, use_ring=True)
+    kw = dict(oracle_kwargs(spec), use_ring=True)
+    y_ref, ga_ref = O.predict(lay.to_dict(arena), inputs, **kw)
+    eng, b, y, ga = run_forward(spec, arena, inputs)
+    assert rel(y, y_ref.ravel()) <= TOL_OUT
+    assert rel(ga, ga_ref[..., 0]) <= TOL_OUT
+    with pytest.raises(NotImplementedError):              # training of this variant is not accelerated yet
+        eng.forward(b, training=True)
+
+
 def test_malformed_input_is_reported():
     from scann_b200._abi import ScannAbiError
     spec, lay, arena = small("qm9", L=1)
