@@ -138,13 +138,20 @@ int scann_la_backward(int grid, const int32_t* ntiles, const int32_t* tile_a0, c
                       float* dbeta_g, float* dbk, void* stream);
 /* Same backward on the tcgen05 tensor cores (three kernels: attention, geometry, pair weight gradients).
  * kbuf / prebuf: in = keys / filter_geo pre-activation saved by scann_la_forward_tc, out = d_k / d_pre.
- * dg: gradient w.r.t. g' from the next layer (dg_has_up != 0, updated in place) or scratch. */
+ * dg: gradient w.r.t. g' from the next layer (dg_has_up != 0, updated in place) or scratch.
+ * Two kernels (attention, geometry); the pair weight gradients are scann_la_wgrad_tc. */
 int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                          const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
                          const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
                          float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
                          float* dg, int dg_has_up, float* dg_out, float* dq, float* s_pre, float* t_scatter,
                          float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream);
+/* Pair weight gradients of one layer (3xTF32, MN-major operands) into wpart[grid][2][128][128]:
+ * slot 0 = (x[j]*g')^T d_k (key/kernel), slot 1 = g^T d_pre (filter_geo rows 128..255).  Needs the d_k /
+ * d_pre that scann_la_backward_tc left in kbuf / prebuf; off the critical path (side stream). */
+int scann_la_wgrad_tc(int grid, const int32_t* ntiles, const int32_t* pair_c, const int32_t* pair_j, const float* x,
+                      const float* g_in, const float* g_new, const float* dk, const float* dpre, float* wpart,
+                      void* stream);
 /* dWk += sum_cta wpart[cta][0] ; dW2 += sum_cta wpart[cta][1]  (per-CTA partial weight gradients). */
 int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2, void* stream);
 

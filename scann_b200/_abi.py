@@ -38,6 +38,7 @@ PROTOTYPES = {
     "scann_la_forward_noupdate_tc": (ci, [ci] + [vp] * 21 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
+    "scann_la_wgrad_tc": (ci, [ci] + [vp] * 9 + [vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

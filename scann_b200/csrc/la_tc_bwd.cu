@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_wgrad_tc_kernel(const LaWgr
 // kbuf / prebuf: in = keys / filter_geo pre-activation saved by scann_la_forward_tc, out = d_k / d_pre.
 // dg: gradient w.r.t. g' from the next layer (dg_has_up != 0) or scratch that is overwritten.
 // s_pre is written for atoms with pairs; t_scatter / dx_scatter are accumulated (pre-zero them).
-// Weight gradients land in wpart[grid][2][128][128] (reduce with scann_la_wpart_reduce).
+// The pair weight gradients are a separate call (scann_la_wgrad_tc); wpart is unused here.
 extern "C" int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                                     const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
                                     const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
@@ -581,8 +581,6 @@ extern "C" int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)LA_GEOM_BWD_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(la_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_WGRAD_SMEM);
         if (e != cudaSuccess) { scann_set_error("la_backward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
         configured = true;
     }
@@ -594,9 +592,27 @@ extern "C" int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g};
     la_geom_bwd_tc_kernel<<<grid, LTC_THREADS, LA_GEOM_BWD_SMEM, st>>>(gb);
-    LaWgradArgs w0{ntiles, pair_c, pair_j, x, g_new, kbuf, 0, wpart};
-    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w0);
-    LaWgradArgs w1{ntiles, pair_c, pair_j, x, g_in, prebuf, 1, wpart};
-    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w1);
     return scann_check_launch("scann_la_backward_tc");
+}
+
+// Pair weight gradients of one LocalAttention layer into wpart[grid][2][128][128] (off the critical path of
+// the backward chain: may run on a side stream once scann_la_backward_tc of the layer has finished):
+//   wpart[.][0] = sum (x[j]*g')^T d_k (-> key/kernel),  wpart[.][1] = sum g^T d_pre (-> filter_geo rows 128..255)
+extern "C" int scann_la_wgrad_tc(int grid, const int32_t* ntiles, const int32_t* pair_c, const int32_t* pair_j,
+                                 const float* x, const float* g_in, const float* g_new, const float* dk,
+                                 const float* dpre, float* wpart, void* stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(la_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)LA_WGRAD_SMEM);
+        if (e != cudaSuccess) { scann_set_error("la_wgrad_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+        configured = true;
+    }
+    if (grid <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    LaWgradArgs w0{ntiles, pair_c, pair_j, x, g_new, dk, 0, wpart};
+    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w0);
+    LaWgradArgs w1{ntiles, pair_c, pair_j, x, g_in, dpre, 1, wpart};
+    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w1);
+    return scann_check_launch("scann_la_wgrad_tc");
 }

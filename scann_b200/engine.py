@@ -94,6 +94,8 @@ class Engine:
         self.tc_dense = eng != "simt" and os.environ.get("SCANN_DENSE", "tc") == "tc"
         self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
         self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
+        self.use_side_stream = os.environ.get("SCANN_SIDE_STREAM", "1") == "1"
+        self.side_stream = torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -296,9 +298,11 @@ class Engine:
             ws["ctxg"] = torch.empty(b.B, D, **f)
             ws["tb"] = torch.empty(b.B, D, **f)
             # backward temporaries
-            for k in ("dx", "d_v2", "d_t1", "d_h", "d_ctx", "dq", "d_ta"):
+            for k in ("dx", "d_h", "d_ctx", "d_ta"):
                 ws[k] = torch.empty(R, D, **f)
-            ws["scat"] = torch.empty(3, R, D, **f)           # s_pre, t_scatter, dx_scatter (zeroed together)
+            for k in ("d_v2", "d_t1", "dq"):                 # read by the side-stream weight-gradient kernels
+                ws[k] = [torch.empty(R, D, **f) for _ in range(L)]
+            ws["scat"] = [torch.empty(3, R, D, **f) for _ in range(L)]   # s_pre, t_scatter, dx_scatter per layer
             ws["dg"] = [torch.empty(rows, D, **f) for _ in range(2)]
             ws["d_qk"] = torch.empty(R, 2 * D, **f)
             ws["d_tb"] = torch.empty(b.B, D, **f)
@@ -432,10 +436,31 @@ class Engine:
     # ------------------------------------------------------------------ backward
     def backward(self, b: Batch, target: torch.Tensor) -> None:
         """Accumulates G = sum_b (y_b - t_b) dy_b/dtheta into the (pre-zeroed) gradient arena and
-        the SSE into its tail.  ``forward(b, training=True)`` must have run on the same batch."""
+        the SSE into its tail.  ``forward(b, training=True)`` must have run on the same batch.
+
+        The chain of input gradients (dense_tc / LayerNorm backward / local-attention backward) is the
+        critical path and runs on the current stream; every weight-gradient kernel only feeds the
+        optimiser, so they are issued on a side stream (fork / join through events, captured into the
+        same CUDA graph) and overlap the next layer's chain.  Buffers read by the side stream are
+        per layer."""
         sp, st = self.spec, self._stream()
         ws = self._workspace(b, True)
         L, R, n = sp.n_attention, b.R, self.layout.total
+        main = torch.cuda.current_stream(self.device)
+        side = self.side_stream if self.use_side_stream else main
+        sst = side.cuda_stream
+
+        def fork():                      # side stream may start once everything issued so far is done
+            if side is not main:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+
+        def wgrad(A, lda, G, ldg, kblk, nblk, rows, dW, db):
+            check(lib.scann_dense_wgrad(ptr_array(A), lda, ptr_array(G), ldg, kblk, nblk, rows, ptr_array(dW),
+                                        ptr_array(db) if db else None, sst), "dense_wgrad")
+            self.launches += 1
+
         check(lib.scann_transpose_blocks(_p(self.params), _p(self.paramsT), _p(self.tblocks), self.tblocks.numel(), st),
               "transpose_blocks")
         check(lib.scann_rmse_prepare(_p(ws["y"]), _p(target), b.B, _p(ws["dy"]), _p(self.grads, n), st), "rmse_prepare")
@@ -445,45 +470,43 @@ class Engine:
                                          self.gw("predict_property/kernel"), self.gw("predict_property/bias"), st),
               "ga_head_backward")
         self.launches += 3
-        self._wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
-                    [self.gw("bf_property/bias")])
         dqk = ws["d_qk"]
-        self._wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
-                    [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
-                    [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
         self._dense([_p(dqk), _p(dqk, D)], 2 * D,
                     [self.wT("global_attention/query/kernel"), self.wT("global_attention/key/kernel")], None, 2, 1, R,
                     _p(ws["d_ta"]), D, mode=2, pre_in=ws["ta"])
-        self._wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")],
-                    [self.gw("after_Lc/bias")])
         dx = ws["dx"]
         self._dense([_p(ws["d_ta"])], D, [self.wT("after_Lc/kernel")], None, 1, 1, R, _p(dx), D)
+        fork()
+        wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
+              [self.gw("bf_property/bias")])
+        wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
+              [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
+              [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
+        wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")], [self.gw("after_Lc/bias")])
         dg_up = None
         for l in range(L - 1, -1, -1):
             la = layer_name("local_attention", l)
             rn = layer_name("residual_norm", l)
             fg = f"{la}/filter_geo/kernel"
+            d_v2, d_t1, dq = ws["d_v2"][l], ws["d_t1"][l], ws["dq"][l]
             if sp.use_attn_norm:
                 check(lib.scann_layernorm_backward(_p(dx), _p(ws["v2"][l]), self.w(f"{rn}/layer_norm/gamma"), R,
-                                                   _p(ws["d_v2"]), 0, D, self.gw(f"{rn}/layer_norm/gamma"),
+                                                   _p(d_v2), 0, D, self.gw(f"{rn}/layer_norm/gamma"),
                                                    self.gw(f"{rn}/layer_norm/beta"), st), "ln_bwd")
-                self._wgrad([_p(ws["h1"][l])], D, [_p(ws["d_v2"])], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
-                            [self.gw(f"{rn}/dense_1/bias")])
-                self._dense([_p(ws["d_v2"])], D, [self.wT(f"{rn}/dense_1/kernel")], None, 1, 1, R, _p(ws["d_t1"]), D,
+                self._dense([_p(d_v2)], D, [self.wT(f"{rn}/dense_1/kernel")], None, 1, 1, R, _p(d_t1), D,
                             mode=2, pre_in=ws["t1"][l])
-                self._wgrad([_p(ws["h"][l])], D, [_p(ws["d_t1"])], D, 1, 1, R, [self.gw(f"{rn}/dense/kernel")],
-                            [self.gw(f"{rn}/dense/bias")])
-                self._dense([_p(ws["d_t1"])], D, [self.wT(f"{rn}/dense/kernel")], None, 1, 1, R, _p(ws["d_h"]), D,
-                            resid=ws["d_v2"])
+                self._dense([_p(d_t1)], D, [self.wT(f"{rn}/dense/kernel")], None, 1, 1, R, _p(ws["d_h"]), D,
+                            resid=d_v2)
                 d_h = ws["d_h"]
                 self.launches += 1
             else:
                 d_h = dx
             check(lib.scann_layernorm_backward(_p(d_h), _p(ws["ctxpre"][l]), self.w(f"{la}/layer_norm/gamma"), R,
-                                               _p(ws["d_ctx"]), _p(ws["dq"]), D, self.gw(f"{la}/layer_norm/gamma"),
+                                               _p(ws["d_ctx"]), _p(dq), D, self.gw(f"{la}/layer_norm/gamma"),
                                                self.gw(f"{la}/layer_norm/beta"), st), "ln_bwd")
-            ws["scat"].zero_()
-            s_pre, t_sc, dx_sc = ws["scat"][0], ws["scat"][1], ws["scat"][2]
+            scat = ws["scat"][l]
+            scat.zero_()
+            s_pre, t_sc, dx_sc = scat[0], scat[1], scat[2]
             dg_out = ws["dg"][(L - l) % 2]
             self._ev("la_backward", True)
             if self.tc_la_bwd:
@@ -494,31 +517,44 @@ class Engine:
                                                _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
                                                self.wT(f"{la}/key/kernel"), self.w(f"{la}/layer_norm_g/gamma"),
                                                _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
-                                               _p(ws["dq"]), _p(s_pre), _p(t_sc), _p(dx_sc), _p(ws["wpart"]),
+                                               _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc), 0,
                                                self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
                                                self.gw(f"{la}/key/bias"), st), "la_backward_tc")
-                self.launches += 3
+                self.launches += 2
             else:
-              if True:
                 check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                                             _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
                                             _p(ws["g"][l]), self.w(fg, D * D), self.w(f"{la}/key/kernel"),
                                             self.wT(fg, D * D), self.wT(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                                             self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
-                                            _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(ws["dq"]), _p(s_pre), _p(t_sc),
+                                            _p(ws["d_ctx"]), _p(dg_up), _p(dg_out), _p(dq), _p(s_pre), _p(t_sc),
                                             _p(dx_sc), _p(ws["wpart"]),
                                             self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
                                             self.gw(f"{la}/key/bias"), st), "la_backward")
+                self.launches += 1
             self._ev("la_backward", False)
-            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, self.gw(f"{la}/key/kernel"),
-                                            self.gw(fg, D * D), st), "la_wpart_reduce")
-            self.launches += 4
-            self._wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(ws["dq"])], D, 1, 3, R,
-                        [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
-                        [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
-            self._dense([_p(s_pre), _p(t_sc), _p(ws["dq"])], D,
+            # next link of the critical path: gradient w.r.t. the layer input x_l
+            self._dense([_p(s_pre), _p(t_sc), _p(dq)], D,
                         [self.wT(fg, 0), self.wT(fg, 2 * D * D), self.wT(f"{la}/query/kernel")], None, 3, 1, R, _p(dx),
                         D, resid=dx_sc)
+            # ---- weight gradients of this layer (side stream)
+            fork()
+            if self.tc_la_bwd:
+                check(lib.scann_la_wgrad_tc(self.la_grid, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
+                                            _p(ws["g"][l]), _p(ws["g"][l + 1]), _p(ws["kk"][l]), _p(ws["pre"][l]),
+                                            _p(ws["wpart"]), sst), "la_wgrad_tc")
+                self.launches += 2
+            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, self.gw(f"{la}/key/kernel"),
+                                            self.gw(fg, D * D), sst), "la_wpart_reduce")
+            self.launches += 1
+            if sp.use_attn_norm:
+                wgrad([_p(ws["h1"][l])], D, [_p(d_v2)], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
+                      [self.gw(f"{rn}/dense_1/bias")])
+                wgrad([_p(ws["h"][l])], D, [_p(d_t1)], D, 1, 1, R, [self.gw(f"{rn}/dense/kernel")],
+                      [self.gw(f"{rn}/dense/bias")])
+            wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(dq)], D, 1, 3, R,
+                  [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
+                  [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
             dg_up = dg_out
         check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                            _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
@@ -532,6 +568,10 @@ class Engine:
                                        self.gw("embed_atom/embeddings"), 0, 0, self.gw("dense_embed/kernel"),
                                        self.gw("dense_embed/bias"), st), "embed_backward")
         self.launches += 4
+        if side is not main:             # join: the optimiser needs every weight gradient
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     # ------------------------------------------------------------------ optimiser
     def _set_adam(self, lr: float, batch_global: int, decay: float = 1e-5, b1=0.9, b2=0.999, eps=1e-7):
