@@ -185,6 +185,8 @@ int scann_tc_probe(const float* A, const float* W, float* D, int layout, int npr
 int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream);
 /* Phase timestamps (clock64) of CTA 0 of the last la_geom_fwd_tc launch; host_out32: 32 int64 (HOST). */
 int scann_debug_clocks(long long* host_out32);
+/* Same for CTA (0,0) of the last dense_tc launch; host_out16: 16 int64 (HOST). */
+int scann_debug_clocks_dense(long long* host_out16);
 
 #ifdef __cplusplus
 }

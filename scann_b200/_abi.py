@@ -48,6 +48,7 @@ PROTOTYPES = {
     "scann_tc_probe": (ci, [vp, vp, vp, ci, ci, vp]),
     "scann_tc_time": (ci, [vp, ci, ci, ci, vp]),
     "scann_debug_clocks": (ci, [vp]),
+    "scann_debug_clocks_dense": (ci, [vp]),
 }
 
 

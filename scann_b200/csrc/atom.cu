@@ -149,6 +149,28 @@ __global__ void __launch_bounds__(128) embed_bwd_final_kernel(int E, int n_atoms
 // Geometry initialisation (g_update): g0 = swish(rbf_d Wd + bd) * swish(rbf_w Ww + bw)
 // rbf_x[k] = exp(-(x - c_k)^2 / 0.25)                 (scann_model.py:378-389, custom_layers.py:55-65)
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF + 1], int* s_c, float* s_d, float* s_w,
+                                               const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
+                                               const float* __restrict__ pair_w, const float* __restrict__ cd,
+                                               const float* __restrict__ cw, size_t base) {
+    // per-tile pair data -> smem (one coalesced pass), then the 2 x 20 Gaussians of every row
+    if (threadIdx.x < SCANN_TILE) {
+        const int c = pair_c[base + threadIdx.x];
+        s_c[threadIdx.x] = c;
+        s_d[threadIdx.x] = c >= 0 ? pair_d[base + threadIdx.x] : 0.f;
+        s_w[threadIdx.x] = c >= 0 ? pair_w[base + threadIdx.x] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SCANN_TILE * 2 * SCANN_RBF; i += blockDim.x) {
+        const int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
+        const float x = (k < SCANN_RBF) ? s_d[row] : s_w[row];
+        const float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
+        const float df = x - c;
+        s_rbf[row][k] = s_c[row] >= 0 ? expf(-(df * df) / 0.25f) : 0.f;
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __restrict__ ntiles,
                                                             const int32_t* __restrict__ pair_c,
                                                             const float* __restrict__ pair_d,
@@ -158,6 +180,8 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
                                                             const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ g0) {
     __shared__ float s_rbf[SCANN_TILE][2 * SCANN_RBF + 1];
+    __shared__ int s_c[SCANN_TILE];
+    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
     float wd[SCANN_RBF], ww[SCANN_RBF];
 #pragma unroll
@@ -170,30 +194,16 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t base = (size_t)t * SCANN_TILE;
         __syncthreads();
-        for (int i = threadIdx.x; i < SCANN_TILE * 2 * SCANN_RBF; i += blockDim.x) {
-            int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
-            float v = 0.f;
-            if (pair_c[base + row] >= 0) {
-                float x = (k < SCANN_RBF) ? pair_d[base + row] : pair_w[base + row];
-                float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
-                float df = x - c;
-                v = expf(-(df * df) / 0.25f);
-            }
-            s_rbf[row][k] = v;
-        }
-        __syncthreads();
+        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
+#pragma unroll 4
         for (int row = half; row < SCANN_TILE; row += 2) {
-            float out = 0.f;
-            if (pair_c[base + row] >= 0) {
-                float a = bdn, b = bwn;
+            float a = bdn, b = bwn;
 #pragma unroll
-                for (int k = 0; k < SCANN_RBF; ++k) {
-                    a = fmaf(s_rbf[row][k], wd[k], a);
-                    b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
-                }
-                out = swish_f(a) * swish_f(b);
+            for (int k = 0; k < SCANN_RBF; ++k) {
+                a = fmaf(s_rbf[row][k], wd[k], a);
+                b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
             }
-            g0[(base + row) * SCANN_D + n] = out;
+            g0[(base + row) * SCANN_D + n] = s_c[row] >= 0 ? swish_f(a) * swish_f(b) : 0.f;
         }
     }
 }
@@ -210,6 +220,8 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
                                                             float* __restrict__ dbd, float* __restrict__ dWw,
                                                             float* __restrict__ dbw) {
     __shared__ float s_rbf[SCANN_TILE][2 * SCANN_RBF + 1];
+    __shared__ int s_c[SCANN_TILE];
+    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
     float wd[SCANN_RBF], ww[SCANN_RBF], gd[SCANN_RBF], gw[SCANN_RBF];
 #pragma unroll
@@ -225,35 +237,32 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t base = (size_t)t * SCANN_TILE;
         __syncthreads();
-        for (int i = threadIdx.x; i < SCANN_TILE * 2 * SCANN_RBF; i += blockDim.x) {
-            int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
-            float v = 0.f;
-            if (pair_c[base + row] >= 0) {
-                float x = (k < SCANN_RBF) ? pair_d[base + row] : pair_w[base + row];
-                float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
-                float df = x - c;
-                v = expf(-(df * df) / 0.25f);
-            }
-            s_rbf[row][k] = v;
-        }
-        __syncthreads();
-        for (int row = half; row < SCANN_TILE; row += 2) {
-            if (pair_c[base + row] < 0) continue;
-            float a = bdn, b = bwn;
+        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
+        // the gradient rows of this thread's half are independent loads: keep 8 in flight
+        for (int r8 = half; r8 < SCANN_TILE; r8 += 16) {
+            float dv[8];
 #pragma unroll
-            for (int k = 0; k < SCANN_RBF; ++k) {
-                a = fmaf(s_rbf[row][k], wd[k], a);
-                b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
-            }
-            float d = dg0[(base + row) * SCANN_D + n];
-            float da = d * swish_f(b) * swish_grad_f(a);
-            float db = d * swish_f(a) * swish_grad_f(b);
-            gbd += da;
-            gbw += db;
+            for (int q = 0; q < 8; ++q) dv[q] = dg0[(base + r8 + 2 * q) * SCANN_D + n];
 #pragma unroll
-            for (int k = 0; k < SCANN_RBF; ++k) {
-                gd[k] = fmaf(s_rbf[row][k], da, gd[k]);
-                gw[k] = fmaf(s_rbf[row][SCANN_RBF + k], db, gw[k]);
+            for (int q = 0; q < 8; ++q) {
+                const int row = r8 + 2 * q;
+                if (s_c[row] < 0) continue;
+                float a = bdn, b = bwn;
+#pragma unroll
+                for (int k = 0; k < SCANN_RBF; ++k) {
+                    a = fmaf(s_rbf[row][k], wd[k], a);
+                    b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
+                }
+                const float sa = sigmoid_f(a), sb = sigmoid_f(b);
+                const float da = dv[q] * (b * sb) * (sa * (1.0f + a * (1.0f - sa)));
+                const float db = dv[q] * (a * sa) * (sb * (1.0f + b * (1.0f - sb)));
+                gbd += da;
+                gbw += db;
+#pragma unroll
+                for (int k = 0; k < SCANN_RBF; ++k) {
+                    gd[k] = fmaf(s_rbf[row][k], da, gd[k]);
+                    gw[k] = fmaf(s_rbf[row][SCANN_RBF + k], db, gw[k]);
+                }
             }
         }
     }

@@ -45,6 +45,18 @@ __device__ __forceinline__ void warp_sum2(float& a, float& b) {
     }
 }
 
+// Row-group mapping of the tensor-core epilogues: a warp step covers 4 rows, 8 lanes per row, lane l of a
+// row owns the four 16-byte chunks c4 = l + 8*it (it = 0..3), i.e. 16 of the 128 columns.  Per-row fixed
+// costs (index loads, reductions, addressing) are amortised over 16 elements per lane instead of 4; global
+// accesses stay fully coalesced (8 lanes x 16 B = one 128-byte line per row and instruction).
+__device__ __forceinline__ void oct_sum2(float& a, float& b) {      // sums over the 8 lanes of a row
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -17,6 +17,10 @@
 
 #define DTC_THREADS 256
 
+// phase timestamps of CTA (0,0) (clock64), read back with scann_debug_clocks_dense: development aid
+__device__ long long g_dbg_clk_dense[16];
+#define DCLK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clk_dense[i] = clock64(); } while (0)
+
 struct DenseTcArgs {
     const float* A[3];
     int lda;
@@ -41,6 +45,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = blockIdx.x * 128, nb = blockIdx.y;
+    DCLK(0);
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     tc_fence_before();
@@ -51,6 +56,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
     uint32_t phase = 0;
+    DCLK(1);
 
     for (int kb = 0; kb < a.kblk; ++kb) {
         // (b) activation tile: issue all global loads first (16 x LDG.128 in flight per thread)
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        if (kb == 0) DCLK(2);
         if (tid == 0) {
             tc_fence_after();
             const uint64_t dh = tc_desc_kmajor(smem_u32(sXhi), 0), dl = tc_desc_kmajor(smem_u32(sXlo), 0);
@@ -115,6 +122,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         phase ^= 1;
         tc_fence_after();
         __syncthreads();
+        if (kb == 0) DCLK(3);
     }
     // epilogue 1: D^T (lane = n, column = r) -> shared image S[r][n]  (S aliases the hi image)
     {
@@ -131,51 +139,90 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
     }
     tc_fence_before();
     __syncthreads();
+    DCLK(4);
     if (warp == 0) tmem_dealloc(tmem, 512);
-    // epilogue 2: one warp per row, lane = 4 consecutive columns
-    const int c0 = lane * 4;
-    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.bias[nb]) bias = ldg4(a.bias[nb] + c0);
-    float4 gam = bias, bet = bias;
-    if (a.mode == 3) { gam = ldg4(a.gamma + c0); bet = ldg4(a.beta + c0); }
-    // all global loads of the warp's 16 rows are issued before the first use (no 16-deep latency chain)
-    constexpr int RPW = 128 / (DTC_THREADS / 32);
-    float4 rv[RPW], pv[RPW];
+    DCLK(6);
+    // epilogue 2: row groups (4 rows per warp step, 8 lanes per row, 16 columns per lane)
+    const int l8 = lane & 7, rsub = lane >> 3;
+    float4 bias[4], gam[4], bet[4];
 #pragma unroll
-    for (int i = 0; i < RPW; ++i) {
-        const int r = r0 + warp + i * (DTC_THREADS / 32);
-        rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pv[i] = rv[i];
-        if (r < a.R) {
-            if (a.resid) rv[i] = ld4(a.resid + (size_t)r * a.ldres + nb * SCANN_D + c0);
-            if (a.mode == 2) pv[i] = ld4(a.pre_in + (size_t)r * a.ldc + nb * SCANN_D + c0);
-        }
+    for (int it = 0; it < 4; ++it) {
+        const int c0 = (l8 + 8 * it) * 4;
+        bias[it] = a.bias[nb] ? ldg4(a.bias[nb] + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gam[it] = a.mode == 3 ? ldg4(a.gamma + c0) : bias[it];
+        bet[it] = a.mode == 3 ? ldg4(a.beta + c0) : bias[it];
     }
+#pragma unroll 1
+    for (int step = 0; step < 128 / (DTC_THREADS / 32) / 4; ++step) {
+        const int rr = warp * (128 / (DTC_THREADS / 32)) + step * 4 + rsub, r = r0 + rr;
+        const bool ok = r < a.R;
+        float v[4][4];
 #pragma unroll
-    for (int i = 0; i < RPW; ++i) {
-        const int rr = warp + i * (DTC_THREADS / 32), r = r0 + rr;
-        const bool ok = r < a.R;                     // warp-uniform
-        float4 acc = *reinterpret_cast<const float4*>(sXhi + tc_off4(rr, lane));
-        float v[4] = {acc.x + bias.x + rv[i].x, acc.y + bias.y + rv[i].y, acc.z + bias.z + rv[i].z,
-                      acc.w + bias.w + rv[i].w};
+        for (int it = 0; it < 4; ++it) {
+            const int c4 = l8 + 8 * it, c0 = c4 * 4;
+            float4 acc = *reinterpret_cast<const float4*>(sXhi + tc_off4(rr, c4));
+            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.resid && ok) rv = ld4(a.resid + (size_t)r * a.ldres + nb * SCANN_D + c0);
+            v[it][0] = acc.x + bias[it].x + rv.x; v[it][1] = acc.y + bias[it].y + rv.y;
+            v[it][2] = acc.z + bias[it].z + rv.z; v[it][3] = acc.w + bias[it].w + rv.w;
+        }
         if (a.mode == 1) {
-            if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + nb * SCANN_D + c0, make_float4(v[0], v[1], v[2], v[3]));
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = swish_fast(v[j]);
+            for (int it = 0; it < 4; ++it) {
+                if (a.pre_out && ok)
+                    st4(a.pre_out + (size_t)r * a.ldc + nb * SCANN_D + (l8 + 8 * it) * 4,
+                        make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[it][q] = swish_fast(v[it][q]);
+            }
         } else if (a.mode == 2) {
-            v[0] *= swish_grad_fast(pv[i].x); v[1] *= swish_grad_fast(pv[i].y);
-            v[2] *= swish_grad_fast(pv[i].z); v[3] *= swish_grad_fast(pv[i].w);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) p = ld4(a.pre_in + (size_t)r * a.ldc + nb * SCANN_D + (l8 + 8 * it) * 4);
+                v[it][0] *= swish_grad_fast(p.x); v[it][1] *= swish_grad_fast(p.y);
+                v[it][2] *= swish_grad_fast(p.z); v[it][3] *= swish_grad_fast(p.w);
+            }
         } else if (a.mode == 3) {
-            if (a.pre_out && ok) st4(a.pre_out + (size_t)r * a.ldc + c0, make_float4(v[0], v[1], v[2], v[3]));
-            float mean = warp_sum(v[0] + v[1] + v[2] + v[3]) * (1.0f / SCANN_D);
-            float d0 = v[0] - mean, d1 = v[1] - mean, d2 = v[2] - mean, d3 = v[3] - mean;
-            float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / SCANN_D);
-            float inv = rsqrtf(var + SCANN_LN_EPS);
-            v[0] = d0 * inv * gam.x + bet.x; v[1] = d1 * inv * gam.y + bet.y;
-            v[2] = d2 * inv * gam.z + bet.z; v[3] = d3 * inv * gam.w + bet.w;
+            float s1 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                if (a.pre_out && ok)
+                    st4(a.pre_out + (size_t)r * a.ldc + (l8 + 8 * it) * 4, make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
+                s1 += v[it][0] + v[it][1] + v[it][2] + v[it][3];
+            }
+            // shifted one-pass moments: shift = mean of the row's first 16-column slice
+            const float sh = __shfl_sync(0xffffffffu, s1, lane & 24) * (1.0f / 16.0f);
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { v[it][q] -= sh; m1 += v[it][q]; m2 = fmaf(v[it][q], v[it][q], m2); }
+            oct_sum2(m1, m2);
+            m1 *= (1.0f / SCANN_D);
+            const float inv = rsqrtf(fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f) + SCANN_LN_EPS);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                v[it][0] = (v[it][0] - m1) * inv * gam[it].x + bet[it].x;
+                v[it][1] = (v[it][1] - m1) * inv * gam[it].y + bet[it].y;
+                v[it][2] = (v[it][2] - m1) * inv * gam[it].z + bet[it].z;
+                v[it][3] = (v[it][3] - m1) * inv * gam[it].w + bet[it].w;
+            }
         }
-        if (ok) st4(a.C + (size_t)r * a.ldc + nb * SCANN_D + c0, make_float4(v[0], v[1], v[2], v[3]));
+        if (ok) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+                st4(a.C + (size_t)r * a.ldc + nb * SCANN_D + (l8 + 8 * it) * 4,
+                    make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
+        }
     }
+    DCLK(5);
+}
+
+extern "C" int scann_debug_clocks_dense(long long* host_out16) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out16, g_dbg_clk_dense, sizeof(long long) * 16);
+    if (e != cudaSuccess) { scann_set_error("debug_clocks_dense: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
 }
 
 extern "C" int scann_dense_forward_tc(const float* const* A, int lda, const float* const* W, const float* const* bias,

@@ -114,7 +114,6 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
     DBG_CLK(0);
     weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);
     DBG_CLK(1);
-    const float4 gam = ldg4(a.gamma_g + lane * 4), bet = ldg4(a.beta_g + lane * 4);
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t rowbase = (size_t)t * SCANN_TILE;
@@ -147,17 +146,21 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         }
         if (t == (int)blockIdx.x) DBG_CLK(3);
         // ---- while the tensor core works: indices and gathered projections of this warp's rows
-        int pc[LTC_RPW];
-        float4 p13[LTC_RPW];
+        // (row groups: 2 steps x 4 rows per warp, 8 lanes per row, 16 columns per lane)
+        const int l8 = lane & 7, rsub = lane >> 3;
+        int pc[2];
+        float4 p13[2][4];
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+        for (int sp = 0; sp < 2; ++sp) {
+            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            pc[sp] = a.pair_c[rowbase + r];
+            const int j = pc[sp] >= 0 ? a.pair_j[rowbase + r] : 0;
+            const int c = pc[sp] >= 0 ? pc[sp] : 0;
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) {
-            p13[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pc[i] >= 0) {
-                const int j = a.pair_j[rowbase + warp + LTC_WARPS * i];
-                p13[i] = f4add(ld4(a.proj + (size_t)pc[i] * 3 * SCANN_D + lane * 4),
-                               ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + lane * 4));
+            for (int it = 0; it < 4; ++it) {
+                const int c0 = (l8 + 8 * it) * 4;
+                p13[sp][it] = f4add(ld4(a.proj + (size_t)c * 3 * SCANN_D + c0),
+                                    ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + c0));
             }
         }
         if (t == (int)blockIdx.x) DBG_CLK(4);
@@ -171,34 +174,45 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         if (t == (int)blockIdx.x) DBG_CLK(6);
         // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) {
-            const int r = warp + LTC_WARPS * i;
-            const uint32_t off = tc_off4(r, lane);
-            float4 acc = *reinterpret_cast<const float4*>(sS + off);
-            float4 gh = *reinterpret_cast<const float4*>(sHi + off), gl = *reinterpret_cast<const float4*>(sLo + off);
-            float pre[4] = {acc.x + p13[i].x, acc.y + p13[i].y, acc.z + p13[i].z, acc.w + p13[i].w};
-            float g[4] = {gh.x + gl.x, gh.y + gl.y, gh.z + gl.z, gh.w + gl.w};
-            float z[4];
+        for (int sp = 0; sp < 2; ++sp) {
+            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            float z[4][4], pre[4][4];
+            float s1 = 0.f;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) z[q] = swish_fast(pre[q]) + g[q];
-            // one-pass moments around the lane's own partial mean (numerically safe: shifted data)
-            float s1 = z[0] + z[1] + z[2] + z[3];
-            float sh = __shfl_sync(0xffffffffu, s1, 0) * 0.25f;     // common shift ~ row mean estimate
-            float d0 = z[0] - sh, d1 = z[1] - sh, d2 = z[2] - sh, d3 = z[3] - sh;
-            float m1 = d0 + d1 + d2 + d3, m2 = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-            warp_sum2(m1, m2);
-            m1 *= (1.0f / SCANN_D);
-            float var = fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f);
-            float inv = rsqrtf(var + SCANN_LN_EPS);
-            z[0] = d0 - m1; z[1] = d1 - m1; z[2] = d2 - m1; z[3] = d3 - m1;
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
-            if (pc[i] >= 0) {
-                o = make_float4(z[0] * inv * gam.x + bet.x, z[1] * inv * gam.y + bet.y, z[2] * inv * gam.z + bet.z,
-                                z[3] * inv * gam.w + bet.w);
-                po = make_float4(pre[0], pre[1], pre[2], pre[3]);
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t off = tc_off4(r, l8 + 8 * it);
+                const float4 acc = *reinterpret_cast<const float4*>(sS + off);
+                const float4 gh = *reinterpret_cast<const float4*>(sHi + off), gl = *reinterpret_cast<const float4*>(sLo + off);
+                pre[it][0] = acc.x + p13[sp][it].x; pre[it][1] = acc.y + p13[sp][it].y;
+                pre[it][2] = acc.z + p13[sp][it].z; pre[it][3] = acc.w + p13[sp][it].w;
+                z[it][0] = swish_fast(pre[it][0]) + (gh.x + gl.x); z[it][1] = swish_fast(pre[it][1]) + (gh.y + gl.y);
+                z[it][2] = swish_fast(pre[it][2]) + (gh.z + gl.z); z[it][3] = swish_fast(pre[it][3]) + (gh.w + gl.w);
+                s1 += z[it][0] + z[it][1] + z[it][2] + z[it][3];
             }
-            st4(a.g_out + (rowbase + r) * SCANN_D + lane * 4, o);
-            if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + lane * 4, po);
+            // one-pass moments around a common shift (the first lane's partial mean)
+            const float sh = __shfl_sync(0xffffffffu, s1, lane & 24) * (1.0f / 16.0f);
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { z[it][q] -= sh; m1 += z[it][q]; m2 = fmaf(z[it][q], z[it][q], m2); }
+            oct_sum2(m1, m2);
+            m1 *= (1.0f / SCANN_D);
+            const float inv = rsqrtf(fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f) + SCANN_LN_EPS);
+            const bool ok = pc[sp] >= 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int c0 = (l8 + 8 * it) * 4;
+                const float4 gm = ldg4(a.gamma_g + c0), bt = ldg4(a.beta_g + c0);
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
+                if (ok) {
+                    o = make_float4((z[it][0] - m1) * inv * gm.x + bt.x, (z[it][1] - m1) * inv * gm.y + bt.y,
+                                    (z[it][2] - m1) * inv * gm.z + bt.z, (z[it][3] - m1) * inv * gm.w + bt.w);
+                    po = make_float4(pre[it][0], pre[it][1], pre[it][2], pre[it][3]);
+                }
+                st4(a.g_out + (rowbase + r) * SCANN_D + c0, o);
+                if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + c0, po);
+            }
         }
         __syncthreads();                 // images and S are rewritten by the next tile
         if (t == (int)blockIdx.x) DBG_CLK(7);
@@ -250,55 +264,64 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t rowbase = (size_t)t * SCANN_TILE;
-        int pc[LTC_RPW];
-        // ---- stage a = x[j] * g' (warp per row: coalesced row loads and gathers), hi/lo images
-        {
-            float4 gv[LTC_RPW], xv[LTC_RPW];
+        // row groups: 2 steps x 4 rows per warp, 8 lanes per row, 16 columns per lane
+        const int l8 = lane & 7, rsub = lane >> 3;
+        int pc[2];
+        // ---- stage a = x[j] * g' (coalesced row loads and gathers), hi/lo images
 #pragma unroll
-            for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+        for (int sp = 0; sp < 2; ++sp) {
+            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            pc[sp] = a.pair_c[rowbase + r];
+            const bool ok = pc[sp] >= 0;
+            const int j = ok ? a.pair_j[rowbase + r] : 0;
+            float4 gv[4], xv[4];
 #pragma unroll
-            for (int i = 0; i < LTC_RPW; ++i) {
-                const int r = warp + LTC_WARPS * i;
-                gv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                xv[i] = gv[i];
-                if (pc[i] >= 0) {
-                    const int j = a.pair_j[rowbase + r];
-                    if (a.g_new) gv[i] = ld4(a.g_new + (rowbase + r) * SCANN_D + lane * 4);
-                    xv[i] = ld4(a.x + (size_t)j * SCANN_D + lane * 4);
+            for (int it = 0; it < 4; ++it) {
+                const int c0 = (l8 + 8 * it) * 4;
+                gv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[it] = gv[it];
+                if (ok) {
+                    if (a.g_new) gv[it] = ld4(a.g_new + (rowbase + r) * SCANN_D + c0);
+                    xv[it] = ld4(a.x + (size_t)j * SCANN_D + c0);
                 }
             }
             if (!a.g_new) {
-                // SCANN without geometry update: the 20 Gaussians of the distance are computed by lanes
-                // 0..19 and broadcast; Wf (10 KB) is read through L1
-                const float cen = lane < SCANN_RBF ? __ldg(a.centers + lane) : 0.f;
-                const float4 bfv = ldg4(a.bf + lane * 4);
+                // SCANN without geometry update: g' = swish(rbf(d) @ Wf + bf) * w.  The 20 Gaussians of the
+                // row's distance are computed by its 8 lanes (3 each) and broadcast; Wf is read through L1
+                float d = 0.f, wgt = 0.f;
+                if (ok) { d = a.pair_d[rowbase + r]; wgt = a.pair_w[rowbase + r]; }
+                float rb[3];
 #pragma unroll
-                for (int i = 0; i < LTC_RPW; ++i) {
-                    const int r = warp + LTC_WARPS * i;
-                    float d = 0.f, wgt = 0.f;
-                    if (pc[i] >= 0) { d = a.pair_d[rowbase + r]; wgt = a.pair_w[rowbase + r]; }
-                    const float df = d - cen;
-                    const float rb = expf(-(df * df) / 0.25f);
-                    float4 acc = bfv;
-#pragma unroll
-                    for (int k = 0; k < SCANN_RBF; ++k) {
-                        const float rk = __shfl_sync(0xffffffffu, rb, k);
-                        const float4 wv = ldg4(a.Wf + k * SCANN_D + lane * 4);
-                        acc.x = fmaf(rk, wv.x, acc.x); acc.y = fmaf(rk, wv.y, acc.y);
-                        acc.z = fmaf(rk, wv.z, acc.z); acc.w = fmaf(rk, wv.w, acc.w);
-                    }
-                    gv[i] = pc[i] >= 0 ? make_float4(swish_f(acc.x) * wgt, swish_f(acc.y) * wgt, swish_f(acc.z) * wgt,
-                                                     swish_f(acc.w) * wgt)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int q = 0; q < 3; ++q) {
+                    const int k = l8 + 8 * q;
+                    const float df = d - (k < SCANN_RBF ? __ldg(a.centers + k) : 0.f);
+                    rb[q] = expf(-(df * df) / 0.25f);
                 }
+                float4 acc[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) acc[it] = ldg4(a.bf + (l8 + 8 * it) * 4);
+#pragma unroll
+                for (int k = 0; k < SCANN_RBF; ++k) {
+                    const float rk = __shfl_sync(0xffffffffu, rb[k >> 3], (lane & 24) | (k & 7));
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        const float4 wv = ldg4(a.Wf + k * SCANN_D + (l8 + 8 * it) * 4);
+                        acc[it].x = fmaf(rk, wv.x, acc[it].x); acc[it].y = fmaf(rk, wv.y, acc[it].y);
+                        acc[it].z = fmaf(rk, wv.z, acc[it].z); acc[it].w = fmaf(rk, wv.w, acc[it].w);
+                    }
+                }
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    gv[it] = ok ? make_float4(swish_f(acc[it].x) * wgt, swish_f(acc[it].y) * wgt,
+                                              swish_f(acc[it].z) * wgt, swish_f(acc[it].w) * wgt)
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int i = 0; i < LTC_RPW; ++i) {
-                const int r = warp + LTC_WARPS * i;
+            for (int it = 0; it < 4; ++it) {
                 float4 h, l;
-                tf32_split(gv[i].x * xv[i].x, h.x, l.x); tf32_split(gv[i].y * xv[i].y, h.y, l.y);
-                tf32_split(gv[i].z * xv[i].z, h.z, l.z); tf32_split(gv[i].w * xv[i].w, h.w, l.w);
-                const uint32_t off = tc_off4(r, lane);
+                tf32_split(gv[it].x * xv[it].x, h.x, l.x); tf32_split(gv[it].y * xv[it].y, h.y, l.y);
+                tf32_split(gv[it].z * xv[it].z, h.z, l.z); tf32_split(gv[it].w * xv[it].w, h.w, l.w);
+                const uint32_t off = tc_off4(r, l8 + 8 * it);
                 *reinterpret_cast<float4*>(sHi + off) = h;
                 *reinterpret_cast<float4*>(sLo + off) = l;
             }
@@ -311,26 +334,35 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
             issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
         }
         // ---- prefetch the queries of this warp's rows while the tensor core works
-        float4 qv[LTC_RPW];
+        float4 qv[2][4];
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) {
-            qv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pc[i] >= 0) qv[i] = ld4(a.proj + (size_t)pc[i] * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
-        }
+        for (int sp = 0; sp < 2; ++sp)
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                qv[sp][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (pc[sp] >= 0)
+                    qv[sp][it] = ld4(a.proj + (size_t)pc[sp] * 3 * SCANN_D + 2 * SCANN_D + (l8 + 8 * it) * 4);
+            }
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
         tmem_to_rows(t_dm, t_dc, sS, a.bk, warp, lane);          // keys k = a @ Wk + bk
         tc_fence_before();
         __syncthreads();
-        // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = 4 lanes)
+        // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = chunks 4h..4h+3 = 4 adjacent lanes)
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) {
-            const int r = warp + LTC_WARPS * i;
-            float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
-            float e = quad_sum(kv.x * qv[i].x + kv.y * qv[i].y + kv.z * qv[i].z + kv.w * qv[i].w) * 0.25f;
-            if ((lane & 3) == 0) Es[r * 8 + (lane >> 2)] = e;
-            if (a.k_out) st4(a.k_out + (rowbase + r) * SCANN_D + lane * 4, pc[i] >= 0 ? kv : make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int sp = 0; sp < 2; ++sp) {
+            const int r = warp * LTC_RPW + sp * 4 + rsub;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r, l8 + 8 * it));
+                const float4 q = qv[sp][it];
+                const float e = quad_sum(kv.x * q.x + kv.y * q.y + kv.z * q.z + kv.w * q.w) * 0.25f;
+                if ((l8 & 3) == 0) Es[r * 8 + 2 * it + (l8 >> 2)] = e;
+                if (a.k_out)
+                    st4(a.k_out + (rowbase + r) * SCANN_D + (l8 + 8 * it) * 4,
+                        pc[sp] >= 0 ? kv : make_float4(0.f, 0.f, 0.f, 0.f));
+            }
         }
         __syncthreads();
         // ---- per atom: softmax over its rows, context, residual q, LayerNorm (one warp per atom)

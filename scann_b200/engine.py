@@ -96,6 +96,7 @@ class Engine:
         self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
         self.use_side_stream = os.environ.get("SCANN_SIDE_STREAM", "1") == "1"
         self.side_stream = torch.cuda.Stream(device=self.device)
+        self._prep_event = None
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -302,7 +303,8 @@ class Engine:
                 ws[k] = torch.empty(R, D, **f)
             for k in ("d_v2", "d_t1", "dq"):                 # read by the side-stream weight-gradient kernels
                 ws[k] = [torch.empty(R, D, **f) for _ in range(L)]
-            ws["scat"] = [torch.empty(3, R, D, **f) for _ in range(L)]   # s_pre, t_scatter, dx_scatter per layer
+            ws["scat_all"] = torch.empty(L, 3, R, D, **f)    # s_pre, t_scatter, dx_scatter per layer, zeroed once
+            ws["scat"] = [ws["scat_all"][l] for l in range(L)]
             ws["dg"] = [torch.empty(rows, D, **f) for _ in range(2)]
             ws["d_qk"] = torch.empty(R, 2 * D, **f)
             ws["d_tb"] = torch.empty(b.B, D, **f)
@@ -461,15 +463,19 @@ class Engine:
                                         ptr_array(db) if db else None, sst), "dense_wgrad")
             self.launches += 1
 
-        check(lib.scann_transpose_blocks(_p(self.params), _p(self.paramsT), _p(self.tblocks), self.tblocks.numel(), st),
-              "transpose_blocks")
+        if side is not main and self._prep_event is not None:
+            main.wait_event(self._prep_event)        # transposed weights + zeroed scatter buffers are ready
+            self._prep_event = None
+        else:
+            self._backward_prep(ws, st)
+            ws["scat_all"].zero_()
         check(lib.scann_rmse_prepare(_p(ws["y"]), _p(target), b.B, _p(ws["dy"]), _p(self.grads, n), st), "rmse_prepare")
         check(lib.scann_ga_head_backward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                          self.wT("bf_property/kernel"), self.w("predict_property/kernel"),
                                          _p(ws["tb"]), _p(ws["dy"]), _p(ws["d_qk"]), _p(ws["d_tb"]),
                                          self.gw("predict_property/kernel"), self.gw("predict_property/bias"), st),
               "ga_head_backward")
-        self.launches += 3
+        self.launches += 2
         dqk = ws["d_qk"]
         self._dense([_p(dqk), _p(dqk, D)], 2 * D,
                     [self.wT("global_attention/query/kernel"), self.wT("global_attention/key/kernel")], None, 2, 1, R,
@@ -505,7 +511,6 @@ class Engine:
                                                _p(ws["d_ctx"]), _p(dq), D, self.gw(f"{la}/layer_norm/gamma"),
                                                self.gw(f"{la}/layer_norm/beta"), st), "ln_bwd")
             scat = ws["scat"][l]
-            scat.zero_()
             s_pre, t_sc, dx_sc = scat[0], scat[1], scat[2]
             dg_out = ws["dg"][(L - l) % 2]
             self._ev("la_backward", True)
@@ -573,6 +578,13 @@ class Engine:
             ev.record(side)
             main.wait_event(ev)
 
+    def _backward_prep(self, ws: dict, stream: int) -> None:
+        """Work the backward needs that does not depend on the forward: transposed weight blocks and
+        zeroed scatter targets."""
+        check(lib.scann_transpose_blocks(_p(self.params), _p(self.paramsT), _p(self.tblocks), self.tblocks.numel(),
+                                         stream), "transpose_blocks")
+        self.launches += 1
+
     # ------------------------------------------------------------------ optimiser
     def _set_adam(self, lr: float, batch_global: int, decay: float = 1e-5, b1=0.9, b2=0.999, eps=1e-7):
         t = self.step_count + 1
@@ -628,6 +640,18 @@ class Engine:
         if replan:
             self._plan(b)
         self.grads.zero_()
+        ws = self._workspace(b, True)
+        if self.use_side_stream:
+            # overlap with the forward: weight transposes and the zero-fill of the scatter targets
+            main = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side_stream.wait_event(ev)
+            with torch.cuda.stream(self.side_stream):
+                self._backward_prep(ws, self.side_stream.cuda_stream)
+                ws["scat_all"].zero_()
+                self._prep_event = torch.cuda.Event()
+                self._prep_event.record(self.side_stream)
         self.forward(b, training=True)
         self.backward(b, b.target)
         if allreduce is not None:

@@ -15,3 +15,12 @@ c = np.array(buf[:9], dtype=np.int64)
 names = ["weights->TMEM", "stage tile", "issue MMA", "prefetch gathers", "wait MMA", "TMEM->smem", "row epilogue", "rest (2nd tile etc)"]
 for n, d in zip(names, np.diff(c)): print(f"{n:22s} {d:8d} cycles")
 print("total", c[8] - c[0])
+
+buf2 = (ctypes.c_longlong * 16)()
+check(lib.scann_debug_clocks_dense(ctypes.cast(buf2, ctypes.c_void_p)))
+c = np.array(buf2[:7], dtype=np.int64)
+print("dealloc", c[6]-c[4], "epilogue2 after dealloc", c[5]-c[6])
+c = c[:6]
+print("dense_tc (last launch = GA q/k projection, kblk=1):")
+for n, d in zip(["alloc+init", "W->TMEM + stage X", "MMA issue+wait", "TMEM->smem", "row epilogue"], np.diff(c)): print(f"{n:22s} {d:8d} cycles")
+print("total", c[5] - c[0])
