@@ -32,6 +32,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+WORKLOADS = {
+    # name: (config name in scann_b200.configs, synthetic shape, structures per GPU)
+    "qm9": ("qm9", "qm9", 128),                 # BASELINE.json configs[1] (default, the headline)
+    "mp2018": ("mp2018", "mp2018", 64),         # configs[2] / [4]: Materials Project shaped batches
+    "fullerene": ("fullerene", "fullerene", 128),
+}
+
 QM9_CONFIG = {
     "model": {"n_atoms": 10, "embedding_dim": 48, "n_attention": 7, "local_dim": 128, "num_head": 8,
               "global_dim": 128, "dense_out": 128, "scale": 0.5, "use_attn_norm": True, "use_ga_norm": True,
@@ -39,6 +46,16 @@ QM9_CONFIG = {
     "hyper": {"batch_size": 128, "lr": 0.0005, "min_lr": 0.0001, "scheduler": "sgdr", "target": "homo"},
 }
 METRIC = "structures/sec (QM9 train step fwd+bwd+Adam, batch 128 per GPU)"
+
+
+def workload_config(name):
+    from scann_b200.configs import get_config
+    if name == "qm9":
+        return QM9_CONFIG, "qm9", 128, METRIC
+    cfg_name, shape, B = WORKLOADS[name]
+    cfg = get_config(cfg_name)
+    cfg["hyper"].setdefault("lr", 1e-4)
+    return cfg, shape, B, f"structures/sec ({name} train step fwd+bwd+Adam, batch {B} per GPU)"
 UNIT = "structures/s"
 
 
@@ -165,13 +182,13 @@ def run_ours(args):
     rank, local_rank, world = sdist.init()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    model = create_model(QM9_CONFIG, seed=1)
+    CFG, shape_name, B, metric = workload_config(args.workload)
+    model = create_model(CFG, seed=1)
     sdist.attach(model, world)
     eng = model.engine
-    B = 128
-    inputs, target = make_batch("qm9", seed=rank, B=B)
+    inputs, target = make_batch(shape_name, seed=rank, B=B)
     A_valid, P_valid = count_valid(inputs)
-    lr = QM9_CONFIG["hyper"]["lr"]
+    lr = CFG["hyper"]["lr"]
 
     # device-resident copies of the padded inputs (the `value` arm starts from HBM)
     dev_inputs = {k: torch.from_numpy(np.ascontiguousarray(v.view(np.uint8) if v.dtype == np.bool_ else v)).to(dev)
@@ -260,7 +277,7 @@ def run_ours(args):
         finish()
         return
 
-    L = QM9_CONFIG["model"]["n_attention"]
+    L = CFG["model"]["n_attention"]
     peaks, peak_kind = measured_peaks()
     # algorithmic bytes per launch: valid pairs P and atoms A only
     bytes_bwd = 1540.0 * P_valid + 1028.0 * A_valid
@@ -278,7 +295,7 @@ def run_ours(args):
                            "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     # bounded CPU sample (rank 0, N=1 only)
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.workload == "qm9":
         step, cores = cpu_train_step_fn()
         step()
         t0 = time.perf_counter()
@@ -289,10 +306,11 @@ def run_ours(args):
                "sample": f"{n // 128} train steps of the same 128-structure batch (~{args.cpu_seconds:.0f} s), "
                          "PyTorch-CPU restatement of the reference graph (TensorFlow not installable)"}
     out = {
-        "metric": METRIC, "value": B * world * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": metric, "value": B * world * args.steps / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "qm9_train_step_b128", "structures_per_gpu": B, "M": 29, "N": 16, "layers": L,
+        "config": {"workload": f"{args.workload}_train_step_b{B}", "structures_per_gpu": B,
+                   "M": int(inputs["neighbors"].shape[1]), "N": int(inputs["neighbors"].shape[2]), "layers": L,
                    "valid_atoms_per_gpu": A_valid, "valid_pairs_per_gpu": P_valid, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB write outside the timed events)",
                    "engine": "tcgen05 3xTF32 (fp32-accurate)" if eng.tc_la_bwd else "fp32 SIMT",
@@ -317,6 +335,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline sample")
+    ap.add_argument("--workload", default="qm9", choices=sorted(WORKLOADS),
+                    help="qm9 (default, BASELINE.json configs[1]) | mp2018 | fullerene: other shapes, for reference")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
