@@ -45,9 +45,10 @@ int scann_device_cc(void);
  * padded arrays of DataIterator.__getitem__ (scann/utils/datagenerator.py:80-101):
  * neighbor_mask [B,M,N] uint8, neighbors [B,M,N] int32, dist/weight [B,M,N] fp32.
  * Outputs: cnt[R], rowptr[R], tile_a0/tile_a1[tile_cap] (atom range of each tile), ntiles[1],
- * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*128].  scratch: >= 2*ceil(R/128) int32. */
+ * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*128].  scratch: >= 2*ceil(R/128) int32.
+ * tile_rows (<= 128): greedy fill limit per tile, chosen by the caller to balance SM waves. */
 int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
-                     const float* weight, int B, int M, int N, int tile_cap, int32_t* cnt, int32_t* rowptr,
+                     const float* weight, int B, int M, int N, int tile_cap, int tile_rows, int32_t* cnt, int32_t* rowptr,
                      int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles, int32_t* pair_c, int32_t* pair_j,
                      int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* scratch, int scratch_len,
                      int32_t* status, void* stream);

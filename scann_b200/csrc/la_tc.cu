@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         float4 p13[2][4];
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            const int r = sp * 64 + warp * 4 + rsub;
             pc[sp] = a.pair_c[rowbase + r];
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
             const int j = pc[sp] >= 0 ? a.pair_j[rowbase + r] : 0;
             const int c = pc[sp] >= 0 ? pc[sp] : 0;
 #pragma unroll
@@ -175,7 +176,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;        // the warp's 4 rows are padding
+            const int r = sp * 64 + warp * 4 + rsub;
             float z[4][4], pre[4][4];
             float s1 = 0.f;
 #pragma unroll
@@ -270,8 +272,10 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         // ---- stage a = x[j] * g' (coalesced row loads and gathers), hi/lo images
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            const int r = sp * 64 + warp * 4 + rsub;
             pc[sp] = a.pair_c[rowbase + r];
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;       // operand rows of padding stay stale: harmless,
+                                                                     // column r of D^T depends on operand row r only
             const bool ok = pc[sp] >= 0;
             const int j = ok ? a.pair_j[rowbase + r] : 0;
             float4 gv[4], xv[4];
@@ -352,7 +356,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = chunks 4h..4h+3 = 4 adjacent lanes)
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = warp * LTC_RPW + sp * 4 + rsub;
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
+            const int r = sp * 64 + warp * 4 + rsub;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r, l8 + 8 * it));

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int r = warp + LTC_WARPS * (hb * 4 + ii);
+                if (pc[hb * 4 + ii] < 0) continue;                       // padding row (warp-uniform)
                 *reinterpret_cast<float4*>(sS + tc_off4(r, lane)) = kv[ii];
                 float e = kv[ii].x * qv[ii].x + kv[ii].y * qv[ii].y + kv[ii].z * qv[ii].z + kv[ii].w * qv[ii].w;
                 float d = kv[ii].x * dc[ii].x + kv[ii].y * dc[ii].y + kv[ii].z * dc[ii].z + kv[ii].w * dc[ii].w;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                if (pc[i] < 0) continue;
                 float4 dk = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pc[i] >= 0) {
                     const float p = Es[r * 8 + (lane >> 2)], de = 0.25f * Ds[r * 8 + (lane >> 2)];
@@ -250,6 +252,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                if (pc[i] < 0) continue;
                 float4 da = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
                 if (pc[i] >= 0) {
                     red_add4(a.dx_scatter + (size_t)jj[ii] * SCANN_D + lane * 4, da.x * gp[ii].x, da.y * gp[ii].y,
@@ -337,6 +340,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                if (pc[i] < 0) { dz[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }      // padding row
                 const float pre[4] = {pv[ii].x, pv[ii].y, pv[ii].z, pv[ii].w};
                 const float g[4] = {gv[ii].x, gv[ii].y, gv[ii].z, gv[ii].w};
                 const float dgt[4] = {dv[ii].x, dv[ii].y, dv[ii].z, dv[ii].w};
@@ -410,6 +414,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i) {
             const int r = warp + LTC_WARPS * i;
+            if (pc[i] < 0) continue;
             float4 v = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
             st4(a.dg_out + (rowbase + r) * SCANN_D + lane * 4,
                 make_float4(v.x + dz[i].x, v.y + dz[i].y, v.z + dz[i].z, v.w + dz[i].w));

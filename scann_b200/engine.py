@@ -95,6 +95,9 @@ class Engine:
         self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
         self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
         self.use_side_stream = os.environ.get("SCANN_SIDE_STREAM", "1") == "1"
+        # Opt-in: smaller, wave-balanced tiles.  Measured on QM9/128: local-attention kernels -3 %, but the
+        # kernels whose cost is per tile rather than per row (geom_init, la_wgrad_tc) lose more: 2.06 vs 1.93 ms.
+        self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "0") == "1"
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
 
@@ -145,7 +148,7 @@ class Engine:
         return self.params.cpu().numpy()
 
     # ------------------------------------------------------------------ inputs
-    def load_batch(self, inputs: Dict[str, object], plan: bool = True) -> Batch:
+    def load_batch(self, inputs: Dict[str, object], plan: bool = True, pairs_hint: Optional[int] = None) -> Batch:
         """Stage one padded batch (reference layout, scann/utils/datagenerator.py:123-135) in the
         persistent device buffers of its shape class and build its pair plan.  Host arrays go through
         pinned staging buffers; CUDA tensors / ``__dlpack__`` objects are copied device-to-device.
@@ -157,15 +160,24 @@ class Engine:
         R = B * M
         nmask_in = inputs["neighbor_mask"]
         P_host = int(np.count_nonzero(nmask_in)) if isinstance(nmask_in, np.ndarray) else None
-        # tile capacity: every non-final tile of a greedy group holds more than 128-N rows
+        if P_host is None:
+            P_host = pairs_hint
         P = P_host if P_host is not None else B * M * N
         ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
-        cap = P // (129 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2
+        # rows per tile: fill whole waves of SMs (the kernels' cost per tile scales with its rows, and a
+        # tile count just above a multiple of the SM count costs a whole extra round)
+        tile_rows = TILE
+        if P_host is not None and self.balance_tiles and N <= 64:
+            waves = max(1, -(-P // (TILE * self.sm_count)))
+            tile_rows = min(TILE, max(2 * N, 32, -(-P // (waves * self.sm_count)) + (N + 1) // 2))
+        # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
+        cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
         tile_cap = max(64, (cap + 63) // 64 * 64)
-        key = (B, M, N, tile_cap)
+        key = (B, M, N, tile_cap, tile_rows)
         b = self._batches.get(key)
         if b is None:
             b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups)
+            b.tile_rows = tile_rows
         b.P_host = P_host
         b.h2d_bytes = 0
 
@@ -249,7 +261,7 @@ class Engine:
         a = np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1))
         if a.size != b.B:
             raise ValueError("target must have one value per structure")
-        key = (b.B, b.M, b.N, b.tile_cap)
+        key = (b.B, b.M, b.N, b.tile_cap, b.tile_rows)
         slot = self._pinned.get(("target", key))
         if slot is None:
             slot = self._pinned[("target", key)] = [torch.empty(b.B, dtype=torch.float32).pin_memory(), None]
@@ -264,14 +276,14 @@ class Engine:
 
     def _plan(self, b: Batch) -> None:
         check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
-                                   _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
+                                   b.tile_rows, _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
                                    _p(b.scratch), b.scratch.numel(), _p(self.status), self._stream()), "plan_build")
         self.launches += 4
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, b: Batch, training: bool) -> dict:
-        key = (b.R, b.B, b.tile_cap, training)
+        key = (b.R, b.B, b.tile_cap, training)      # workspaces depend on the capacity, not on tile_rows
         ws = self._ws.get(key)
         if ws is not None:
             return ws
