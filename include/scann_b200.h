@@ -37,6 +37,11 @@ int scann_version(void);
 /* SM count of the current device, -1 when no CUDA device is usable (callers must refuse to run). */
 int scann_device_sm_count(void);
 int scann_device_cc(void);
+/* Programmatic dependent launch (per calling thread; returns the previous setting).  When on, the kernels of
+ * the forward / backward chain are launched with programmatic stream serialisation so that a kernel's
+ * prologue (tensor-memory allocation, weights -> tensor memory) overlaps the tail of its stream predecessor.
+ * Switch it off for a launch whose stream predecessor is not a kernel of this library (memset, event join). */
+int scann_set_pdl(int on);
 
 /* ---- batch plan ---------------------------------------------------------------------------
  * Replaces the mask / index bookkeeping the reference does with dense padded tensors:

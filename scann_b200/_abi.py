@@ -22,6 +22,7 @@ PROTOTYPES = {
     "scann_version": (ci, []),
     "scann_device_sm_count": (ci, []),
     "scann_device_cc": (ci, []),
+    "scann_set_pdl": (ci, [ci]),
     "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
     "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp]),
     "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp]),

@@ -25,6 +25,17 @@ int scann_check_launch(const char* what) {
 
 extern "C" const char* scann_last_error(void) { return g_err; }
 
+// Programmatic dependent launch for the kernels that support it (common.cuh); per calling thread.
+// The caller switches it off around launches whose stream predecessor is not one of this library's
+// PDL-aware kernels (memsets, event joins from another stream).
+static thread_local bool g_pdl = false;
+bool scann_pdl_enabled() { return g_pdl; }
+extern "C" int scann_set_pdl(int on) {
+    int prev = g_pdl ? 1 : 0;
+    g_pdl = on != 0;
+    return prev;
+}
+
 extern "C" int scann_version(void) { return 100; }   // 0.1.0
 
 // Number of SMs of the current device, or -1 (with the error string set) when no CUDA device

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int32_t* __restric
     extern __shared__ float s_cat[];   // [EMB_ROWS][Kin]
     const int Kin = E + (ring ? 10 : 0);
     const int r0 = blockIdx.x * EMB_ROWS;
+    pdl_wait();
+    pdl_trigger();      // only after the own wait: at most one kernel ahead becomes resident early
     for (int i = threadIdx.x; i < EMB_ROWS * Kin; i += blockDim.x) {
         int rr = i / Kin, k = i % Kin, r = r0 + rr;
         float v = 0.f;
@@ -190,10 +192,12 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
         ww[k] = Ww[k * SCANN_D + n];
     }
     const float bdn = bd[n], bwn = bw[n];
+    pdl_wait();                                   // weights above are parameters; the plan is a predecessor's output
     const int nt = *ntiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t base = (size_t)t * SCANN_TILE;
         __syncthreads();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
         geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
 #pragma unroll 4
         for (int row = half; row < SCANN_TILE; row += 2) {
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
             g0[(base + row) * SCANN_D + n] = s_c[row] >= 0 ? swish_f(a) * swish_f(b) : 0.f;
         }
     }
+    pdl_trigger();
 }
 
 // Backward: accumulates dWd, dbd, dWw, dbw from d_g0 (no gradient flows to distances/weights).
@@ -233,10 +238,12 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
     }
     const float bdn = bd[n], bwn = bw[n];
     float gbd = 0.f, gbw = 0.f;
+    pdl_wait();
     const int nt = *ntiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t base = (size_t)t * SCANN_TILE;
         __syncthreads();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
         geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
         // the gradient rows of this thread's half are independent loads: keep 8 in flight
         for (int r8 = half; r8 < SCANN_TILE; r8 += 16) {
@@ -266,6 +273,7 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
             }
         }
     }
+    pdl_trigger();
     if ((int)blockIdx.x < nt) {
 #pragma unroll
         for (int k = 0; k < SCANN_RBF; ++k) {
@@ -461,6 +469,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     if (threadIdx.x < SCANN_D) { s_g[threadIdx.x] = 0.f; s_b[threadIdx.x] = 0.f; }
     __syncthreads();
     const float4 gam = ldg4(gamma + lane * 4);
+    pdl_wait();
+    pdl_trigger();
     float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
     for (int r = blockIdx.x * nwarp + warp; r < R; r += gridDim.x * nwarp) {
         float4 x = ld4(v + (size_t)r * SCANN_D + lane * 4);
@@ -502,6 +512,8 @@ __global__ void __launch_bounds__(256) la_nopair_fwd_kernel(const int32_t* __res
                                                             float* __restrict__ ctx_pre, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_wait();
+    pdl_trigger();      // only after the own wait: at most one kernel ahead becomes resident early
     if (r >= R || cnt[r] != 0) return;
     float4 q = ld4(proj + (size_t)r * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
     if (ctx_pre) st4(ctx_pre + (size_t)r * SCANN_D + lane * 4, q);
@@ -539,8 +551,8 @@ extern "C" int scann_embed_forward(const int32_t* atomic, const float* ring, int
                                    const float* be, float* t0, float* x0, int32_t* status, void* stream) {
     int Kin = E + (ring ? 10 : 0);
     size_t smem = (size_t)EMB_ROWS * Kin * sizeof(float);
-    embed_fwd_kernel<<<(R + EMB_ROWS - 1) / EMB_ROWS, 128, smem, (cudaStream_t)stream>>>(atomic, ring, R, E, n_atoms, emb,
-                                                                                       Wr, br, We, be, t0, x0, status);
+    scann_launch(embed_fwd_kernel, dim3((R + EMB_ROWS - 1) / EMB_ROWS), dim3(128), smem, stream, atomic, ring, R, E, n_atoms,
+                 emb, Wr, br, We, be, t0, x0, status);
     return scann_check_launch("scann_embed_forward");
 }
 
@@ -562,8 +574,8 @@ extern "C" int scann_geom_init_forward(const int32_t* ntiles, int grid, const in
                                        const float* pair_w, const float* centers_d, const float* centers_w,
                                        const float* Wd, const float* bd, const float* Ww, const float* bw, float* g0,
                                        void* stream) {
-    geom_init_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
-                                                                 Wd, bd, Ww, bw, g0);
+    scann_launch(geom_init_fwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
+                 Wd, bd, Ww, bw, g0);
     return scann_check_launch("scann_geom_init_forward");
 }
 
@@ -572,8 +584,8 @@ extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, const i
                                         const float* Wd, const float* bd, const float* Ww, const float* bw,
                                         const float* dg0, float* dWd, float* dbd, float* dWw, float* dbw,
                                         void* stream) {
-    geom_init_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
-                                                                 Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
+    scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
+                 Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
     return scann_check_launch("scann_geom_init_backward");
 }
 
@@ -624,14 +636,14 @@ extern "C" int scann_layernorm_backward(const float* dy, const float* v, const f
     if (R <= 0) return 0;
     int grid = (R + 31) / 32;
     if (grid > 592) grid = 592;
-    ln_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, v, gamma, R, dv, dv2, ld2, dgamma, dbeta);
+    scann_launch(ln_bwd_kernel, dim3(grid), dim3(256), 0, stream, dy, v, gamma, R, dv, dv2, ld2, dgamma, dbeta);
     return scann_check_launch("scann_layernorm_backward");
 }
 
 extern "C" int scann_la_nopair_forward(const int32_t* cnt, const float* proj, int R, const float* gamma,
                                        const float* beta, float* ctx_pre, float* out, void* stream) {
     if (R <= 0) return 0;
-    la_nopair_fwd_kernel<<<(R + 7) / 8, 256, 0, (cudaStream_t)stream>>>(cnt, proj, R, gamma, beta, ctx_pre, out);
+    scann_launch(la_nopair_fwd_kernel, dim3((R + 7) / 8), dim3(256), 0, stream, cnt, proj, R, gamma, beta, ctx_pre, out);
     return scann_check_launch("scann_la_nopair_forward");
 }
 

@@ -16,6 +16,7 @@
 #include "tc_common.cuh"
 
 #define DTC_THREADS 256
+extern "C" int scann_device_sm_count(void);
 
 // phase timestamps of CTA (0,0) (clock64), read back with scann_debug_clocks_dense: development aid
 __device__ long long g_dbg_clk_dense[16];
@@ -37,14 +38,42 @@ struct DenseTcArgs {
     const float* beta;
 };
 
+// weight block W[k][n] -> tensor memory as A[M = n][K = k] (hi and lo parts): thread = output feature n,
+// warps 0-3 take k in [0,64), warps 4-7 take k in [64,128)
+__device__ __forceinline__ void dense_weight_to_tmem(const float* __restrict__ W, uint32_t t_whi, uint32_t t_wlo, int warp,
+                                                     int lane) {
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int n = (warp & 3) * 32 + lane, kbase = (warp >> 2) * 64;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        float w[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) w[q] = __ldg(W + (size_t)(kbase + h * 32 + q) * SCANN_D + n);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) tf32_split(w[g * 16 + q], hi[q], lo[q]);
+            tmem_st16(t_whi + lane_base + kbase + h * 32 + g * 16, hi);
+            tmem_st16(t_wlo + lane_base + kbase + h * 32 + g * 16, lo);
+        }
+    }
+}
+
+// TR = activation rows per CTA (32 / 64 / 128 = the N extent of the MMA).  The per-atom tensors of one batch are
+// only a few thousand rows, so the host picks the smallest TR that still fits one wave of CTAs: the kernel's
+// latency (staging, MMA, epilogue) scales with TR while the weight staging is hidden behind the predecessor.
+template <int TR>
 __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcArgs a) {
+    constexpr int XIT = TR / 8;                       // LDG.128 per thread for the activation tile
+    constexpr uint32_t IMG = (TR / 8) * TC_RG_STRIDE; // bytes of one K-major image of TR rows
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sXhi = smem;
-    uint8_t* sXlo = smem + TC_TILE_BYTES;
+    uint8_t* sXlo = smem + IMG;
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int r0 = blockIdx.x * 128, nb = blockIdx.y;
+    const int r0 = blockIdx.x * TR, nb = blockIdx.y;
     DCLK(0);
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
@@ -52,45 +81,30 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 256 + TR;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
+    const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
     uint32_t phase = 0;
     DCLK(1);
+    // the first weight block only depends on parameters: stage it before waiting for the predecessor kernel
+    dense_weight_to_tmem(a.W[nb], t_whi, t_wlo, warp, lane);
+    pdl_wait();
 
     for (int kb = 0; kb < a.kblk; ++kb) {
-        // (b) activation tile: issue all global loads first (16 x LDG.128 in flight per thread)
+        // (b) activation tile: issue all global loads first (TR/8 x LDG.128 in flight per thread)
         const float* A = a.A[kb];
-        float4 xv[16];
+        float4 xv[XIT];
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
+        for (int it = 0; it < XIT; ++it) {
             const int i = tid + it * DTC_THREADS, r = i >> 5, c4 = i & 31;
             xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r0 + r < a.R) xv[it] = ld4(A + (size_t)(r0 + r) * a.lda + c4 * 4);
         }
-        // (a) weight block -> tensor memory: thread = output feature n, columns = k; warps 0-3 take
-        //     k in [0,64), warps 4-7 take k in [64,128)
-        {
-            const float* W = a.W[kb * a.nblk + nb];
-            const int n = (warp & 3) * 32 + lane, kbase = (warp >> 2) * 64;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float w[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) w[q] = __ldg(W + (size_t)(kbase + h * 32 + q) * SCANN_D + n);
-#pragma unroll
-                for (int g = 0; g < 2; ++g) {
-                    float hi[16], lo[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) tf32_split(w[g * 16 + q], hi[q], lo[q]);
-                    tmem_st16(t_whi + lane_base + kbase + h * 32 + g * 16, hi);
-                    tmem_st16(t_wlo + lane_base + kbase + h * 32 + g * 16, lo);
-                }
-            }
-        }
+        // (a) weight block -> tensor memory (block 0 was staged before the dependency wait)
+        if (kb > 0) dense_weight_to_tmem(a.W[kb * a.nblk + nb], t_whi, t_wlo, warp, lane);
         // activation tile -> K-major images (hi, lo)
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
+        for (int it = 0; it < XIT; ++it) {
             const int i = tid + it * DTC_THREADS, r = i >> 5, c4 = i & 31;
             float4 v = xv[it], h, l;
             tf32_split(v.x, h.x, l.x); tf32_split(v.y, h.y, l.y);
@@ -124,11 +138,12 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         __syncthreads();
         if (kb == 0) DCLK(3);
     }
+    pdl_trigger();          // only the epilogue is left: the next kernel may start its own prologue
     // epilogue 1: D^T (lane = n, column = r) -> shared image S[r][n]  (S aliases the hi image)
     {
-        const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 64;
+        const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * (TR / 2);
 #pragma unroll 1
-        for (int rr = rbase; rr < rbase + 64; rr += 16) {
+        for (int rr = rbase; rr < rbase + TR / 2; rr += 16) {
             float m[16], c[16];
             tmem_ld16(t_dm + lane_base + rr, m);
             tmem_ld16(t_dc + lane_base + rr, c);
@@ -153,8 +168,8 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         bet[it] = a.mode == 3 ? ldg4(a.beta + c0) : bias[it];
     }
 #pragma unroll 1
-    for (int step = 0; step < 128 / (DTC_THREADS / 32) / 4; ++step) {
-        const int rr = warp * (128 / (DTC_THREADS / 32)) + step * 4 + rsub, r = r0 + rr;
+    for (int step = 0; step < TR / (DTC_THREADS / 32) / 4; ++step) {
+        const int rr = warp * (TR / (DTC_THREADS / 32)) + step * 4 + rsub, r = r0 + rr;
         const bool ok = r < a.R;
         float v[4][4];
 #pragma unroll
@@ -233,18 +248,29 @@ extern "C" int scann_dense_forward_tc(const float* const* A, int lda, const floa
     if (mode == 3 && nblk != 1) { scann_set_error("dense_tc: LayerNorm epilogue needs nblk == 1"); return 1; }
     if (R <= 0) return 0;
     static bool configured = false;
-    const size_t smem = 2 * TC_TILE_BYTES;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(dense_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(2 * TC_TILE_BYTES));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(dense_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_TILE_BYTES);
         if (e != cudaSuccess) { scann_set_error("dense_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
         configured = true;
     }
+    // smallest row tile whose grid still fits one wave of SMs (one CTA per SM: each allocates all of tensor memory)
+    static int sms = 0;
+    if (sms == 0) sms = scann_device_sm_count();
+    int tr = 128;
+    if (((R + 31) / 32) * nblk <= sms) tr = 32;
+    else if (((R + 63) / 64) * nblk <= sms) tr = 64;
     DenseTcArgs a;
     for (int i = 0; i < 3; ++i) { a.A[i] = i < kblk ? A[i] : nullptr; a.bias[i] = (bias && i < nblk) ? bias[i] : nullptr; }
     for (int i = 0; i < 9; ++i) a.W[i] = i < kblk * nblk ? W[i] : nullptr;
     a.lda = lda; a.kblk = kblk; a.nblk = nblk; a.R = R; a.C = C; a.ldc = ldc; a.mode = mode;
     a.resid = resid; a.ldres = ldres; a.pre_in = pre_in; a.pre_out = pre_out; a.gamma = gamma; a.beta = beta;
-    dim3 grid((R + 127) / 128, nblk);
-    dense_tc_kernel<<<grid, DTC_THREADS, smem, (cudaStream_t)stream>>>(a);
+    dim3 grid((R + tr - 1) / tr, nblk);
+    const size_t smem = 2 * (size_t)(tr / 8) * TC_RG_STRIDE;
+    if (tr == 32) scann_launch(dense_tc_kernel<32>, grid, dim3(DTC_THREADS), smem, stream, a);
+    else if (tr == 64) scann_launch(dense_tc_kernel<64>, grid, dim3(DTC_THREADS), smem, stream, a);
+    else scann_launch(dense_tc_kernel<128>, grid, dim3(DTC_THREADS), smem, stream, a);
     return scann_check_launch("scann_dense_forward_tc");
 }

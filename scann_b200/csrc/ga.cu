@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_fwd_kernel(const float* __
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* qkb = qk + (size_t)b * M * 2 * SCANN_D;
     const uint8_t* mb = atom_mask + (size_t)b * M;
+    pdl_wait();
+    pdl_trigger();      // only after the own wait: at most one kernel ahead becomes resident early
     ga_scores(qkb, mb, M, norm, s_Q, s_s, s_ga, s_red);
     for (int i = tid; i < M; i += GA_THREADS) ga[(size_t)b * M + i] = s_ga[i];
     float c = 0.f;
@@ -127,6 +129,8 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_bwd_kernel(
     const float* qkb = qk + (size_t)b * M * 2 * SCANN_D;
     float* dqkb = d_qk + (size_t)b * M * 2 * SCANN_D;
     const uint8_t* mb = atom_mask + (size_t)b * M;
+    pdl_wait();
+    pdl_trigger();      // only after the own wait: at most one kernel ahead becomes resident early
     const float g = dy[b];
     // head
     {
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_bwd_kernel(
 __global__ void __launch_bounds__(256) rmse_prepare_kernel(const float* __restrict__ y, const float* __restrict__ target,
                                                            int B, float* __restrict__ dy, float* __restrict__ sse) {
     __shared__ float s_a[8], s_b[8];
+    pdl_wait();
+    pdl_trigger();      // only after the own wait: at most one kernel ahead becomes resident early
     float a = 0.f, c = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B; i += gridDim.x * blockDim.x) {
         float e = y[i] - target[i];
@@ -222,8 +228,8 @@ extern "C" int scann_ga_head_forward(const float* qk, const uint8_t* atom_mask, 
     if (B <= 0) return 0;
     size_t smem = (size_t)(2 * SCANN_D + 4 + 2 * M) * sizeof(float);
     if (smem > 48 * 1024) { scann_set_error("ga_head_forward: M=%d too large", M); return 1; }
-    ga_head_fwd_kernel<<<B, GA_THREADS, smem, (cudaStream_t)stream>>>(qk, atom_mask, M, norm, Wb, bb, wp, bp, mrelu, ga,
-                                                                      y, ctx_out, tb_out);
+    scann_launch(ga_head_fwd_kernel, dim3(B), dim3(GA_THREADS), smem, stream, qk, atom_mask, M, norm, Wb, bb, wp, bp, mrelu,
+                 ga, y, ctx_out, tb_out);
     return scann_check_launch("scann_ga_head_forward");
 }
 
@@ -233,8 +239,8 @@ extern "C" int scann_ga_head_backward(const float* qk, const uint8_t* atom_mask,
     if (B <= 0) return 0;
     size_t smem = (size_t)(3 * SCANN_D + 4 + 3 * M) * sizeof(float);
     if (smem > 48 * 1024) { scann_set_error("ga_head_backward: M=%d too large", M); return 1; }
-    ga_head_bwd_kernel<<<B, GA_THREADS, smem, (cudaStream_t)stream>>>(qk, atom_mask, M, norm, WbT, wp, tb, dy, d_qk,
-                                                                      d_tb, dwp, dbp);
+    scann_launch(ga_head_bwd_kernel, dim3(B), dim3(GA_THREADS), smem, stream, qk, atom_mask, M, norm, WbT, wp, tb, dy, d_qk,
+                 d_tb, dwp, dbp);
     return scann_check_launch("scann_ga_head_backward");
 }
 
@@ -242,6 +248,6 @@ extern "C" int scann_rmse_prepare(const float* y, const float* target, int B, fl
     if (B <= 0) return 0;
     int grid = (B + 255) / 256;
     if (grid > 64) grid = 64;
-    rmse_prepare_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, target, B, dy, sse);
+    scann_launch(rmse_prepare_kernel, dim3(grid), dim3(256), 0, stream, y, target, B, dy, sse);
     return scann_check_launch("scann_rmse_prepare");
 }

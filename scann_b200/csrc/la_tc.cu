@@ -102,8 +102,6 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = *a.ntiles;
-    if ((int)blockIdx.x >= nt) return;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     tc_fence_before();
@@ -112,7 +110,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
     const uint32_t tmem = tmem_base_s;
     const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
     DBG_CLK(0);
-    weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);
+    weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);     // parameters only: overlaps the predecessor kernel's tail
+    pdl_wait();
+    const int nt = *a.ntiles;
     DBG_CLK(1);
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
         if (t == (int)blockIdx.x) DBG_CLK(5);
         tmem_to_rows(t_dm, t_dc, sS, nullptr, warp, lane);
         tc_fence_before();
@@ -220,6 +221,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         if (t == (int)blockIdx.x) DBG_CLK(7);
     }
     DBG_CLK(8);
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -252,8 +254,6 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = *a.ntiles;
-    if ((int)blockIdx.x >= nt) return;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     tc_fence_before();
@@ -263,6 +263,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
     const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
     weightT_to_tmem(a.Wk, t_whi, t_wlo, warp, lane);
     const float4 gam = ldg4(a.gamma + lane * 4), bet = ldg4(a.beta + lane * 4);
+    pdl_wait();
+    const int nt = *a.ntiles;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
         const size_t rowbase = (size_t)t * SCANN_TILE;
@@ -350,6 +352,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
         tmem_to_rows(t_dm, t_dc, sS, a.bk, warp, lane);          // keys k = a @ Wk + bk
         tc_fence_before();
         __syncthreads();
@@ -401,6 +404,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         }
         __syncthreads();
     }
+    pdl_trigger();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -429,10 +433,10 @@ extern "C" int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_
     }
     if (grid <= 0) return 0;
     LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
-    la_geom_fwd_tc_kernel<<<grid, LTC_THREADS, LA_GEOM_SMEM, (cudaStream_t)stream>>>(ga);
+    scann_launch(la_geom_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr};
-    la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
+    scann_launch(la_attn_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_tc");
 }
 
@@ -456,7 +460,7 @@ extern "C" int scann_la_forward_noupdate_tc(int grid, const int32_t* ntiles, con
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, nullptr, pair_d, pair_w, centers, Wf, bf};
-    la_attn_fwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_SMEM, (cudaStream_t)stream>>>(aa);
+    scann_launch(la_attn_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");
 }
 

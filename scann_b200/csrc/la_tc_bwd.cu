@@ -101,8 +101,6 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_dbk[SCANN_D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = *a.ntiles;
-    if ((int)blockIdx.x >= nt) return;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (tid < SCANN_D) s_dbk[tid] = 0.f;
@@ -113,6 +111,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
     const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
     // stationary operand A[M = ka][K = n] = Wk[ka][n]  (= transpose of WkT, loaded coalesced)
     b_weightT_to_tmem(a.WkT, t_whi, t_wlo, warp, lane);
+    pdl_wait();
+    const int nt = *a.ntiles;
     float4 dbk = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
         b_tmem_to_rows(t_dm, t_dc, sS, warp, lane);
         tc_fence_before();
         __syncthreads();
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
         }
         __syncthreads();
     }
+    pdl_trigger();
     atomicAdd(&s_dbk[lane * 4 + 0], dbk.x); atomicAdd(&s_dbk[lane * 4 + 1], dbk.y);
     atomicAdd(&s_dbk[lane * 4 + 2], dbk.z); atomicAdd(&s_dbk[lane * 4 + 3], dbk.w);
     tc_fence_before();
@@ -299,8 +301,6 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_acc[2 * SCANN_D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nt = *a.ntiles;
-    if ((int)blockIdx.x >= nt) return;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     if (tid < 2 * SCANN_D) s_acc[tid] = 0.f;
@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
     // stationary operand A[M = k][K = n] = W2[k][n]: (d_pre W2^T)^T = W2 d_pre^T
     b_weightT_to_tmem(a.W2T, t_whi, t_wlo, warp, lane);
     const float4 gam = ldg4(a.gamma_g + lane * 4);
+    pdl_wait();
+    const int nt = *a.ntiles;
     float4 dgam = make_float4(0.f, 0.f, 0.f, 0.f), dbet = dgam;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
@@ -407,6 +409,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
         b_tmem_to_rows(t_dm, t_dc, sS, warp, lane);
         tc_fence_before();
         __syncthreads();
@@ -421,6 +424,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
         }
         __syncthreads();
     }
+    pdl_trigger();
     atomicAdd(&s_acc[lane * 4 + 0], dgam.x); atomicAdd(&s_acc[lane * 4 + 1], dgam.y);
     atomicAdd(&s_acc[lane * 4 + 2], dgam.z); atomicAdd(&s_acc[lane * 4 + 3], dgam.w);
     atomicAdd(&s_acc[SCANN_D + lane * 4 + 0], dbet.x); atomicAdd(&s_acc[SCANN_D + lane * 4 + 1], dbet.y);
@@ -593,10 +597,10 @@ extern "C" int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32
     cudaStream_t st = (cudaStream_t)stream;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
                      dg_has_up, dq, dx_scatter, dbk};
-    la_attn_bwd_tc_kernel<<<grid, LTC_THREADS, LA_ATTN_BWD_SMEM, st>>>(ab);
+    scann_launch(la_attn_bwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g};
-    la_geom_bwd_tc_kernel<<<grid, LTC_THREADS, LA_GEOM_BWD_SMEM, st>>>(gb);
+    scann_launch(la_geom_bwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
     return scann_check_launch("scann_la_backward_tc");
 }
 

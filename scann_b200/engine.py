@@ -100,6 +100,8 @@ class Engine:
         self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "0") == "1"
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
+        # programmatic dependent launch along the forward / backward kernel chain (include/scann_b200.h)
+        self.use_pdl = os.environ.get("SCANN_PDL", "1") == "1"
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -124,6 +126,12 @@ class Engine:
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _pdl(self, on: bool) -> None:
+        """Programmatic dependent launch for the following kernel launches of this thread.  Only switched
+        on between two kernels of this library on the same stream (never right after a memset, a torch
+        kernel or an event join)."""
+        lib.scann_set_pdl(1 if (on and self.use_pdl) else 0)
 
     def w(self, name: str, off: int = 0) -> int:
         return _p(self.params, self.layout[name].offset + off)
@@ -356,12 +364,14 @@ class Engine:
             raise NotImplementedError("training is accelerated for g_update=True, use_ring=False models only; "
                                       "g_update=False / use_ring=True run the inference path")
         ring = sp.use_ring
+        self._pdl(False)
         check(lib.scann_embed_forward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
                                       self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
                                       self.w("extra_embed/bias") if ring else 0,
                                       self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
                                       _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status), st), "embed_forward")
         self.launches += 1
+        self._pdl(True)
         if sp.g_update:
             check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                               _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
@@ -444,6 +454,7 @@ class Engine:
                                         int(sp.mrelu_head), _p(ws["ga"]), _p(ws["y"]),
                                         _p(ws["ctxg"]) if training else 0, _p(ws["tb"]) if training else 0, st),
               "ga_head_forward")
+        self._pdl(False)
         self.launches += 1
         return ws["y"], ws["ga"]
 
@@ -481,7 +492,9 @@ class Engine:
         else:
             self._backward_prep(ws, st)
             ws["scat_all"].zero_()
+        self._pdl(False)
         check(lib.scann_rmse_prepare(_p(ws["y"]), _p(target), b.B, _p(ws["dy"]), _p(self.grads, n), st), "rmse_prepare")
+        self._pdl(True)
         check(lib.scann_ga_head_backward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                          self.wT("bf_property/kernel"), self.w("predict_property/kernel"),
                                          _p(ws["tb"]), _p(ws["dy"]), _p(ws["d_qk"]), _p(ws["d_tb"]),
@@ -579,6 +592,7 @@ class Engine:
                                            self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),
                                            self.gw("neighbor_d/bias"), self.gw("neighbor_w/kernel"),
                                            self.gw("neighbor_w/bias"), st), "geom_init_backward")
+        self._pdl(False)
         E = sp.embedding_dim
         check(lib.scann_embed_backward(_p(b.atomic), 0, R, E, sp.n_atoms, self.w("embed_atom/embeddings"), 0, 0,
                                        self.w("dense_embed/kernel"), _p(ws["t0"]), _p(dx), _p(ws["G"]),
