@@ -14,7 +14,8 @@
  *    streams; the only global state is the per-thread error string;
  *  - per-atom tensors are [R,128] fp32 row-major with R = B*M (row r = b*M + m);
  *    per-pair tensors use the tile-padded packed layout built by scann_plan_build:
- *    tile t owns rows [128 t, 128 t + 128), rows with pair_c < 0 are padding;
+ *    tile t owns rows [S t, S t + S) with S = tile_stride (128, or 64 when the local-attention kernels
+ *    run two warp groups per CTA on 64-row tiles), rows with pair_c < 0 are padding;
  *  - weight blocks are [128,128] fp32 row-major (Keras Dense kernels, [in,out]);
  *  - `status` is a device int32 of SCANN_ERR_* bits set by kernels on malformed input.
  */
@@ -53,7 +54,8 @@ int scann_set_pdl(int on);
  * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*128].  scratch: >= 2*ceil(R/128) int32.
  * tile_rows (<= 128): greedy fill limit per tile, chosen by the caller to balance SM waves. */
 int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
-                     const float* weight, int B, int M, int N, int tile_cap, int tile_rows, int32_t* cnt, int32_t* rowptr,
+                     const float* weight, int B, int M, int N, int tile_cap, int tile_rows, int tile_stride,
+                     int32_t* cnt, int32_t* rowptr,
                      int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles, int32_t* pair_c, int32_t* pair_j,
                      int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* scratch, int scratch_len,
                      int32_t* status, void* stream);
@@ -71,10 +73,10 @@ int scann_embed_backward(const int32_t* atomic, const float* ring, int R, int E,
 
 /* ---- geometry initialisation: GaussianExpansion x2 + neighbor_d/neighbor_w Dense + Multiply --
  * scann/layers/custom_layers.py:55-65, scann/models/scann_model.py:378-389. */
-int scann_geom_init_forward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+int scann_geom_init_forward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c, const float* pair_d,
                             const float* pair_w, const float* centers_d, const float* centers_w, const float* Wd,
                             const float* bd, const float* Ww, const float* bw, float* g0, void* stream);
-int scann_geom_init_backward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+int scann_geom_init_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c, const float* pair_d,
                              const float* pair_w, const float* centers_d, const float* centers_w, const float* Wd,
                              const float* bd, const float* Ww, const float* bw, const float* dg0, float* dWd,
                              float* dbd, float* dWw, float* dbw, void* stream);
@@ -106,6 +108,43 @@ int scann_la_nopair_forward(const int32_t* cnt, const float* proj, int R, const 
 /* dst[off..] = transpose(src[off..]) for each listed 128x128 block (offsets: device int32). */
 int scann_transpose_blocks(const float* src, float* dst, const int32_t* offsets, int nblocks, void* stream);
 
+/* ---- chains of per-atom Dense layers in one kernel ----------------------------------------------
+ * Rows (atoms) are independent in every per-atom layer, so the kernels between two local-attention layers
+ * are fused: ResidualNorm (attention.py:25-40) + the next layer's x @ [W1|W3|Wq] projections
+ * (attention.py:141-161) + "context = q" for atoms without neighbours (attention.py:206-214) in the forward
+ * pass, and their transposes with LayerNorm backward / swish' in the backward pass.  A CTA carries its rows
+ * through up to 6 steps; step i computes
+ *     V = sum_kb A[kb] @ W[kb] + bias (+ resid)
+ *     mode 0: out = V | 1: pre_out <- V, out = swish(V) | 2: out = V * swish'(pre_in)
+ *          3: pre_out <- V, out = LayerNorm(V; gamma, beta, eps 1e-6)
+ *          4: out = LayerNorm-backward(dy = V; forward value pre_in, gamma); dgamma, dbeta accumulated
+ *     C, C2 <- out (nullable);  to_image: out is the A operand of step i+1 (that step has A[0] = NULL, kblk 1;
+ *     an operand loaded from global memory also stays resident for later steps with A[0] = NULL).
+ *     cnt != NULL: rows with cnt[r] == 0 additionally get np_ctx[r] = V, np_out[r] = LayerNorm(V; gamma, beta).
+ * `steps` is a HOST array of nsteps structs holding device pointers. */
+typedef struct ScannChainStep {
+    const float* A[3];
+    const float* W[3];
+    const float* bias;
+    const float* resid;
+    const float* pre_in;
+    float* pre_out;
+    const float* gamma;
+    const float* beta;
+    float* dgamma;
+    float* dbeta;
+    float* C;
+    float* C2;
+    const int32_t* cnt;
+    float* np_ctx;
+    float* np_out;
+    int lda, ldres, ldpre, ldc, ldc2;
+    int kblk;
+    int mode;
+    int to_image;
+} ScannChainStep;
+int scann_dense_chain(const ScannChainStep* steps, int nsteps, int R, void* stream);
+
 /* ---- local attention (the hot kernel) ---------------------------------------------------------
  * LocalAttention.call, g_update=True, v_proj=False, kq_proj=True (scann/layers/attention.py:118-216).
  * proj = [x@W1+bf | x@W3 | x@Wq+bq] ([R,384]); W2 = rows 128..255 of filter_geo/kernel.
@@ -118,7 +157,7 @@ int scann_la_forward(int grid, const int32_t* ntiles, const int32_t* tile_a0, co
                      const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, void* stream);
 /* Same forward on the tcgen05 tensor cores (3xTF32; two kernels: geometry update, attention).
  * pre_out / k_out ([rows,128], nullable) save the filter_geo pre-activation and the keys. */
-int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_forward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                         const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
                         const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
                         const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
@@ -126,7 +165,7 @@ int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0,
                         float* k_out, void* stream);
 /* LocalAttention.call with g_update=False (attention.py:155): geometry' = swish(rbf(d) @ Wf + bf) * w is
  * recomputed per layer from pair_d / pair_w; proj needs only its query block.  Inference only. */
-int scann_la_forward_noupdate_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                                  const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
                                  const int32_t* pair_j, const float* x, const float* proj, const float* pair_d,
                                  const float* pair_w, const float* centers, const float* Wf, const float* bf,
@@ -146,7 +185,7 @@ int scann_la_backward(int grid, const int32_t* ntiles, const int32_t* tile_a0, c
  * kbuf / prebuf: in = keys / filter_geo pre-activation saved by scann_la_forward_tc, out = d_k / d_pre.
  * dg: gradient w.r.t. g' from the next layer (dg_has_up != 0, updated in place) or scratch.
  * Two kernels (attention, geometry); the pair weight gradients are scann_la_wgrad_tc. */
-int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_backward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                          const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
                          const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
                          float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
@@ -155,11 +194,12 @@ int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0
 /* Pair weight gradients of one layer (3xTF32, MN-major operands) into wpart[grid][2][128][128]:
  * slot 0 = (x[j]*g')^T d_k (key/kernel), slot 1 = g^T d_pre (filter_geo rows 128..255).  Needs the d_k /
  * d_pre that scann_la_backward_tc left in kbuf / prebuf; off the critical path (side stream). */
-int scann_la_wgrad_tc(int grid, const int32_t* ntiles, const int32_t* pair_c, const int32_t* pair_j, const float* x,
+int scann_la_wgrad_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* pair_c, const int32_t* pair_j, const float* x,
                       const float* g_in, const float* g_new, const float* dk, const float* dpre, float* wpart,
                       void* stream);
 /* dWk += sum_cta wpart[cta][0] ; dW2 += sum_cta wpart[cta][1]  (per-CTA partial weight gradients). */
-int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2, void* stream);
+int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, int tile_stride, float* dWk, float* dW2,
+                          void* stream);
 
 /* ---- global attention + property head ---------------------------------------------------------
  * GlobalAttention.call (scann/layers/attention.py:267-318) + bf_property / predict_property / mrelu
@@ -193,6 +233,8 @@ int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream);
 int scann_debug_clocks(long long* host_out32);
 /* Same for CTA (0,0) of the last dense_tc launch; host_out16: 16 int64 (HOST). */
 int scann_debug_clocks_dense(long long* host_out16);
+/* Same for CTA 0 of the last dense_chain launch (3 prologue stamps, then 4 per step); host_out64: 64 int64 (HOST). */
+int scann_debug_clocks_chain(long long* host_out64);
 
 #ifdef __cplusplus
 }

@@ -23,24 +23,25 @@ PROTOTYPES = {
     "scann_device_sm_count": (ci, []),
     "scann_device_cc": (ci, []),
     "scann_set_pdl": (ci, [ci]),
-    "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
+    "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
     "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp]),
     "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp]),
-    "scann_geom_init_forward": (ci, [vp, ci] + [vp] * 10 + [vp]),
-    "scann_geom_init_backward": (ci, [vp, ci] + [vp] * 14 + [vp]),
+    "scann_geom_init_forward": (ci, [vp, ci, ci] + [vp] * 10 + [vp]),
+    "scann_geom_init_backward": (ci, [vp, ci, ci] + [vp] * 14 + [vp]),
     "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_forward_tc": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
+    "scann_dense_chain": (ci, [vp, ci, ci, vp]),
     "scann_dense_wgrad": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp]),
     "scann_layernorm_backward": (ci, [vp, vp, vp, ci, vp, vp, ci, vp, vp, vp]),
     "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
-    "scann_la_forward_tc": (ci, [ci] + [vp] * 23 + [vp]),
-    "scann_la_forward_noupdate_tc": (ci, [ci] + [vp] * 21 + [vp]),
+    "scann_la_forward_tc": (ci, [ci, ci] + [vp] * 23 + [vp]),
+    "scann_la_forward_noupdate_tc": (ci, [ci, ci] + [vp] * 21 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
-    "scann_la_backward_tc": (ci, [ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
-    "scann_la_wgrad_tc": (ci, [ci] + [vp] * 9 + [vp]),
-    "scann_la_wpart_reduce": (ci, [vp, vp, ci, vp, vp, vp]),
+    "scann_la_backward_tc": (ci, [ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
+    "scann_la_wgrad_tc": (ci, [ci, ci] + [vp] * 9 + [vp]),
+    "scann_la_wpart_reduce": (ci, [vp, vp, ci, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),
@@ -50,7 +51,35 @@ PROTOTYPES = {
     "scann_tc_time": (ci, [vp, ci, ci, ci, vp]),
     "scann_debug_clocks": (ci, [vp]),
     "scann_debug_clocks_dense": (ci, [vp]),
+    "scann_debug_clocks_chain": (ci, [vp]),
 }
+
+
+class ChainStep(C.Structure):
+    """``ScannChainStep`` of include/scann_b200.h (one step of ``scann_dense_chain``)."""
+    _fields_ = ([("A", vp * 3), ("W", vp * 3)] +
+                [(n, vp) for n in ("bias", "resid", "pre_in", "pre_out", "gamma", "beta", "dgamma", "dbeta", "C", "C2",
+                                   "cnt", "np_ctx", "np_out")] +
+                [(n, ci) for n in ("lda", "ldres", "ldpre", "ldc", "ldc2", "kblk", "mode", "to_image")])
+
+
+def chain_step(A=(), W=(), bias=0, resid=0, ldres=128, pre_in=0, pre_out=0, ldpre=128, gamma=0, beta=0, dgamma=0,
+               dbeta=0, C_=0, ldc=128, C2=0, ldc2=128, cnt=0, np_ctx=0, np_out=0, lda=128, mode=0, to_image=False):
+    """Builds one ChainStep from integer device addresses (0 = NULL).  ``A`` empty: the operand is the image
+    left in shared memory by the previous step."""
+    st = ChainStep()
+    for i, p in enumerate(A):
+        st.A[i] = p or None
+    for i, p in enumerate(W):
+        st.W[i] = p or None
+    st.kblk = len(W)
+    for name, val in (("bias", bias), ("resid", resid), ("pre_in", pre_in), ("pre_out", pre_out), ("gamma", gamma),
+                      ("beta", beta), ("dgamma", dgamma), ("dbeta", dbeta), ("C", C_), ("C2", C2), ("cnt", cnt),
+                      ("np_ctx", np_ctx), ("np_out", np_out)):
+        setattr(st, name, val or None)
+    st.lda, st.ldres, st.ldpre, st.ldc, st.ldc2 = lda, ldres, ldpre, ldc, ldc2
+    st.mode, st.to_image = mode, 1 if to_image else 0
+    return st
 
 
 class ScannAbiError(RuntimeError):

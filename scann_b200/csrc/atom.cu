@@ -154,16 +154,16 @@ __global__ void __launch_bounds__(128) embed_bwd_final_kernel(int E, int n_atoms
 __device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF + 1], int* s_c, float* s_d, float* s_w,
                                                const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
                                                const float* __restrict__ pair_w, const float* __restrict__ cd,
-                                               const float* __restrict__ cw, size_t base) {
+                                               const float* __restrict__ cw, size_t base, int stride) {
     // per-tile pair data -> smem (one coalesced pass), then the 2 x 20 Gaussians of every row
-    if (threadIdx.x < SCANN_TILE) {
+    if ((int)threadIdx.x < stride) {
         const int c = pair_c[base + threadIdx.x];
         s_c[threadIdx.x] = c;
         s_d[threadIdx.x] = c >= 0 ? pair_d[base + threadIdx.x] : 0.f;
         s_w[threadIdx.x] = c >= 0 ? pair_w[base + threadIdx.x] : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < SCANN_TILE * 2 * SCANN_RBF; i += blockDim.x) {
+    for (int i = threadIdx.x; i < stride * 2 * SCANN_RBF; i += blockDim.x) {
         const int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
         const float x = (k < SCANN_RBF) ? s_d[row] : s_w[row];
         const float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
@@ -173,7 +173,7 @@ __device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF + 1]
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __restrict__ ntiles,
+__global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __restrict__ ntiles, int stride,
                                                             const int32_t* __restrict__ pair_c,
                                                             const float* __restrict__ pair_d,
                                                             const float* __restrict__ pair_w,
@@ -195,12 +195,12 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
     pdl_wait();                                   // weights above are parameters; the plan is a predecessor's output
     const int nt = *ntiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t base = (size_t)t * SCANN_TILE;
+        const size_t base = (size_t)t * stride;
         __syncthreads();
         if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
+        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
 #pragma unroll 4
-        for (int row = half; row < SCANN_TILE; row += 2) {
+        for (int row = half; row < stride; row += 2) {
             float a = bdn, b = bwn;
 #pragma unroll
             for (int k = 0; k < SCANN_RBF; ++k) {
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
 }
 
 // Backward: accumulates dWd, dbd, dWw, dbw from d_g0 (no gradient flows to distances/weights).
-__global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __restrict__ ntiles,
+__global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
                                                             const int32_t* __restrict__ pair_c,
                                                             const float* __restrict__ pair_d,
                                                             const float* __restrict__ pair_w,
@@ -241,12 +241,12 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
     pdl_wait();
     const int nt = *ntiles;
     for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t base = (size_t)t * SCANN_TILE;
+        const size_t base = (size_t)t * stride;
         __syncthreads();
         if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base);
+        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
         // the gradient rows of this thread's half are independent loads: keep 8 in flight
-        for (int r8 = half; r8 < SCANN_TILE; r8 += 16) {
+        for (int r8 = half; r8 < stride; r8 += 16) {
             float dv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) dv[q] = dg0[(base + r8 + 2 * q) * SCANN_D + n];
@@ -570,21 +570,23 @@ extern "C" int scann_embed_backward(const int32_t* atomic, const float* ring, in
     return scann_check_launch("scann_embed_backward");
 }
 
-extern "C" int scann_geom_init_forward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+extern "C" int scann_geom_init_forward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c, const float* pair_d,
                                        const float* pair_w, const float* centers_d, const float* centers_w,
                                        const float* Wd, const float* bd, const float* Ww, const float* bw, float* g0,
                                        void* stream) {
-    scann_launch(geom_init_fwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
+    scann_launch(geom_init_fwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, g0);
     return scann_check_launch("scann_geom_init_forward");
 }
 
-extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, const int32_t* pair_c, const float* pair_d,
+extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c, const float* pair_d,
                                         const float* pair_w, const float* centers_d, const float* centers_w,
                                         const float* Wd, const float* bd, const float* Ww, const float* bw,
                                         const float* dg0, float* dWd, float* dbd, float* dWw, float* dbw,
                                         void* stream) {
-    scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, pair_c, pair_d, pair_w, centers_d, centers_w,
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
+    scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
     return scann_check_launch("scann_geom_init_backward");
 }

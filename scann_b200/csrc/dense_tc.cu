@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
         tc_fence_before();
         __syncthreads();
         if (kb == 0) DCLK(2);
-        if (tid == 0) {
+        if (warp == 0 && tc_elect_one()) {
             tc_fence_after();
             const uint64_t dh = tc_desc_kmajor(smem_u32(sXhi), 0), dl = tc_desc_kmajor(smem_u32(sXlo), 0);
             const bool first = kb == 0;

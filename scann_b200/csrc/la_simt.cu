@@ -537,9 +537,9 @@ __global__ void __launch_bounds__(LA_THREADS, 1) la_bwd_simt_kernel(const LaBwdA
 
 // dWk += sum_cta wpart[cta][0], dW2 += sum_cta wpart[cta][1]
 __global__ void __launch_bounds__(256) la_wpart_reduce_kernel(const float* __restrict__ wpart,
-                                                              const int32_t* __restrict__ ntiles, int grid,
+                                                              const int32_t* __restrict__ ntiles, int grid, int groups,
                                                               float* __restrict__ dWk, float* __restrict__ dW2) {
-    const int nact = min(grid, *ntiles);
+    const int nact = min(grid, (*ntiles + groups - 1) / groups);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 2*128*128
     if (i >= 2 * SCANN_D * SCANN_D) return;
     float s = 0.f;
@@ -594,9 +594,11 @@ extern "C" int scann_la_backward(int grid, const int32_t* ntiles, const int32_t*
 }
 
 // dWk += sum over CTAs of wpart[cta][0], dW2 += sum of wpart[cta][1]; `grid` as in scann_la_backward.
-extern "C" int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, float* dWk, float* dW2,
-                                     void* stream) {
-    la_wpart_reduce_kernel<<<(2 * SCANN_D * SCANN_D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(wpart, ntiles, grid,
-                                                                                               dWk, dW2);
+// tile_stride as in scann_la_wgrad_tc (CTA c produced a partial iff c * (128 / tile_stride) < ntiles).
+extern "C" int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, int tile_stride, float* dWk,
+                                     float* dW2, void* stream) {
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_wpart_reduce: tile_stride must be 64 or 128"); return 1; }
+    la_wpart_reduce_kernel<<<(2 * SCANN_D * SCANN_D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        wpart, ntiles, grid, SCANN_TILE / tile_stride, dWk, dW2);
     return scann_check_launch("scann_la_wpart_reduce");
 }

@@ -14,12 +14,34 @@
 //
 // Both weights of a layer (4 x 64 KB as hi/lo tf32) exceed one SM's shared + tensor memory next to the
 // tile operands, hence two kernels; g' makes one extra round trip through L2/HBM.
+//
+// Warp groups.  A tile's phases (global loads -> operand images -> MMA -> TMEM read-back -> row epilogue)
+// are a dependent chain that leaves the SM idle most of the time (ncu: 20-27 % issue utilisation, long-
+// scoreboard and barrier stalls).  The kernels are therefore templated on NG = number of independent WARP
+// GROUPS per CTA: the 16 warps split into NG groups of 16/NG warps, each group owns its own tile stream
+// (tiles of TR = 128/NG rows, tile t -> group t % NG of CTA (t / NG) % grid), its own operand images,
+// mbarrier and accumulator columns, and synchronises with a named barrier (bar.sync 1+g).  The groups share
+// the stationary weight in tensor memory and drift out of phase, so one group's MMA / memory latency hides
+// behind the other's epilogue -- two CTAs per SM would do the same but cannot share the 256 weight columns.
+// NG = 1 is the original single-stream kernel (needed when an atom has more than 64 neighbours).
 #include "common.cuh"
 #include "tc_common.cuh"
 
 #define LTC_THREADS 512
 #define LTC_WARPS 16
-#define LTC_RPW 8                          // rows per warp in the row-wise epilogue
+#define LTC_RPW 8                          // rows per warp in the row-wise epilogue (= TR / warps per group)
+
+template <int NG>
+struct LaGroups {
+    static constexpr int TR = SCANN_TILE / NG;                     // pair rows per tile (MMA N extent)
+    static constexpr int WG = LTC_WARPS / NG;                      // warps per group
+    static constexpr int GT = LTC_THREADS / NG;                    // threads per group
+    static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;   // bytes of one K-major image of TR rows
+};
+// barrier among the GT threads of warp group g (barrier 0 stays __syncthreads)
+__device__ __forceinline__ void group_sync(int g, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
 
 // phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks: development aid
 __device__ long long g_dbg_clk[32];
@@ -51,9 +73,10 @@ __device__ __forceinline__ void weightT_to_tmem(const float* __restrict__ W, uin
 // Fully unrolled with the descriptors advanced by immediates: a single thread issues all MMAs, so
 // every extra instruction per MMA shows up as tensor-pipe idle time (measured: 107 cycles per MMA
 // with descriptors rebuilt in the loop vs the 64-cycle math floor of a 128x128x8 tf32 MMA).
+template <int TR>
 __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
                                              uint32_t t_dc, uint64_t* bar) {
-    const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
+    const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
@@ -64,7 +87,8 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uin
     tc_commit(bar);
 }
 
-// accumulators (lane = feature n, column = row r) -> S[r][n] (+ bias[n]); warp w: lanes 32*(w%4).., rows 32*(w/4)..
+// accumulators (lane = feature n, column = row r) -> S[r][n] (+ bias[n]); warp w of its group: lanes 32*(w%4)..,
+// rows 32*(w/4)..  (the group's 16/NG warps cover its 128/NG rows)
 __device__ __forceinline__ void tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8_t* S, const float* __restrict__ bias,
                                              int warp, int lane) {
     const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 32;
@@ -94,40 +118,50 @@ struct LaGeomArgs {
     float* pre_out;          // [rows,128] pre-activation of filter_geo (nullable; saved for backward)
 };
 
+template <int NG>
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const LaGeomArgs a) {
+    using G = LaGroups<NG>;
+    constexpr int TR = G::TR, WG = G::WG, GT = G::GT;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sHi = smem;
-    uint8_t* sLo = smem + TC_TILE_BYTES;
-    uint8_t* sS = smem + 2 * TC_TILE_BYTES;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[NG];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WG, wg = warp % WG, gtid = tid - grp * GT;
+    uint8_t* sHi = smem + (size_t)grp * 3 * G::IMG;
+    uint8_t* sLo = sHi + G::IMG;
+    uint8_t* sS = sLo + G::IMG;
+    uint64_t* bar = &bars[grp];
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid < NG) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256 + grp * 2 * TR, t_dc = t_dm + TR;
     DBG_CLK(0);
     weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);     // parameters only: overlaps the predecessor kernel's tail
     pdl_wait();
     const int nt = *a.ntiles;
+    tc_fence_before();
+    __syncthreads();                                     // the whole weight is in tensor memory for every group
+    tc_fence_after();
     DBG_CLK(1);
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t rowbase = (size_t)t * SCANN_TILE;
+    const int t_first = blockIdx.x * NG + grp, t_step = gridDim.x * NG;
+    for (int t = t_first; t < nt; t += t_step) {
+        const size_t rowbase = (size_t)t * TR;
         // ---- stage the geometry tile: coalesced loads, hi/lo split, K-major images
         {
             float4 v[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int i = tid + it * LTC_THREADS;
+                const int i = gtid + it * GT;
                 v[it] = ld4(a.g_in + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-                const int i = tid + it * LTC_THREADS;
+                const int i = gtid + it * GT;
                 float4 h, l;
                 tf32_split(v[it].x, h.x, l.x); tf32_split(v[it].y, h.y, l.y);
                 tf32_split(v[it].z, h.z, l.z); tf32_split(v[it].w, h.w, l.w);
@@ -138,13 +172,13 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (t == (int)blockIdx.x) DBG_CLK(2);
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (t == t_first) DBG_CLK(2);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
+            issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);
         }
-        if (t == (int)blockIdx.x) DBG_CLK(3);
+        if (t == t_first) DBG_CLK(3);
         // ---- while the tensor core works: indices and gathered projections of this warp's rows
         // (row groups: 2 steps x 4 rows per warp, 8 lanes per row, 16 columns per lane)
         const int l8 = lane & 7, rsub = lane >> 3;
@@ -152,7 +186,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         float4 p13[2][4];
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = sp * 64 + warp * 4 + rsub;
+            const int r = sp * (TR / 2) + wg * 4 + rsub;
             pc[sp] = a.pair_c[rowbase + r];
             if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
             const int j = pc[sp] >= 0 ? a.pair_j[rowbase + r] : 0;
@@ -164,21 +198,21 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
                                     ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + c0));
             }
         }
-        if (t == (int)blockIdx.x) DBG_CLK(4);
-        mbar_wait(&bar, phase);
+        if (t == t_first) DBG_CLK(4);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
-        if (t == (int)blockIdx.x) DBG_CLK(5);
-        tmem_to_rows(t_dm, t_dc, sS, nullptr, warp, lane);
+        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
+        if (t == t_first) DBG_CLK(5);
+        tmem_to_rows(t_dm, t_dc, sS, nullptr, wg, lane);
         tc_fence_before();
-        __syncthreads();
-        if (t == (int)blockIdx.x) DBG_CLK(6);
+        group_sync(grp, GT);
+        if (t == t_first) DBG_CLK(6);
         // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
             if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;        // the warp's 4 rows are padding
-            const int r = sp * 64 + warp * 4 + rsub;
+            const int r = sp * (TR / 2) + wg * 4 + rsub;
             float z[4][4], pre[4][4];
             float s1 = 0.f;
 #pragma unroll
@@ -217,8 +251,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
                 if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + c0, po);
             }
         }
-        __syncthreads();                 // images and S are rewritten by the next tile
-        if (t == (int)blockIdx.x) DBG_CLK(7);
+        group_sync(grp, GT);             // images and S are rewritten by the next tile
+        if (t == t_first) DBG_CLK(7);
     }
     DBG_CLK(8);
     pdl_trigger();
@@ -245,36 +279,46 @@ struct LaAttnArgs {
     const float* pair_d; const float* pair_w; const float* centers; const float* Wf; const float* bf;
 };
 
+template <int NG>
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const LaAttnArgs a) {
+    using G = LaGroups<NG>;
+    constexpr int TR = G::TR, WG = G::WG, GT = G::GT;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sHi = smem;
-    uint8_t* sLo = smem + TC_TILE_BYTES;
-    uint8_t* sS = smem + 2 * TC_TILE_BYTES;
-    float* Es = reinterpret_cast<float*>(smem + 3 * TC_TILE_BYTES);      // [128][8]
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[NG];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WG, wg = warp % WG, gtid = tid - grp * GT;
+    uint8_t* sHi = smem + (size_t)grp * 3 * G::IMG;
+    uint8_t* sLo = sHi + G::IMG;
+    uint8_t* sS = sLo + G::IMG;
+    float* Es = reinterpret_cast<float*>(smem + 3 * TC_TILE_BYTES) + grp * TR * 8;      // [TR][8] per group
+    uint64_t* bar = &bars[grp];
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid < NG) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256 + grp * 2 * TR, t_dc = t_dm + TR;
     weightT_to_tmem(a.Wk, t_whi, t_wlo, warp, lane);
     const float4 gam = ldg4(a.gamma + lane * 4), bet = ldg4(a.beta + lane * 4);
     pdl_wait();
     const int nt = *a.ntiles;
+    tc_fence_before();
+    __syncthreads();                                     // the whole weight is in tensor memory for every group
+    tc_fence_after();
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t rowbase = (size_t)t * SCANN_TILE;
+    const int t_step = gridDim.x * NG;
+    for (int t = blockIdx.x * NG + grp; t < nt; t += t_step) {
+        const size_t rowbase = (size_t)t * TR;
         // row groups: 2 steps x 4 rows per warp, 8 lanes per row, 16 columns per lane
         const int l8 = lane & 7, rsub = lane >> 3;
         int pc[2];
         // ---- stage a = x[j] * g' (coalesced row loads and gathers), hi/lo images
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
-            const int r = sp * 64 + warp * 4 + rsub;
+            const int r = sp * (TR / 2) + wg * 4 + rsub;
             pc[sp] = a.pair_c[rowbase + r];
             if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;       // operand rows of padding stay stale: harmless,
                                                                      // column r of D^T depends on operand row r only
@@ -334,10 +378,10 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);
+            issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);
         }
         // ---- prefetch the queries of this warp's rows while the tensor core works
         float4 qv[2][4];
@@ -349,18 +393,18 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
                 if (pc[sp] >= 0)
                     qv[sp][it] = ld4(a.proj + (size_t)pc[sp] * 3 * SCANN_D + 2 * SCANN_D + (l8 + 8 * it) * 4);
             }
-        mbar_wait(&bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
-        tmem_to_rows(t_dm, t_dc, sS, a.bk, warp, lane);          // keys k = a @ Wk + bk
+        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
+        tmem_to_rows(t_dm, t_dc, sS, a.bk, wg, lane);            // keys k = a @ Wk + bk
         tc_fence_before();
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = chunks 4h..4h+3 = 4 adjacent lanes)
 #pragma unroll
         for (int sp = 0; sp < 2; ++sp) {
             if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
-            const int r = sp * 64 + warp * 4 + rsub;
+            const int r = sp * (TR / 2) + wg * 4 + rsub;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r, l8 + 8 * it));
@@ -372,10 +416,10 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
                         pc[sp] >= 0 ? kv : make_float4(0.f, 0.f, 0.f, 0.f));
             }
         }
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- per atom: softmax over its rows, context, residual q, LayerNorm (one warp per atom)
         const int a0 = a.tile_a0[t], a1 = a.tile_a1[t];
-        for (int atom = a0 + warp; atom < a1; atom += LTC_WARPS) {
+        for (int atom = a0 + wg; atom < a1; atom += WG) {
             const int n = a.cnt[atom];
             if (n == 0) continue;
             const int r0 = a.rowptr[atom] - (int)rowbase;
@@ -402,7 +446,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
                 make_float4(c0 * inv * gam.x + bet.x, c1 * inv * gam.y + bet.y, c2 * inv * gam.z + bet.z,
                             c3 * inv * gam.w + bet.w));
         }
-        __syncthreads();
+        group_sync(grp, GT);
     }
     pdl_trigger();
     tc_fence_before();
@@ -413,54 +457,65 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
 #define LA_GEOM_SMEM (3 * TC_TILE_BYTES)
 #define LA_ATTN_SMEM (3 * TC_TILE_BYTES + SCANN_TILE * 8 * sizeof(float))
 
+static int la_fwd_configure() {
+    static bool configured = false;
+    if (configured) return 0;
+    cudaError_t e = cudaFuncSetAttribute(la_geom_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_geom_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
+    if (e != cudaSuccess) { scann_set_error("la_forward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+    configured = true;
+    return 0;
+}
+
 // Tensor-core forward of LocalAttention.call (attention.py:118-216); same data contract as
 // scann_la_forward plus the optional training saves pre_out / k_out ([rows,128] each).
-extern "C" int scann_la_forward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
-                                   const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
-                                   const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
-                                   const float* W2, const float* Wk, const float* bk, const float* gamma_g,
-                                   const float* beta_g, const float* gamma, const float* beta, float* g_out,
-                                   float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
+// tile_stride = rows per tile slot of the pair plan (scann_plan_build): 128 (one tile stream per CTA) or
+// 64 (two warp groups per CTA, each streaming 64-row tiles).
+extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+                                   const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
+                                   const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
+                                   const float* g_in, const float* W2, const float* Wk, const float* bk,
+                                   const float* gamma_g, const float* beta_g, const float* gamma, const float* beta,
+                                   float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
                                    void* stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(la_geom_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)LA_GEOM_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
-        if (e != cudaSuccess) { scann_set_error("la_forward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
-        configured = true;
-    }
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
-    scann_launch(la_geom_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr};
-    scann_launch(la_attn_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    if (tile_stride == 64) {
+        scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
+        scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    } else {
+        scann_launch(la_geom_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
+        scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    }
     return scann_check_launch("scann_la_forward_tc");
 }
 
 // LocalAttention.call with g_update = False (attention.py:155-216): neighbor_geometry' =
 // swish(rbf(distance) @ Wf + bf) * weight is recomputed per layer from the 8 bytes/pair of raw geometry;
 // proj needs only its query block (columns 256..383).  Inference path (no saves for backward).
-extern "C" int scann_la_forward_noupdate_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0,
+extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
                                             const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                             const int32_t* pair_c, const int32_t* pair_j, const float* x,
                                             const float* proj, const float* pair_d, const float* pair_w,
                                             const float* centers, const float* Wf, const float* bf, const float* Wk,
                                             const float* bk, const float* gamma, const float* beta, float* ctx_pre,
                                             float* out, float* attn, void* stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)LA_ATTN_SMEM);
-        if (e != cudaSuccess) { scann_set_error("la_forward_noupdate_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
-        configured = true;
-    }
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, nullptr, pair_d, pair_w, centers, Wf, bf};
-    scann_launch(la_attn_fwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    else scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");
 }
 

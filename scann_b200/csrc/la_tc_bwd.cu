@@ -18,6 +18,18 @@
 #define LTC_WARPS 16
 #define LTC_RPW 8
 
+// warp groups: see la_tc.cu
+template <int NG>
+struct LaGroups {
+    static constexpr int TR = SCANN_TILE / NG;
+    static constexpr int WG = LTC_WARPS / NG;
+    static constexpr int GT = LTC_THREADS / NG;
+    static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;
+};
+__device__ __forceinline__ void group_sync(int g, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
+
 // ---- helpers shared with la_tc.cu (kept static to this translation unit) ----
 __device__ __forceinline__ void b_weightT_to_tmem(const float* __restrict__ W, uint32_t t_hi, uint32_t t_lo, int warp,
                                                   int lane) {
@@ -37,9 +49,10 @@ __device__ __forceinline__ void b_weightT_to_tmem(const float* __restrict__ W, u
     tmem_st_wait();
 }
 
+template <int TR>
 __device__ __forceinline__ void b_issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
                                                uint32_t t_dc, uint64_t* bar) {
-    const uint32_t idesc = tc_idesc_tf32(128, 128, false, false);
+    const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
@@ -90,43 +103,53 @@ struct LaAttnBwdArgs {
     float* dbk;              // [128]   += column sums of d_k
 };
 
+template <int NG>
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const LaAttnBwdArgs a) {
+    using G = LaGroups<NG>;
+    constexpr int TR = G::TR, WG = G::WG, GT = G::GT;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sHi = smem;
-    uint8_t* sLo = smem + TC_TILE_BYTES;
-    uint8_t* sS = smem + 2 * TC_TILE_BYTES;                                  // keys, later d_a
-    float* Es = reinterpret_cast<float*>(smem + 3 * TC_TILE_BYTES);          // [128][8] e -> p
-    float* Ds = Es + SCANN_TILE * 8;                                         // [128][8] dp -> de
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[NG];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_dbk[SCANN_D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WG, wg = warp % WG, gtid = tid - grp * GT;
+    uint8_t* sHi = smem + (size_t)grp * 3 * G::IMG;
+    uint8_t* sLo = sHi + G::IMG;
+    uint8_t* sS = sLo + G::IMG;                                              // keys, later d_a
+    float* Es = reinterpret_cast<float*>(smem + 3 * TC_TILE_BYTES) + grp * 2 * TR * 8;   // [TR][8] e -> p
+    float* Ds = Es + TR * 8;                                                 // [TR][8] dp -> de
+    uint64_t* bar = &bars[grp];
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid < NG) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
     if (tid < SCANN_D) s_dbk[tid] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256 + grp * 2 * TR, t_dc = t_dm + TR;
     // stationary operand A[M = ka][K = n] = Wk[ka][n]  (= transpose of WkT, loaded coalesced)
     b_weightT_to_tmem(a.WkT, t_whi, t_wlo, warp, lane);
     pdl_wait();
     const int nt = *a.ntiles;
+    tc_fence_before();
+    __syncthreads();                                     // the whole weight is in tensor memory for every group
+    tc_fence_after();
     float4 dbk = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t rowbase = (size_t)t * SCANN_TILE;
+    const int t_step = gridDim.x * NG;
+    for (int t = blockIdx.x * NG + grp; t < nt; t += t_step) {
+        const size_t rowbase = (size_t)t * TR;
         int pc[LTC_RPW];
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + wg + WG * i];
         // ---- phase A: keys -> S ; e = 0.25 <q_h,k_h>, dp = <dctx_h,k_h> per (row, head)
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
             float4 kv[4], qv[4], dc[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 kv[ii] = make_float4(0.f, 0.f, 0.f, 0.f); qv[ii] = kv[ii]; dc[ii] = kv[ii];
                 if (pc[i] >= 0) {
                     kv[ii] = ld4(a.kbuf + (rowbase + r) * SCANN_D + lane * 4);
@@ -136,7 +159,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int r = warp + LTC_WARPS * (hb * 4 + ii);
+                const int r = wg + WG * (hb * 4 + ii);
                 if (pc[hb * 4 + ii] < 0) continue;                       // padding row (warp-uniform)
                 *reinterpret_cast<float4*>(sS + tc_off4(r, lane)) = kv[ii];
                 float e = kv[ii].x * qv[ii].x + kv[ii].y * qv[ii].y + kv[ii].z * qv[ii].z + kv[ii].w * qv[ii].w;
@@ -146,10 +169,10 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                 if ((lane & 3) == 0) { Es[r * 8 + (lane >> 2)] = e; Ds[r * 8 + (lane >> 2)] = d; }
             }
         }
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- phase B (warp per atom): p, de ; dq = d_ctx + 0.25 sum_n de k
         const int a0 = a.tile_a0[t], a1 = a.tile_a1[t];
-        for (int atom = a0 + warp; atom < a1; atom += LTC_WARPS) {
+        for (int atom = a0 + wg; atom < a1; atom += WG) {
             const int n = a.cnt[atom];
             if (n == 0) continue;
             const int r0 = a.rowptr[atom] - (int)rowbase;
@@ -190,7 +213,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                     make_float4(dc.x + 0.25f * c0, dc.y + 0.25f * c1, dc.z + 0.25f * c2, dc.w + 0.25f * c3));
             }
         }
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- phase C: dk = p d_ctx[c] + 0.25 de q[c] -> hi/lo images, global (in place over k), dbk
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
@@ -206,7 +229,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 if (pc[i] < 0) continue;
                 float4 dk = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (pc[i] >= 0) {
@@ -221,18 +244,18 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            b_issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);     // d_a^T = Wk dk^T
+            b_issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);     // d_a^T = Wk dk^T
         }
-        mbar_wait(&bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
-        b_tmem_to_rows(t_dm, t_dc, sS, warp, lane);
+        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
+        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane);
         tc_fence_before();
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- phase D: d_nbr = d_a * g' -> dx[j] ; dg' (+)= d_a * x[j]
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
@@ -240,7 +263,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
             int jj[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 gp[ii] = make_float4(0.f, 0.f, 0.f, 0.f); xj[ii] = gp[ii]; dg[ii] = gp[ii];
                 jj[ii] = 0;
                 if (pc[i] >= 0) {
@@ -252,7 +275,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 if (pc[i] < 0) continue;
                 float4 da = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
                 if (pc[i] >= 0) {
@@ -264,7 +287,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                 st4(a.dg + (rowbase + r) * SCANN_D + lane * 4, dg[ii]);
             }
         }
-        __syncthreads();
+        group_sync(grp, GT);
     }
     pdl_trigger();
     atomicAdd(&s_dbk[lane * 4 + 0], dbk.x); atomicAdd(&s_dbk[lane * 4 + 1], dbk.y);
@@ -292,36 +315,46 @@ struct LaGeomBwdArgs {
     float* dgamma_g; float* dbeta_g;
 };
 
+template <int NG>
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const LaGeomBwdArgs a) {
+    using G = LaGroups<NG>;
+    constexpr int TR = G::TR, WG = G::WG, GT = G::GT;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sHi = smem;
-    uint8_t* sLo = smem + TC_TILE_BYTES;
-    uint8_t* sS = smem + 2 * TC_TILE_BYTES;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[NG];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_acc[2 * SCANN_D];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WG, wg = warp % WG, gtid = tid - grp * GT;
+    uint8_t* sHi = smem + (size_t)grp * 3 * G::IMG;
+    uint8_t* sLo = sHi + G::IMG;
+    uint8_t* sS = sLo + G::IMG;
+    uint64_t* bar = &bars[grp];
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (tid < NG) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
     if (tid < 2 * SCANN_D) s_acc[tid] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 384;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256 + grp * 2 * TR, t_dc = t_dm + TR;
     // stationary operand A[M = k][K = n] = W2[k][n]: (d_pre W2^T)^T = W2 d_pre^T
     b_weightT_to_tmem(a.W2T, t_whi, t_wlo, warp, lane);
     const float4 gam = ldg4(a.gamma_g + lane * 4);
     pdl_wait();
     const int nt = *a.ntiles;
+    tc_fence_before();
+    __syncthreads();                                     // the whole weight is in tensor memory for every group
+    tc_fence_after();
     float4 dgam = make_float4(0.f, 0.f, 0.f, 0.f), dbet = dgam;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t rowbase = (size_t)t * SCANN_TILE;
+    const int t_step = gridDim.x * NG;
+    for (int t = blockIdx.x * NG + grp; t < nt; t += t_step) {
+        const size_t rowbase = (size_t)t * TR;
         int pc[LTC_RPW];
         float4 dz[LTC_RPW];
 #pragma unroll
-        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + warp + LTC_WARPS * i];
+        for (int i = 0; i < LTC_RPW; ++i) pc[i] = a.pair_c[rowbase + wg + WG * i];
         // ---- phase A: recompute z statistics, LN_g backward, d_pre
 #pragma unroll
         for (int hb = 0; hb < 2; ++hb) {
@@ -329,7 +362,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
             int jj[4];
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 pv[ii] = make_float4(0.f, 0.f, 0.f, 0.f); gv[ii] = pv[ii]; dv[ii] = pv[ii];
                 jj[ii] = 0;
                 if (pc[i] >= 0) {
@@ -341,7 +374,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
             }
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
-                const int i = hb * 4 + ii, r = warp + LTC_WARPS * i;
+                const int i = hb * 4 + ii, r = wg + WG * i;
                 if (pc[i] < 0) { dz[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }      // padding row
                 const float pre[4] = {pv[ii].x, pv[ii].y, pv[ii].z, pv[ii].w};
                 const float g[4] = {gv[ii].x, gv[ii].y, gv[ii].z, gv[ii].w};
@@ -387,14 +420,14 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            b_issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, &bar);     // W2 d_pre^T
+            b_issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);     // W2 d_pre^T
         }
         // ---- phase B (warp per atom, overlaps the MMA): s_pre[c] = sum_n d_pre
         const int a0 = a.tile_a0[t], a1 = a.tile_a1[t];
-        for (int atom = a0 + warp; atom < a1; atom += LTC_WARPS) {
+        for (int atom = a0 + wg; atom < a1; atom += WG) {
             const int n = a.cnt[atom];
             if (n == 0) continue;
             const int r0 = a.rowptr[atom] - (int)rowbase;
@@ -406,23 +439,23 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
             }
             st4(a.s_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
         }
-        mbar_wait(&bar, phase);
+        mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();     // last tile of this CTA, only its epilogue is left
-        b_tmem_to_rows(t_dm, t_dc, sS, warp, lane);
+        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
+        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane);
         tc_fence_before();
-        __syncthreads();
+        group_sync(grp, GT);
         // ---- phase C: dg = d_z + d_pre @ W2^T
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i) {
-            const int r = warp + LTC_WARPS * i;
+            const int r = wg + WG * i;
             if (pc[i] < 0) continue;
             float4 v = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
             st4(a.dg_out + (rowbase + r) * SCANN_D + lane * 4,
                 make_float4(v.x + dz[i].x, v.y + dz[i].y, v.z + dz[i].z, v.w + dz[i].w));
         }
-        __syncthreads();
+        group_sync(grp, GT);
     }
     pdl_trigger();
     atomicAdd(&s_acc[lane * 4 + 0], dgam.x); atomicAdd(&s_acc[lane * 4 + 1], dgam.y);
@@ -456,33 +489,49 @@ __device__ __forceinline__ float rna_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// Each warp group accumulates X^T Y of its own tile stream in its own pair of accumulators (main, correction);
+// group 0 adds the other groups' sums (handed over through shared memory) and writes wpart[cta][mode].
+template <int NG>
 __global__ void __launch_bounds__(LTC_THREADS, 1) la_wgrad_tc_kernel(const LaWgradArgs a) {
+    using G = LaGroups<NG>;
+    constexpr int TR = G::TR, WG = G::WG, GT = G::GT;
+    constexpr uint32_t MNB = (uint32_t)TR * 128u;        // one column block: [TR rows x 32 columns], row pitch 128 B
+    constexpr uint32_t MNT = 4u * MNB;                   // one MN-major image [TR x 128] fp32
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // the BASE32B swizzle is a function of the absolute shared address: align the images to 1024 bytes
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sX = smem;                                 // X_hi, then X_lo
-    uint8_t* sYh = smem + TC_MN_TILE_BYTES;
-    uint8_t* sYl = smem + 2 * TC_MN_TILE_BYTES;
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[NG];
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_has[NG];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / WG, wg = warp % WG, gtid = tid - grp * GT;
+    uint8_t* sX = smem + (size_t)grp * 3 * MNT;          // X_hi, then X_lo
+    uint8_t* sYh = sX + MNT;
+    uint8_t* sYl = sYh + MNT;
+    uint64_t* bar = &bars[grp];
     const int nt = *a.ntiles;
-    if ((int)blockIdx.x >= nt) return;
-    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if ((int)blockIdx.x * NG >= nt) return;              // no tile for any group of this CTA
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256 * NG);
+    if (tid < NG) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t t_dm = tmem_base_s, t_dc = tmem_base_s + 128;
+    const uint32_t t_dm = tmem_base_s + grp * 256, t_dc = t_dm + 128;
     const uint32_t idesc = tc_idesc_tf32(128, 128, true, true);
+    auto mn_off = [](int r, int c) -> uint32_t {
+        return (uint32_t)(c >> 5) * MNB + (uint32_t)r * 128u + (((((uint32_t)c >> 3) & 3u) ^ ((uint32_t)r & 3u)) << 5) +
+               ((uint32_t)c & 7u) * 4u;
+    };
+    auto mn_desc = [](uint32_t saddr) -> uint64_t { return tc_desc(saddr, MNB, 512u) | ((uint64_t)1 << 61); };
     uint32_t phase = 0;
     bool first = true;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t rowbase = (size_t)t * SCANN_TILE;
+    for (int t = blockIdx.x * NG + grp; t < nt; t += gridDim.x * NG) {
+        const size_t rowbase = (size_t)t * TR;
         float4 xv[LTC_RPW], yv[LTC_RPW];
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i) {
-            const int r = warp + LTC_WARPS * i;
+            const int r = wg + WG * i;
             const int c = a.pair_c[rowbase + r];
             xv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             yv[i] = xv[i];
@@ -496,13 +545,13 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_wgrad_tc_kernel(const LaWgr
             }
         }
         if (!first) {                         // the previous tile's last MMAs still read the images
-            mbar_wait(&bar, phase);
+            mbar_wait(bar, phase);
             phase ^= 1;
             tc_fence_after();
         }
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i) {
-            const uint32_t off = tc_mn_off(warp + LTC_WARPS * i, lane * 4);
+            const uint32_t off = mn_off(wg + WG * i, lane * 4);
             float4 h, l;
             tf32_split(xv[i].x, h.x, l.x); tf32_split(xv[i].y, h.y, l.y);
             tf32_split(xv[i].z, h.z, l.z); tf32_split(xv[i].w, h.w, l.w);
@@ -512,59 +561,90 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_wgrad_tc_kernel(const LaWgr
         }
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            const uint64_t dx = tc_desc_mn32(smem_u32(sX), 0), dyh = tc_desc_mn32(smem_u32(sYh), 0),
-                           dyl = tc_desc_mn32(smem_u32(sYl), 0);
+            const uint64_t dx = mn_desc(smem_u32(sX)), dyh = mn_desc(smem_u32(sYh)), dyl = mn_desc(smem_u32(sYl));
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks)           // K-step = 8 pair rows = 1024 bytes of each image
+            for (int ks = 0; ks < TR / 8; ++ks)       // K-step = 8 pair rows = 1024 bytes of each image
                 tc_mma_ss(t_dm, dx + (uint64_t)(ks * 64), dyh + (uint64_t)(ks * 64), idesc, !(first && ks == 0));
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks)
+            for (int ks = 0; ks < TR / 8; ++ks)
                 tc_mma_ss(t_dc, dx + (uint64_t)(ks * 64), dyl + (uint64_t)(ks * 64), idesc, !(first && ks == 0));
-            tc_commit(&bar);
+            tc_commit(bar);
         }
-        mbar_wait(&bar, phase);              // X_hi has been consumed: replace it by X_lo
+        mbar_wait(bar, phase);               // X_hi has been consumed: replace it by X_lo
         phase ^= 1;
         tc_fence_after();
 #pragma unroll
         for (int i = 0; i < LTC_RPW; ++i)
-            *reinterpret_cast<float4*>(sX + tc_mn_off(warp + LTC_WARPS * i, lane * 4)) = xv[i];
+            *reinterpret_cast<float4*>(sX + mn_off(wg + WG * i, lane * 4)) = xv[i];
         fence_async_smem();
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        group_sync(grp, GT);
+        if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            const uint64_t dx = tc_desc_mn32(smem_u32(sX), 0), dyh = tc_desc_mn32(smem_u32(sYh), 0);
+            const uint64_t dx = mn_desc(smem_u32(sX)), dyh = mn_desc(smem_u32(sYh));
 #pragma unroll
-            for (int ks = 0; ks < 16; ++ks) tc_mma_ss(t_dc, dx + (uint64_t)(ks * 64), dyh + (uint64_t)(ks * 64), idesc, true);
-            tc_commit(&bar);
+            for (int ks = 0; ks < TR / 8; ++ks) tc_mma_ss(t_dc, dx + (uint64_t)(ks * 64), dyh + (uint64_t)(ks * 64), idesc, true);
+            tc_commit(bar);
         }
         first = false;
     }
-    mbar_wait(&bar, phase);
-    tc_fence_after();
-    // D[m][n] (lane = m, column = n) -> wpart[cta][mode][m][n]
-    float* dst = a.wpart + ((size_t)blockIdx.x * 2 + a.mode) * SCANN_D * SCANN_D;
-    {
-        const int m = (warp & 3) * 32 + lane, nbase = (warp >> 2) * 32;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
+    if (!first) {
+        mbar_wait(bar, phase);
+        tc_fence_after();
+    }
+    if (gtid == 0) s_has[grp] = first ? 0 : 1;
+    // D[m][n] (lane = m, column = n): warp wg of a group covers lanes 32*(wg%4).. and CPW columns from (wg/4)*CPW
+    constexpr int CPW = 512 / WG;
+    const int m = (wg & 3) * 32 + lane, nbase = (wg >> 2) * CPW;
+    const uint32_t lane_base = (uint32_t)((wg & 3) * 32) << 16;
+    float4* xfer = reinterpret_cast<float4*>(smem + (size_t)3 * MNT);     // groups >= 1 own this region (their images)
+    if (NG > 1 && grp > 0 && !first) {
+#pragma unroll 1
+        for (int h = 0; h < CPW / 16; ++h) {
             float v[16], c[16];
             tmem_ld16(t_dm + lane_base + nbase + h * 16, v);
             tmem_ld16(t_dc + lane_base + nbase + h * 16, c);
             tmem_ld_wait();
 #pragma unroll
             for (int q = 0; q < 16; q += 4)
-                st4(dst + (size_t)m * SCANN_D + nbase + h * 16 + q,
-                    make_float4(v[q] + c[q], v[q + 1] + c[q + 1], v[q + 2] + c[q + 2], v[q + 3] + c[q + 3]));
+                xfer[(size_t)((grp - 1) * (CPW / 4) + h * 4 + q / 4) * GT + gtid] =
+                    make_float4(v[q] + c[q], v[q + 1] + c[q + 1], v[q + 2] + c[q + 2], v[q + 3] + c[q + 3]);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base_s, 256);
+    tc_fence_after();
+    if (grp == 0) {
+        float* dst = a.wpart + ((size_t)blockIdx.x * 2 + a.mode) * SCANN_D * SCANN_D;
+#pragma unroll 1
+        for (int h = 0; h < CPW / 16; ++h) {
+            float v[16], c[16];
+            if (!first) {
+                tmem_ld16(t_dm + lane_base + nbase + h * 16, v);
+                tmem_ld16(t_dc + lane_base + nbase + h * 16, c);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) { v[q] = 0.f; c[q] = 0.f; }
+            }
+#pragma unroll
+            for (int q = 0; q < 16; q += 4) {
+                float4 o = make_float4(v[q] + c[q], v[q + 1] + c[q + 1], v[q + 2] + c[q + 2], v[q + 3] + c[q + 3]);
+                for (int og = 1; og < NG; ++og) {
+                    if (!s_has[og]) continue;
+                    const float4 p = xfer[(size_t)((og - 1) * (CPW / 4) + h * 4 + q / 4) * GT + gtid];
+                    o = make_float4(o.x + p.x, o.y + p.y, o.z + p.z, o.w + p.w);
+                }
+                st4(dst + (size_t)m * SCANN_D + nbase + h * 16 + q, o);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base_s, 256 * NG);
 }
 
 #define LA_ATTN_BWD_SMEM (3 * TC_TILE_BYTES + 2 * SCANN_TILE * 8 * sizeof(float))
@@ -576,52 +656,64 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_wgrad_tc_kernel(const LaWgr
 // dg: gradient w.r.t. g' from the next layer (dg_has_up != 0) or scratch that is overwritten.
 // s_pre is written for atoms with pairs; t_scatter / dx_scatter are accumulated (pre-zero them).
 // The pair weight gradients are a separate call (scann_la_wgrad_tc); wpart is unused here.
-extern "C" int scann_la_backward_tc(int grid, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
-                                    const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
-                                    const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
-                                    const float* g_new, float* kbuf, float* prebuf, const float* W2T, const float* WkT,
-                                    const float* gamma_g, const float* d_ctx, float* dg, int dg_has_up, float* dg_out,
-                                    float* dq, float* s_pre, float* t_scatter, float* dx_scatter, float* wpart,
-                                    float* dgamma_g, float* dbeta_g, float* dbk, void* stream) {
+static int la_bwd_configure() {
     static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(la_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)LA_ATTN_BWD_SMEM);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)LA_GEOM_BWD_SMEM);
-        if (e != cudaSuccess) { scann_set_error("la_backward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
-        configured = true;
-    }
+    if (configured) return 0;
+    cudaError_t e = cudaFuncSetAttribute(la_attn_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_WGRAD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_WGRAD_SMEM);
+    if (e != cudaSuccess) { scann_set_error("la_backward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
+    configured = true;
+    return 0;
+}
+
+extern "C" int scann_la_backward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+                                    const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
+                                    const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
+                                    const float* g_in, const float* g_new, float* kbuf, float* prebuf, const float* W2T,
+                                    const float* WkT, const float* gamma_g, const float* d_ctx, float* dg, int dg_has_up,
+                                    float* dg_out, float* dq, float* s_pre, float* t_scatter, float* dx_scatter,
+                                    float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream) {
+    (void)wpart;
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
                      dg_has_up, dq, dx_scatter, dbk};
-    scann_launch(la_attn_bwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g};
-    scann_launch(la_geom_bwd_tc_kernel, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+    if (tile_stride == 64) {
+        scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        scann_launch(la_geom_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+    } else {
+        scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        scann_launch(la_geom_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+    }
     return scann_check_launch("scann_la_backward_tc");
 }
 
 // Pair weight gradients of one LocalAttention layer into wpart[grid][2][128][128] (off the critical path of
 // the backward chain: may run on a side stream once scann_la_backward_tc of the layer has finished):
 //   wpart[.][0] = sum (x[j]*g')^T d_k (-> key/kernel),  wpart[.][1] = sum g^T d_pre (-> filter_geo rows 128..255)
-extern "C" int scann_la_wgrad_tc(int grid, const int32_t* ntiles, const int32_t* pair_c, const int32_t* pair_j,
-                                 const float* x, const float* g_in, const float* g_new, const float* dk,
-                                 const float* dpre, float* wpart, void* stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(la_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)LA_WGRAD_SMEM);
-        if (e != cudaSuccess) { scann_set_error("la_wgrad_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
-        configured = true;
-    }
+// CTA c holds a valid partial iff c * (128 / tile_stride) < ntiles (scann_la_wpart_reduce applies the same rule).
+extern "C" int scann_la_wgrad_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* pair_c,
+                                 const int32_t* pair_j, const float* x, const float* g_in, const float* g_new,
+                                 const float* dk, const float* dpre, float* wpart, void* stream) {
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_wgrad_tc: tile_stride must be 64 or 128"); return 1; }
+    if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     LaWgradArgs w0{ntiles, pair_c, pair_j, x, g_new, dk, 0, wpart};
-    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w0);
     LaWgradArgs w1{ntiles, pair_c, pair_j, x, g_in, dpre, 1, wpart};
-    la_wgrad_tc_kernel<<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w1);
+    if (tile_stride == 64) {
+        la_wgrad_tc_kernel<2><<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w0);
+        la_wgrad_tc_kernel<2><<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w1);
+    } else {
+        la_wgrad_tc_kernel<1><<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w0);
+        la_wgrad_tc_kernel<1><<<grid, LTC_THREADS, LA_WGRAD_SMEM, st>>>(w1);
+    }
     return scann_check_launch("scann_la_wgrad_tc");
 }

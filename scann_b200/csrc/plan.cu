@@ -5,10 +5,11 @@
 // Masked slots never reach a model output (their softmax weight is exactly 0 in fp32 and
 // the context sum multiplies by the mask again), so the kernels only materialise VALID
 // pairs.  Pairs of one centre atom stay contiguous (slot order preserved) and are grouped
-// into tiles of at most `tile_rows` (<= SCANN_TILE = 128) rows that never split an atom; the caller picks
-// tile_rows so that the tile count fills whole waves of SMs (e.g. 296 tiles of ~80 rows instead of 175 tiles
-// of 128 rows on 148 SMs: the kernels' cost per tile is roughly proportional to its rows).  Tile t owns rows
-// [t*128, t*128+128) of every per-pair tensor, unused rows are padding (pair_c = -1).
+// into tiles of at most `tile_rows` (<= tile_stride) rows that never split an atom; the caller picks
+// tile_rows so that the tile count fills whole waves of SMs (the kernels' cost per tile is roughly
+// proportional to its rows).  Tile t owns rows [t*tile_stride, (t+1)*tile_stride) of every per-pair tensor
+// (tile_stride = 128, or 64 when the local-attention kernels run two warp groups per CTA); unused rows are
+// padding (pair_c = -1).
 #include "common.cuh"
 
 #define PLAN_GSZ 128   // atom rows per greedy group (one thread walks one group)
@@ -34,7 +35,7 @@ __global__ void plan_count_kernel(const uint8_t* __restrict__ nmask, const int32
 
 // One thread per group of PLAN_GSZ consecutive atom rows: greedy first-fit in order.
 // rowptr[r] <- local_tile*128 + offset (group-local); gtiles[g] <- tiles used by the group.
-__global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ngroups, int tile_rows,
+__global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ngroups, int tile_rows, int tile_stride,
                                   int32_t* __restrict__ rowptr, int32_t* __restrict__ gtiles) {
     __shared__ int32_t s_cnt[32 * (PLAN_GSZ + 1)];
     int g0 = blockIdx.x * 32;
@@ -52,7 +53,7 @@ __global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ng
         int c = sc[a];
         if (c == 0) { sc[a] = -1; continue; }
         if (fill + c > tile_rows && fill > 0) { ++tile; fill = 0; }
-        sc[a] = tile * SCANN_TILE + fill;
+        sc[a] = tile * tile_stride + fill;
         fill += c;
         any = 1;
     }
@@ -89,7 +90,7 @@ __global__ void plan_scan_kernel(const int32_t* __restrict__ gtiles, int ngroups
 __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_t* __restrict__ nbr,
                                  const float* __restrict__ dist, const float* __restrict__ weight,
                                  const int32_t* __restrict__ cnt, const int32_t* __restrict__ gbase,
-                                 const int32_t* __restrict__ ntiles, int R, int M, int N,
+                                 const int32_t* __restrict__ ntiles, int R, int M, int N, int tile_stride,
                                  int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_a0,
                                  int32_t* __restrict__ tile_a1, int32_t* __restrict__ pair_c,
                                  int32_t* __restrict__ pair_j, int32_t* __restrict__ pair_slot,
@@ -98,10 +99,10 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
     if (r >= R) return;
     int c = cnt[r];
     if (c == 0 || *ntiles == 0) { rowptr[r] = 0; return; }
-    int rp = gbase[r / PLAN_GSZ] * SCANN_TILE + rowptr[r];
+    int rp = gbase[r / PLAN_GSZ] * tile_stride + rowptr[r];
     rowptr[r] = rp;
-    int tile = rp / SCANN_TILE;
-    if (rp % SCANN_TILE == 0) tile_a0[tile] = r;
+    int tile = rp / tile_stride;
+    if (rp % tile_stride == 0) tile_a0[tile] = r;
     atomicMax(&tile_a1[tile], r + 1);
     int b = r / M;
     const uint8_t* m = nmask + (size_t)r * N;
@@ -120,29 +121,31 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
 }
 
 extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
-                                const float* weight, int B, int M, int N, int tile_cap, int tile_rows, int32_t* cnt,
+                                const float* weight, int B, int M, int N, int tile_cap, int tile_rows,
+                                int tile_stride, int32_t* cnt,
                                 int32_t* rowptr, int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles,
                                 int32_t* pair_c, int32_t* pair_j, int32_t* pair_slot, float* pair_d,
                                 float* pair_w, int32_t* scratch, int scratch_len, int32_t* status, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     long long Rll = (long long)B * M;
     if (Rll <= 0 || N <= 0 || Rll * N > 0x7fffffffLL) { scann_set_error("plan: bad shape B=%d M=%d N=%d", B, M, N); return 1; }
-    if (tile_rows < 1 || tile_rows > SCANN_TILE) { scann_set_error("plan: tile_rows must be in 1..128"); return 1; }
+    if (tile_stride != 64 && tile_stride != SCANN_TILE) { scann_set_error("plan: tile_stride must be 64 or 128"); return 1; }
+    if (tile_rows < 1 || tile_rows > tile_stride) { scann_set_error("plan: tile_rows must be in 1..tile_stride"); return 1; }
     int R = (int)Rll;
     int ngroups = (R + PLAN_GSZ - 1) / PLAN_GSZ;
     if (scratch_len < 2 * ngroups) { scann_set_error("plan: scratch too small (%d < %d)", scratch_len, 2 * ngroups); return 1; }
     int32_t* gtiles = scratch;
     int32_t* gbase = scratch + ngroups;
-    size_t rows = (size_t)tile_cap * SCANN_TILE;
+    size_t rows = (size_t)tile_cap * tile_stride;
     // padding rows are recognised by pair_c < 0; every consumer guards on it, so the other
     // per-pair arrays need no initialisation.  tile_a1 is built with atomicMax.
     cudaMemsetAsync(pair_c, 0xFF, rows * sizeof(int32_t), st);
     cudaMemsetAsync(tile_a1, 0, (size_t)tile_cap * sizeof(int32_t), st);
     plan_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(neighbor_mask, neighbors, R, M, N, cnt, status);
-    plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, tile_rows, rowptr, gtiles);
+    plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, tile_rows, tile_stride, rowptr, gtiles);
     plan_scan_kernel<<<1, 1024, 0, st>>>(gtiles, ngroups, tile_cap, gbase, ntiles, status);
     plan_fill_kernel<<<(R + 127) / 128, 128, 0, st>>>(neighbor_mask, neighbors, dist, weight, cnt, gbase, ntiles, R, M,
-                                                     N, rowptr, tile_a0, tile_a1, pair_c, pair_j, pair_slot, pair_d,
+                                                     N, tile_stride, rowptr, tile_a0, tile_a1, pair_c, pair_j, pair_slot, pair_d,
                                                      pair_w);
     return scann_check_launch("scann_plan_build");
 }

@@ -70,6 +70,20 @@ __device__ __forceinline__ uint32_t tc_idesc_tf32(int M, int N, bool a_mn, bool 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One elected lane of a CONVERGED warp (elect.sync).  tcgen05.mma / commit must be issued from such a lane inside
+// a warp-uniform branch: under a divergent `if (tid == 0)` the compiler wraps every MMA in an
+// ELECT / BRA.U.ANY loop (one MMA per ~50-60 cycles whatever its size -- measured), whereas with elect.sync it
+// issues them back to back from the uniform datapath.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tcgen05 wrappers ----
 __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accum) {
     asm volatile(

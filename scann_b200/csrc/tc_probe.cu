@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128, 1) tc_time_kernel(float* out, int mode, i
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    if (tid == 0) {
+    if (warp == 0 && ((mode & 8) ? tc_elect_one() : tid == 0)) {      // mode & 8: elect.sync issue (uniform datapath)
         const uint32_t cg = (mode & 2) ? 128u : TC_CG_STRIDE;
         const uint32_t rg = 32u * cg;
         const uint32_t idesc = tc_idesc_tf32(128, ncols, false, false);

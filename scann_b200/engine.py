@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import check, lib, ptr_array
+from ._abi import ChainStep, chain_step, check, lib, ptr_array
 from .config import ModelSpec, N_RBF, check_kernel_support
 from .params import ParamLayout, layer_name
 
@@ -98,10 +98,18 @@ class Engine:
         # Opt-in: smaller, wave-balanced tiles.  Measured on QM9/128: local-attention kernels -3 %, but the
         # kernels whose cost is per tile rather than per row (geom_init, la_wgrad_tc) lose more: 2.06 vs 1.93 ms.
         self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "0") == "1"
+        # rows per tile slot of the pair plan: 64 = two warp groups per CTA in the tensor-core local-attention
+        # kernels (needs <= 64 neighbours per atom), 128 = one tile stream per CTA (also the SIMT engine)
+        self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "64"))
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
         # programmatic dependent launch along the forward / backward kernel chain (include/scann_b200.h)
         self.use_pdl = os.environ.get("SCANN_PDL", "1") == "1"
+        # development aid: kernels to leave out of the step (results are then meaningless; only the timing
+        # difference to the full step is of interest) -- comma list of wgrad,la_fwd,la_bwd,rn,geom_init
+        self._skip = set(filter(None, os.environ.get("SCANN_DEBUG_SKIP", "").split(",")))
+        # per-atom Dense layers between two local-attention layers fused into one chained kernel
+        self.use_chain = os.environ.get("SCANN_CHAIN", "1") == "1" and self.tc_dense and self.tc_la_fwd
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -174,17 +182,19 @@ class Engine:
         ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
         # rows per tile: fill whole waves of SMs (the kernels' cost per tile scales with its rows, and a
         # tile count just above a multiple of the SM count costs a whole extra round)
-        tile_rows = TILE
+        stride = 64 if (self.tile_stride_pref == 64 and self.tc_la_fwd and self.tc_la_bwd and N <= 32) else TILE
+        tile_rows = stride
         if P_host is not None and self.balance_tiles and N <= 64:
-            waves = max(1, -(-P // (TILE * self.sm_count)))
-            tile_rows = min(TILE, max(2 * N, 32, -(-P // (waves * self.sm_count)) + (N + 1) // 2))
+            slots = self.sm_count * (TILE // stride)
+            waves = max(1, -(-P // (stride * slots)))
+            tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
         # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
         cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
         tile_cap = max(64, (cap + 63) // 64 * 64)
-        key = (B, M, N, tile_cap, tile_rows)
+        key = (B, M, N, tile_cap, tile_rows, stride)
         b = self._batches.get(key)
         if b is None:
-            b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups)
+            b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups, stride)
             b.tile_rows = tile_rows
         b.P_host = P_host
         b.h2d_bytes = 0
@@ -233,11 +243,12 @@ class Engine:
             self._plan(b)
         return b
 
-    def _new_batch(self, B: int, M: int, N: int, tile_cap: int, ngroups: int) -> Batch:
+    def _new_batch(self, B: int, M: int, N: int, tile_cap: int, ngroups: int, stride: int = TILE) -> Batch:
         dev = self.device
         b = Batch()
         b.B, b.M, b.N, b.R, b.tile_cap, b.ngroups = B, M, N, B * M, tile_cap, ngroups
-        rows = tile_cap * TILE
+        b.stride = stride
+        rows = b.rows = tile_cap * stride
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
         b.atomic = torch.zeros(b.R, **i32)
@@ -269,7 +280,7 @@ class Engine:
         a = np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1))
         if a.size != b.B:
             raise ValueError("target must have one value per structure")
-        key = (b.B, b.M, b.N, b.tile_cap, b.tile_rows)
+        key = (b.B, b.M, b.N, b.tile_cap, b.tile_rows, b.stride)
         slot = self._pinned.get(("target", key))
         if slot is None:
             slot = self._pinned[("target", key)] = [torch.empty(b.B, dtype=torch.float32).pin_memory(), None]
@@ -284,20 +295,20 @@ class Engine:
 
     def _plan(self, b: Batch) -> None:
         check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
-                                   b.tile_rows, _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
+                                   b.tile_rows, b.stride, _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
                                    _p(b.scratch), b.scratch.numel(), _p(self.status), self._stream()), "plan_build")
         self.launches += 4
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, b: Batch, training: bool) -> dict:
-        key = (b.R, b.B, b.tile_cap, training)      # workspaces depend on the capacity, not on tile_rows
+        key = (b.R, b.B, b.rows, training)          # workspaces depend on the capacity, not on tile_rows
         ws = self._ws.get(key)
         if ws is not None:
             return ws
         dev = self.device
         L = self.spec.n_attention
-        R, rows = b.R, b.tile_cap * TILE
+        R, rows = b.R, b.rows
         f = dict(dtype=torch.float32, device=dev)
         ws = {}
         nsave = L + 1 if training else 2
@@ -347,6 +358,12 @@ class Engine:
                                       self._stream()), "dense_forward")
         self.launches += 1
 
+    def _chain(self, steps, R):
+        """One scann_dense_chain launch: ``steps`` is a list of ChainStep (see include/scann_b200.h)."""
+        arr = (ChainStep * len(steps))(*steps)
+        check(lib.scann_dense_chain(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, self._stream()), "dense_chain")
+        self.launches += 1
+
     def _wgrad(self, A, lda, G, ldg, kblk, nblk, R, dW, db):
         check(lib.scann_dense_wgrad(ptr_array(A), lda, ptr_array(G), ldg, kblk, nblk, R, ptr_array(dW),
                                     ptr_array(db) if db else None, self._stream()), "dense_wgrad")
@@ -372,12 +389,14 @@ class Engine:
                                       _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status), st), "embed_forward")
         self.launches += 1
         self._pdl(True)
-        if sp.g_update:
-            check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+        if sp.g_update and "geom_init" not in self._skip:
+            check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                               _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                               self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
                                               self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
             self.launches += 1
+        if self.use_chain and (not training or self.tc_la_bwd):
+            return self._forward_chained(b, ws, training, attn_out)
         for l in range(L):
             la = layer_name("local_attention", l)
             rn = layer_name("residual_norm", l)
@@ -390,7 +409,7 @@ class Engine:
             out = h if sp.use_attn_norm else x_out
             attn = None
             if attn_out is not None:
-                attn = torch.zeros(b.tile_cap * TILE, 8, dtype=torch.float32, device=self.device)
+                attn = torch.zeros(b.rows, 8, dtype=torch.float32, device=self.device)
                 attn_out.append(attn)
             if not sp.g_update:
                 # SCANN without geometry update (attention.py:155): only the query block of proj is needed
@@ -399,7 +418,7 @@ class Engine:
                 check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
                                                   self.w(f"{la}/layer_norm/beta"), 0, _p(out), st), "la_nopair")
                 check(lib.scann_la_forward_noupdate_tc(
-                    self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
+                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
                     _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d), self.w(fg),
                     self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                     self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), st),
@@ -420,22 +439,24 @@ class Engine:
             check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
                                               self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), st), "la_nopair")
             self._ev("la_forward", True)
-            la_args = (self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+            la_args = (_p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                        _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in),
                        self.w(fg, D * D), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                        self.w(f"{la}/layer_norm_g/gamma"), self.w(f"{la}/layer_norm_g/beta"),
                        self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"),
                        _p(g_out), _p(ctxpre), _p(out), _p(attn))
-            if self.tc_la_fwd:
+            if "la_fwd" in self._skip:
+                pass
+            elif self.tc_la_fwd:
                 save = training and self.tc_la_bwd
-                check(lib.scann_la_forward_tc(*la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
+                check(lib.scann_la_forward_tc(self.la_grid, b.stride, *la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
                                               st), "la_forward_tc")
                 self.launches += 1
             else:
-                check(lib.scann_la_forward(*la_args, st), "la_forward")
+                check(lib.scann_la_forward(self.la_grid, *la_args, st), "la_forward")
             self._ev("la_forward", False)
             self.launches += 2
-            if sp.use_attn_norm:
+            if sp.use_attn_norm and "rn" not in self._skip:
                 # ResidualNorm: LN(h + Dense(swish(Dense(h))))  (attention.py:25-40)
                 self._dense([_p(h)], D, [self.w(f"{rn}/dense/kernel")], [self.w(f"{rn}/dense/bias")], 1, 1, R, _p(h1),
                             D, mode=1, pre_out=ws["t1"][l] if training else None)
@@ -448,6 +469,106 @@ class Engine:
         self._dense([_p(ws["xa"])], D, [self.w("global_attention/query/kernel"), self.w("global_attention/key/kernel")],
                     [self.w("global_attention/query/bias"), self.w("global_attention/key/bias")], 1, 2, R,
                     _p(ws["qk"]), 2 * D)
+        check(lib.scann_ga_head_forward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
+                                        self.w("bf_property/kernel"), self.w("bf_property/bias"),
+                                        self.w("predict_property/kernel"), self.w("predict_property/bias"),
+                                        int(sp.mrelu_head), _p(ws["ga"]), _p(ws["y"]),
+                                        _p(ws["ctxg"]) if training else 0, _p(ws["tb"]) if training else 0, st),
+              "ga_head_forward")
+        self._pdl(False)
+        self.launches += 1
+        return ws["y"], ws["ga"]
+
+    def _forward_chained(self, b: Batch, ws: dict, training: bool, attn_out: Optional[list]):
+        """Layers of the forward pass with the per-atom Dense layers fused (scann_dense_chain):
+        [projections of layer 0] -> LA_0 -> [ResidualNorm_0 + projections of layer 1] -> LA_1 -> ... ->
+        [ResidualNorm_{L-1} + after_Lc + GlobalAttention q/k] -> GA + head."""
+        sp, st = self.spec, self._stream()
+        L, R = sp.n_attention, b.R
+        xs, gs = ws["x"], ws["g"]
+
+        def bufs(l):
+            li = l if training else 0
+            x_in = xs[l] if training else xs[l % 2]
+            x_out = xs[l + 1] if training else xs[(l + 1) % 2]
+            h = ws["h"][li]
+            return li, x_in, x_out, ws["proj"][li], h, ws["h1"][li], (h if sp.use_attn_norm else x_out)
+
+        def proj_steps(l, src):
+            """x @ [W1 | W3 | Wq] (+ biases) of layer l into its proj buffer; rows without a valid neighbour get
+            context = q and out = LN(q).  ``src``: global tensor holding x_l, or None = resident image."""
+            la = layer_name("local_attention", l)
+            fg = f"{la}/filter_geo/kernel"
+            li, _, _, proj, _, _, out = bufs(l)
+            ctxpre = ws["ctxpre"][l] if training else None
+            A = [_p(src)] if src is not None else []
+            steps = []
+            if sp.g_update:
+                steps.append(chain_step(A=A, W=[self.w(fg, 0)], bias=self.w(f"{la}/filter_geo/bias"), C_=_p(proj), ldc=3 * D))
+                steps.append(chain_step(W=[self.w(fg, 2 * D * D)], C_=_p(proj, D), ldc=3 * D))
+                A = []
+            steps.append(chain_step(A=A, W=[self.w(f"{la}/query/kernel")], bias=self.w(f"{la}/query/bias"),
+                                    C_=_p(proj, 2 * D), ldc=3 * D, cnt=_p(b.cnt), np_ctx=_p(ctxpre), np_out=_p(out),
+                                    gamma=self.w(f"{la}/layer_norm/gamma"), beta=self.w(f"{la}/layer_norm/beta")))
+            return steps
+
+        self._chain(proj_steps(0, xs[0]), R)
+        for l in range(L):
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            fg = f"{la}/filter_geo/kernel"
+            li, x_in, x_out, proj, h, h1, out = bufs(l)
+            ctxpre = ws["ctxpre"][l] if training else None
+            attn = None
+            if attn_out is not None:
+                attn = torch.zeros(b.rows, 8, dtype=torch.float32, device=self.device)
+                attn_out.append(attn)
+            self._ev("la_forward", True)
+            if "la_fwd" in self._skip:
+                pass
+            elif sp.g_update:
+                g_in = gs[l] if training else gs[l % 2]
+                g_out = gs[l + 1] if training else gs[(l + 1) % 2]
+                save = training and self.tc_la_bwd
+                check(lib.scann_la_forward_tc(
+                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in), self.w(fg, D * D),
+                    self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"), self.w(f"{la}/layer_norm_g/gamma"),
+                    self.w(f"{la}/layer_norm_g/beta"), self.w(f"{la}/layer_norm/gamma"),
+                    self.w(f"{la}/layer_norm/beta"), _p(g_out), _p(ctxpre), _p(out), _p(attn),
+                    _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, st), "la_forward_tc")
+                self.launches += 2
+            else:
+                check(lib.scann_la_forward_noupdate_tc(
+                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
+                    self.w(fg), self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
+                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), st),
+                    "la_forward_noupdate_tc")
+                self.launches += 1
+            self._ev("la_forward", False)
+            steps = []
+            src = x_out                       # where x_{l+1} lives if no step of this chain produces it
+            if sp.use_attn_norm and "rn" not in self._skip:
+                # ResidualNorm: LN(h + Dense(swish(Dense(h))))  (attention.py:25-40)
+                steps.append(chain_step(A=[_p(h)], W=[self.w(f"{rn}/dense/kernel")], bias=self.w(f"{rn}/dense/bias"),
+                                        mode=1, pre_out=_p(ws["t1"][l]) if training else 0, C_=_p(h1), to_image=True))
+                steps.append(chain_step(W=[self.w(f"{rn}/dense_1/kernel")], bias=self.w(f"{rn}/dense_1/bias"),
+                                        resid=_p(h), mode=3, pre_out=_p(ws["v2"][l]) if training else 0,
+                                        gamma=self.w(f"{rn}/layer_norm/gamma"), beta=self.w(f"{rn}/layer_norm/beta"),
+                                        C_=_p(x_out), to_image=True))
+                src = None
+            if l + 1 < L:
+                steps += proj_steps(l + 1, src)
+            else:
+                A = [_p(src)] if src is not None else []
+                steps.append(chain_step(A=A, W=[self.w("after_Lc/kernel")], bias=self.w("after_Lc/bias"), mode=1,
+                                        pre_out=_p(ws["ta"]) if training else 0, C_=_p(ws["xa"]), to_image=True))
+                steps.append(chain_step(W=[self.w("global_attention/query/kernel")],
+                                        bias=self.w("global_attention/query/bias"), C_=_p(ws["qk"]), ldc=2 * D))
+                steps.append(chain_step(W=[self.w("global_attention/key/kernel")],
+                                        bias=self.w("global_attention/key/bias"), C_=_p(ws["qk"], D), ldc=2 * D))
+            self._chain(steps, R)
         check(lib.scann_ga_head_forward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                         self.w("bf_property/kernel"), self.w("bf_property/bias"),
                                         self.w("predict_property/kernel"), self.w("predict_property/bias"),
@@ -501,6 +622,8 @@ class Engine:
                                          self.gw("predict_property/kernel"), self.gw("predict_property/bias"), st),
               "ga_head_backward")
         self.launches += 2
+        if self.use_chain and self.tc_la_bwd:
+            return self._backward_chained(b, ws, fork, wgrad, side, main, sst)
         dqk = ws["d_qk"]
         self._dense([_p(dqk), _p(dqk, D)], 2 * D,
                     [self.wT("global_attention/query/kernel"), self.wT("global_attention/key/kernel")], None, 2, 1, R,
@@ -539,9 +662,11 @@ class Engine:
             s_pre, t_sc, dx_sc = scat[0], scat[1], scat[2]
             dg_out = ws["dg"][(L - l) % 2]
             self._ev("la_backward", True)
-            if self.tc_la_bwd:
+            if "la_bwd" in self._skip:
+                pass
+            elif self.tc_la_bwd:
                 dg_buf = ws["dg"][(L - 1 - l) % 2]
-                check(lib.scann_la_backward_tc(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                check(lib.scann_la_backward_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                                                _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
                                                _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
                                                _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
@@ -568,13 +693,16 @@ class Engine:
                         [self.wT(fg, 0), self.wT(fg, 2 * D * D), self.wT(f"{la}/query/kernel")], None, 3, 1, R, _p(dx),
                         D, resid=dx_sc)
             # ---- weight gradients of this layer (side stream)
+            if "wgrad" in self._skip:
+                dg_up = dg_out
+                continue
             fork()
             if self.tc_la_bwd:
-                check(lib.scann_la_wgrad_tc(self.la_grid, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
+                check(lib.scann_la_wgrad_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
                                             _p(ws["g"][l]), _p(ws["g"][l + 1]), _p(ws["kk"][l]), _p(ws["pre"][l]),
                                             _p(ws["wpart"]), sst), "la_wgrad_tc")
                 self.launches += 2
-            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, self.gw(f"{la}/key/kernel"),
+            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, b.stride, self.gw(f"{la}/key/kernel"),
                                             self.gw(fg, D * D), sst), "la_wpart_reduce")
             self.launches += 1
             if sp.use_attn_norm:
@@ -586,7 +714,15 @@ class Engine:
                   [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
                   [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
             dg_up = dg_out
-        check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+        self._backward_tail(b, ws, dg_up, side, main)
+
+    def _backward_tail(self, b: Batch, ws: dict, dg_up, side, main) -> None:
+        """Geometry-initialisation and embedding backward, then the join with the weight-gradient stream."""
+        sp, st = self.spec, self._stream()
+        R = b.R
+        dx = ws["dx"]
+        if "geom_init" not in self._skip:
+          check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                            _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                            self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
                                            self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),
@@ -603,6 +739,94 @@ class Engine:
             ev = torch.cuda.Event()
             ev.record(side)
             main.wait_event(ev)
+
+    def _backward_chained(self, b: Batch, ws: dict, fork, wgrad, side, main, sst) -> None:
+        """Backward layers with the per-atom links fused (scann_dense_chain):
+        [GA projections^T, after_Lc^T, tail(L-1)] -> LA_bwd(L-1) -> [x-gradient of layer L-1, tail(L-2)] -> ... ->
+        LA_bwd(0) -> [x-gradient of layer 0] -> geometry init / embedding backward.
+        tail(l) turns the gradient w.r.t. x_{l+1} into d_ctx / dq of layer l: LayerNorm backward of ResidualNorm,
+        its two Dense layers transposed (swish'), LayerNorm backward of the attention output."""
+        sp, st = self.spec, self._stream()
+        L, R = sp.n_attention, b.R
+        dqk, dx = ws["d_qk"], ws["dx"]
+
+        def with_tail(head: dict, l: int):
+            """``head``: keyword arguments of the GEMM step that produces d x_{l+1}; returns the step list."""
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            la_ln = dict(mode=4, pre_in=_p(ws["ctxpre"][l]), gamma=self.w(f"{la}/layer_norm/gamma"),
+                         dgamma=self.gw(f"{la}/layer_norm/gamma"), dbeta=self.gw(f"{la}/layer_norm/beta"),
+                         C_=_p(ws["d_ctx"]), C2=_p(ws["dq"][l]))
+            if not sp.use_attn_norm:
+                return [chain_step(**head, **la_ln)]
+            d_v2, d_t1 = ws["d_v2"][l], ws["d_t1"][l]
+            return [
+                chain_step(**head, mode=4, pre_in=_p(ws["v2"][l]), gamma=self.w(f"{rn}/layer_norm/gamma"),
+                           dgamma=self.gw(f"{rn}/layer_norm/gamma"), dbeta=self.gw(f"{rn}/layer_norm/beta"),
+                           C_=_p(d_v2), to_image=True),
+                chain_step(W=[self.wT(f"{rn}/dense_1/kernel")], mode=2, pre_in=_p(ws["t1"][l]), C_=_p(d_t1), to_image=True),
+                chain_step(W=[self.wT(f"{rn}/dense/kernel")], resid=_p(d_v2), **la_ln),
+            ]
+
+        steps = [chain_step(A=[_p(dqk), _p(dqk, D)], lda=2 * D,
+                            W=[self.wT("global_attention/query/kernel"), self.wT("global_attention/key/kernel")],
+                            mode=2, pre_in=_p(ws["ta"]), C_=_p(ws["d_ta"]), to_image=True)]
+        steps += with_tail(dict(W=[self.wT("after_Lc/kernel")]), L - 1)
+        self._chain(steps, R)
+        fork()
+        wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
+              [self.gw("bf_property/bias")])
+        wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
+              [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
+              [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
+        wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")], [self.gw("after_Lc/bias")])
+        dg_up = None
+        for l in range(L - 1, -1, -1):
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            fg = f"{la}/filter_geo/kernel"
+            d_v2, d_t1, dq = ws["d_v2"][l], ws["d_t1"][l], ws["dq"][l]
+            scat = ws["scat"][l]
+            s_pre, t_sc, dx_sc = scat[0], scat[1], scat[2]
+            dg_out = ws["dg"][(L - l) % 2]
+            dg_buf = ws["dg"][(L - 1 - l) % 2]
+            self._ev("la_backward", True)
+            if "la_bwd" not in self._skip:
+                check(lib.scann_la_backward_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1),
+                                               _p(b.cnt), _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
+                                               _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
+                                               _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
+                                               self.wT(f"{la}/key/kernel"), self.w(f"{la}/layer_norm_g/gamma"),
+                                               _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
+                                               _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc), 0,
+                                               self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
+                                               self.gw(f"{la}/key/bias"), st), "la_backward_tc")
+                self.launches += 2
+            self._ev("la_backward", False)
+            # next link of the critical path: gradient w.r.t. the layer input x_l, then the tail of layer l-1
+            head = dict(A=[_p(s_pre), _p(t_sc), _p(dq)], W=[self.wT(fg, 0), self.wT(fg, 2 * D * D),
+                                                           self.wT(f"{la}/query/kernel")], resid=_p(dx_sc))
+            self._chain(with_tail(head, l - 1) if l > 0 else [chain_step(**head, C_=_p(dx))], R)
+            dg_up = dg_out
+            # ---- weight gradients of this layer (side stream)
+            if "wgrad" in self._skip:
+                continue
+            fork()
+            check(lib.scann_la_wgrad_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
+                                        _p(ws["g"][l]), _p(ws["g"][l + 1]), _p(ws["kk"][l]), _p(ws["pre"][l]),
+                                        _p(ws["wpart"]), sst), "la_wgrad_tc")
+            check(lib.scann_la_wpart_reduce(_p(ws["wpart"]), _p(b.ntiles), self.la_grid, b.stride,
+                                            self.gw(f"{la}/key/kernel"), self.gw(fg, D * D), sst), "la_wpart_reduce")
+            self.launches += 3
+            if sp.use_attn_norm:
+                wgrad([_p(ws["h1"][l])], D, [_p(d_v2)], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
+                      [self.gw(f"{rn}/dense_1/bias")])
+                wgrad([_p(ws["h"][l])], D, [_p(d_t1)], D, 1, 1, R, [self.gw(f"{rn}/dense/kernel")],
+                      [self.gw(f"{rn}/dense/bias")])
+            wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(dq)], D, 1, 3, R,
+                  [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
+                  [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
+        self._backward_tail(b, ws, dg_up, side, main)
 
     def _backward_prep(self, ws: dict, stream: int) -> None:
         """Work the backward needs that does not depend on the forward: transposed weight blocks and

@@ -127,7 +127,7 @@ class _Plan:
         self.status = torch.zeros(1, **i32)
         scratch = torch.empty(2 * ngroups + 8, **i32)
         zeros = torch.zeros(P, dtype=torch.float32, device=dev)
-        check(lib.scann_plan_build(_p(mask_u8), _p(neighbors), _p(zeros), _p(zeros), B, M, N, cap, TILE, _p(self.cnt),
+        check(lib.scann_plan_build(_p(mask_u8), _p(neighbors), _p(zeros), _p(zeros), B, M, N, cap, TILE, TILE, _p(self.cnt),
                                    _p(self.rowptr), _p(self.tile_a0), _p(self.tile_a1), _p(self.ntiles),
                                    _p(self.pair_c), _p(self.pair_j), _p(self.pair_slot), _p(self.pair_d),
                                    _p(self.pair_w), _p(scratch), scratch.numel(), _p(self.status), _stream()),

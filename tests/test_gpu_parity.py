@@ -80,7 +80,7 @@ def test_plan_gathers_and_masks_bit_exact(shape, B):
     pc, pj, slot = b.pair_c.cpu().numpy(), b.pair_j.cpu().numpy(), b.pair_slot.cpu().numpy()
     nt = int(b.ntiles.item())
     valid = pc >= 0
-    assert not valid[nt * 128:].any()
+    assert not valid[nt * b.stride:].any()
     nm = inputs["neighbor_mask"].reshape(-1)
     assert valid.sum() == nm.sum()
     assert np.array_equal(np.sort(slot[valid]), np.flatnonzero(nm))           # every valid slot exactly once
@@ -95,7 +95,7 @@ def test_plan_gathers_and_masks_bit_exact(shape, B):
     rp = b.rowptr.cpu().numpy()
     for r in np.flatnonzero(cnt)[:200]:
         rows = np.arange(rp[r], rp[r] + cnt[r])
-        assert rows[0] // 128 == rows[-1] // 128
+        assert rows[0] // b.stride == rows[-1] // b.stride
         assert (pc[rows] == r).all() and (np.diff(slot[rows]) > 0).all()
 
 
@@ -121,6 +121,30 @@ def test_gradients_match_golden(name):
     g = eng.grad_out.cpu().numpy().astype(np.float64)
     loss = eng.loss_value(b.B).cpu().numpy()
     assert abs(loss[0] - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
+    assert rel(g[z["grad_idx"]], z["grad_sample"]) <= TOL_GRAD
+    assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
+
+
+@pytest.mark.parametrize("stride,balance", [(128, "0"), (64, "0"), (64, "1"), (128, "1")])
+def test_both_tile_layouts_match_golden(monkeypatch, stride, balance):
+    """The pair plan has two layouts (tile slots of 128 rows = one tile stream per CTA, 64 rows = two warp
+    groups per CTA) and an optional wave-balanced fill; every combination must give the same answer."""
+    monkeypatch.setenv("SCANN_TILE_STRIDE", str(stride))
+    monkeypatch.setenv("SCANN_BALANCE_TILES", balance)
+    name = "qm9_b4"
+    cfg, spec, lay, arena, inputs, target = build_case(name)
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    assert b.stride == stride
+    y, ga = eng.forward(b)
+    torch.cuda.synchronize()
+    assert rel(y.cpu().numpy(), z["y"].ravel()) <= TOL_OUT
+    assert rel(ga.cpu().numpy().reshape(b.B, b.M), z["ga"][..., 0]) <= TOL_OUT
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = eng.grad_out.cpu().numpy().astype(np.float64)
     assert rel(g[z["grad_idx"]], z["grad_sample"]) <= TOL_GRAD
     assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
 
