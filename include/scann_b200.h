@@ -201,6 +201,25 @@ int scann_la_wgrad_tc(int grid, int tile_stride, const int32_t* ntiles, const in
 int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, int tile_stride, float* dWk, float* dW2,
                           void* stream);
 
+/* ---- all weight-gradient GEMMs of a train step in one persistent launch ---------------------------
+ * dW += X^T Y for a list of problems (TF autodiff of every Dense / einsum kernel of the graph inside keras fit:
+ * scann/layers/attention.py:118-216,25-40, scann/models/scann_model.py:424-447).  rows >= 0: per-atom problem
+ * over that many rows; rows < 0: per-pair problem over the tile-padded pair rows (ntiles * tile_stride rows, rows
+ * with pair_c < 0 skipped), with X rows multiplied by xg[pair_j[row]] when xg != NULL.  db (nullable) += column
+ * sums of Y (bias gradient).  `problems` is a DEVICE array; results are accumulated with atomics. */
+typedef struct ScannWgradProblem {
+    const float* X;
+    const float* Y;
+    const float* xg;
+    float* dW;
+    float* db;
+    int ldx, ldy;
+    int rows;
+    int pad;
+} ScannWgradProblem;
+int scann_wgrad_batch_tc(int grid, const ScannWgradProblem* problems, int nprob, const int32_t* ntiles, int tile_stride,
+                         const int32_t* pair_c, const int32_t* pair_j, void* stream);
+
 /* ---- global attention + property head ---------------------------------------------------------
  * GlobalAttention.call (scann/layers/attention.py:267-318) + bf_property / predict_property / mrelu
  * (scann/models/scann_model.py:437-447, scann/layers/custom_layers.py:6-15).  qk = [q | k] [R,256].

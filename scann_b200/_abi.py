@@ -41,6 +41,7 @@ PROTOTYPES = {
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
     "scann_la_wgrad_tc": (ci, [ci, ci] + [vp] * 9 + [vp]),
+    "scann_wgrad_batch_tc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
@@ -80,6 +81,12 @@ def chain_step(A=(), W=(), bias=0, resid=0, ldres=128, pre_in=0, pre_out=0, ldpr
     st.lda, st.ldres, st.ldpre, st.ldc, st.ldc2 = lda, ldres, ldpre, ldc, ldc2
     st.mode, st.to_image = mode, 1 if to_image else 0
     return st
+
+
+class WgradProblem(C.Structure):
+    """``ScannWgradProblem`` of include/scann_b200.h (one dW += X^T Y problem of ``scann_wgrad_batch_tc``)."""
+    _fields_ = [("X", vp), ("Y", vp), ("xg", vp), ("dW", vp), ("db", vp), ("ldx", ci), ("ldy", ci), ("rows", ci),
+                ("pad", ci)]
 
 
 class ScannAbiError(RuntimeError):

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) embed_bwd_final_kernel(int E, int n_atoms
 // Geometry initialisation (g_update): g0 = swish(rbf_d Wd + bd) * swish(rbf_w Ww + bw)
 // rbf_x[k] = exp(-(x - c_k)^2 / 0.25)                 (scann_model.py:378-389, custom_layers.py:55-65)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF + 1], int* s_c, float* s_d, float* s_w,
+__device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF], int* s_c, float* s_d, float* s_w,
                                                const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
                                                const float* __restrict__ pair_w, const float* __restrict__ cd,
                                                const float* __restrict__ cw, size_t base, int stride) {
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
                                                             const float* __restrict__ Wd, const float* __restrict__ bd,
                                                             const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ g0) {
-    __shared__ float s_rbf[SCANN_TILE][2 * SCANN_RBF + 1];
+    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
     __shared__ int s_c[SCANN_TILE];
     __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
@@ -202,12 +202,16 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
 #pragma unroll 4
         for (int row = half; row < stride; row += 2) {
             float a = bdn, b = bwn;
+            const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
 #pragma unroll
-            for (int k = 0; k < SCANN_RBF; ++k) {
-                a = fmaf(s_rbf[row][k], wd[k], a);
-                b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
+            for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                const float4 rd = rb[k4], rw = rb[SCANN_RBF / 4 + k4];
+                a = fmaf(rd.x, wd[4 * k4], a); a = fmaf(rd.y, wd[4 * k4 + 1], a);
+                a = fmaf(rd.z, wd[4 * k4 + 2], a); a = fmaf(rd.w, wd[4 * k4 + 3], a);
+                b = fmaf(rw.x, ww[4 * k4], b); b = fmaf(rw.y, ww[4 * k4 + 1], b);
+                b = fmaf(rw.z, ww[4 * k4 + 2], b); b = fmaf(rw.w, ww[4 * k4 + 3], b);
             }
-            g0[(base + row) * SCANN_D + n] = s_c[row] >= 0 ? swish_f(a) * swish_f(b) : 0.f;
+            g0[(base + row) * SCANN_D + n] = s_c[row] >= 0 ? swish_fast(a) * swish_fast(b) : 0.f;
         }
     }
     pdl_trigger();
@@ -224,7 +228,7 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
                                                             const float* __restrict__ dg0, float* __restrict__ dWd,
                                                             float* __restrict__ dbd, float* __restrict__ dWw,
                                                             float* __restrict__ dbw) {
-    __shared__ float s_rbf[SCANN_TILE][2 * SCANN_RBF + 1];
+    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
     __shared__ int s_c[SCANN_TILE];
     __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
@@ -255,20 +259,28 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
                 const int row = r8 + 2 * q;
                 if (s_c[row] < 0) continue;
                 float a = bdn, b = bwn;
+                const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
+                float4 rd[SCANN_RBF / 4], rw[SCANN_RBF / 4];
 #pragma unroll
-                for (int k = 0; k < SCANN_RBF; ++k) {
-                    a = fmaf(s_rbf[row][k], wd[k], a);
-                    b = fmaf(s_rbf[row][SCANN_RBF + k], ww[k], b);
+                for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                    rd[k4] = rb[k4];
+                    rw[k4] = rb[SCANN_RBF / 4 + k4];
+                    a = fmaf(rd[k4].x, wd[4 * k4], a); a = fmaf(rd[k4].y, wd[4 * k4 + 1], a);
+                    a = fmaf(rd[k4].z, wd[4 * k4 + 2], a); a = fmaf(rd[k4].w, wd[4 * k4 + 3], a);
+                    b = fmaf(rw[k4].x, ww[4 * k4], b); b = fmaf(rw[k4].y, ww[4 * k4 + 1], b);
+                    b = fmaf(rw[k4].z, ww[4 * k4 + 2], b); b = fmaf(rw[k4].w, ww[4 * k4 + 3], b);
                 }
-                const float sa = sigmoid_f(a), sb = sigmoid_f(b);
+                const float sa = sigmoid_fast(a), sb = sigmoid_fast(b);
                 const float da = dv[q] * (b * sb) * (sa * (1.0f + a * (1.0f - sa)));
                 const float db = dv[q] * (a * sa) * (sb * (1.0f + b * (1.0f - sb)));
                 gbd += da;
                 gbw += db;
 #pragma unroll
-                for (int k = 0; k < SCANN_RBF; ++k) {
-                    gd[k] = fmaf(s_rbf[row][k], da, gd[k]);
-                    gw[k] = fmaf(s_rbf[row][SCANN_RBF + k], db, gw[k]);
+                for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                    gd[4 * k4] = fmaf(rd[k4].x, da, gd[4 * k4]); gd[4 * k4 + 1] = fmaf(rd[k4].y, da, gd[4 * k4 + 1]);
+                    gd[4 * k4 + 2] = fmaf(rd[k4].z, da, gd[4 * k4 + 2]); gd[4 * k4 + 3] = fmaf(rd[k4].w, da, gd[4 * k4 + 3]);
+                    gw[4 * k4] = fmaf(rw[k4].x, db, gw[4 * k4]); gw[4 * k4 + 1] = fmaf(rw[k4].y, db, gw[4 * k4 + 1]);
+                    gw[4 * k4 + 2] = fmaf(rw[k4].z, db, gw[4 * k4 + 2]); gw[4 * k4 + 3] = fmaf(rw[k4].w, db, gw[4 * k4 + 3]);
                 }
             }
         }

@@ -55,13 +55,16 @@ struct ChainArgs {
     ChainStep s[CH_MAX_STEPS];
 };
 
-__device__ __forceinline__ void chain_weight_to_tmem(const float* __restrict__ W, uint32_t t_whi, uint32_t t_wlo, int warp,
-                                                     int lane) {
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+// weight block W[k][n] -> registers of thread (n = output feature, 64 consecutive k): all 64 loads in flight
+__device__ __forceinline__ void chain_weight_load(const float* __restrict__ W, float (&w)[64], int warp, int lane) {
     const int n = (warp & 3) * 32 + lane, kbase = (warp >> 2) * 64;
-    float w[64];
 #pragma unroll
-    for (int q = 0; q < 64; ++q) w[q] = __ldg(W + (size_t)(kbase + q) * SCANN_D + n);     // all 64 loads in flight
+    for (int q = 0; q < 64; ++q) w[q] = __ldg(W + (size_t)(kbase + q) * SCANN_D + n);
+}
+// registers -> tensor memory as A[M = n][K = k], hi and lo tf32 parts
+__device__ __forceinline__ void chain_weight_store(const float (&w)[64], uint32_t t_whi, uint32_t t_wlo, int warp) {
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int kbase = (warp >> 2) * 64;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         float hi[16], lo[16];
@@ -71,12 +74,20 @@ __device__ __forceinline__ void chain_weight_to_tmem(const float* __restrict__ W
         tmem_st16(t_wlo + lane_base + kbase + g * 16, lo);
     }
 }
+__device__ __forceinline__ void chain_weight_to_tmem(const float* __restrict__ W, uint32_t t_whi, uint32_t t_wlo, int warp,
+                                                     int lane) {
+    float w[64];
+    chain_weight_load(W, w, warp, lane);
+    chain_weight_store(w, t_whi, t_wlo, warp);
+}
 
 template <int TR>
 __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid_constant__ ChainArgs a) {
     constexpr int XIT = TR / 8;                         // LDG.128 per thread for one activation tile
     constexpr uint32_t IMG = (TR / 8) * TC_RG_STRIDE;   // bytes of one K-major image of TR rows
     constexpr int STEPS = TR / (CH_THREADS / 32) / 4;   // row-group steps per warp in the epilogue
+    // with 32-row tiles the registers allow fetching the NEXT step's weight block while the epilogue runs
+    constexpr bool WPREF = TR == 32;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* sXhi = smem;
     uint8_t* sXlo = smem + IMG;
@@ -104,10 +115,22 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
     pdl_wait();
     CCLK(2);
 
+    float wnext[64];                 // only live when WPREF
+    bool have_next = false;
 #pragma unroll 1
     for (int si = 0; si < a.nsteps; ++si) {
         const ChainStep& st = a.s[si];
+        // parameters of the epilogue: issue the loads now, they are needed after the MMA
+        float4 bias[4], gam[4], bet[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int c0 = (l8 + 8 * it) * 4;
+            bias[it] = st.bias ? ldg4(st.bias + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
+            gam[it] = st.gamma ? ldg4(st.gamma + c0) : bias[it];
+            bet[it] = st.beta ? ldg4(st.beta + c0) : bias[it];
+        }
         // ------------------------------------------------------------------ GEMM: D^T = sum_kb W_kb^T X_kb^T
+        float4 rv0[4], pv0[4];
 #pragma unroll 1
         for (int kb = 0; kb < st.kblk; ++kb) {
             const float* A = st.A[kb];
@@ -120,7 +143,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                     if (r0 + r < a.R) xv[it] = ld4(A + (size_t)(r0 + r) * st.lda + c4 * 4);
                 }
             }
-            if (si > 0 || kb > 0) chain_weight_to_tmem(st.W[kb], t_whi, t_wlo, warp, lane);
+            if (WPREF && kb == 0 && have_next) chain_weight_store(wnext, t_whi, t_wlo, warp);
+            else if (si > 0 || kb > 0) chain_weight_to_tmem(st.W[kb], t_whi, t_wlo, warp, lane);
             if (A) {
 #pragma unroll
                 for (int it = 0; it < XIT; ++it) {
@@ -152,12 +176,30 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                 for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
                 tc_commit(&bar);
             }
+            if (kb == st.kblk - 1) {
+                // while the tensor core works: the global rows the first epilogue step needs
+                const int rr = warp * (TR / (CH_THREADS / 32)) + rsub, r = r0 + rr;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    rv0[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    pv0[it] = rv0[it];
+                    if (r < a.R) {
+                        if (st.resid) rv0[it] = ld4(st.resid + (size_t)r * st.ldres + (l8 + 8 * it) * 4);
+                        if (st.mode == 2 || st.mode == 4) pv0[it] = ld4(st.pre_in + (size_t)r * st.ldpre + (l8 + 8 * it) * 4);
+                    }
+                }
+            }
             mbar_wait(&bar, phase);
             phase ^= 1;
             tc_fence_after();
             __syncthreads();
         }
         CCLK(4 + si * 4);
+        if constexpr (WPREF) {
+            // the weights in tensor memory are free now: fetch the next step's first block behind the epilogue
+            have_next = si + 1 < a.nsteps;
+            if (have_next) chain_weight_load(a.s[si + 1].W[0], wnext, warp, lane);
+        }
         if (si == a.nsteps - 1) pdl_trigger();      // only the last epilogue is left
         // ------------------------------------------------------------------ epilogue 1: D^T -> S[r][n]
         {
@@ -178,14 +220,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
         CCLK(5 + si * 4);
         // ------------------------------------------------------------------ epilogue 2: row groups
         const int mode = st.mode;
-        float4 bias[4], gam[4], bet[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-            const int c0 = (l8 + 8 * it) * 4;
-            bias[it] = st.bias ? ldg4(st.bias + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
-            gam[it] = st.gamma ? ldg4(st.gamma + c0) : bias[it];
-            bet[it] = st.beta ? ldg4(st.beta + c0) : bias[it];
-        }
         float dgam[4][4], dbet[4][4];
 #pragma unroll
         for (int it = 0; it < 4; ++it)
@@ -200,8 +234,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
             for (int it = 0; it < 4; ++it) {
                 const int c4 = l8 + 8 * it, c0 = c4 * 4;
                 const float4 acc = *reinterpret_cast<const float4*>(sS + tc_off4(rr, c4));
-                float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (st.resid && ok) rv = ld4(st.resid + (size_t)r * st.ldres + c0);
+                float4 rv = rv0[it];
+                if (step > 0) {
+                    rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (st.resid && ok) rv = ld4(st.resid + (size_t)r * st.ldres + c0);
+                }
                 v[it][0] = acc.x + bias[it].x + rv.x; v[it][1] = acc.y + bias[it].y + rv.y;
                 v[it][2] = acc.z + bias[it].z + rv.z; v[it][3] = acc.w + bias[it].w + rv.w;
             }
@@ -217,8 +254,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
             } else if (mode == 2) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) p = ld4(st.pre_in + (size_t)r * st.ldpre + (l8 + 8 * it) * 4);
+                    float4 p = pv0[it];
+                    if (step > 0) {
+                        p = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) p = ld4(st.pre_in + (size_t)r * st.ldpre + (l8 + 8 * it) * 4);
+                    }
                     v[it][0] *= swish_grad_fast(p.x); v[it][1] *= swish_grad_fast(p.y);
                     v[it][2] *= swish_grad_fast(p.z); v[it][3] *= swish_grad_fast(p.w);
                 }
@@ -254,8 +294,11 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                 float s1 = 0.f;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) p = ld4(st.pre_in + (size_t)r * st.ldpre + (l8 + 8 * it) * 4);
+                    float4 p = pv0[it];
+                    if (step > 0) {
+                        p = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok) p = ld4(st.pre_in + (size_t)r * st.ldpre + (l8 + 8 * it) * 4);
+                    }
                     x[it][0] = p.x; x[it][1] = p.y; x[it][2] = p.z; x[it][3] = p.w;
                     s1 += p.x + p.y + p.z + p.w;
                 }

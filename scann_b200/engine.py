@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _abi
-from ._abi import ChainStep, chain_step, check, lib, ptr_array
+from ._abi import ChainStep, WgradProblem, chain_step, check, lib, ptr_array
 from .config import ModelSpec, N_RBF, check_kernel_support
 from .params import ParamLayout, layer_name
 
@@ -110,6 +110,8 @@ class Engine:
         self._skip = set(filter(None, os.environ.get("SCANN_DEBUG_SKIP", "").split(",")))
         # per-atom Dense layers between two local-attention layers fused into one chained kernel
         self.use_chain = os.environ.get("SCANN_CHAIN", "1") == "1" and self.tc_dense and self.tc_la_fwd
+        # every weight-gradient GEMM of the step in one persistent launch at the end of the backward pass
+        self.use_wgrad_batch = os.environ.get("SCANN_WGRAD_BATCH", "1") == "1" and self.use_chain and self.tc_la_bwd
 
     # ------------------------------------------------------------------ helpers
     def _ev(self, name: str, begin: bool) -> None:
@@ -773,13 +775,16 @@ class Engine:
                             mode=2, pre_in=_p(ws["ta"]), C_=_p(ws["d_ta"]), to_image=True)]
         steps += with_tail(dict(W=[self.wT("after_Lc/kernel")]), L - 1)
         self._chain(steps, R)
-        fork()
-        wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
-              [self.gw("bf_property/bias")])
-        wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
-              [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
-              [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
-        wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")], [self.gw("after_Lc/bias")])
+        batched = self.use_wgrad_batch
+        if not batched:
+            fork()
+            wgrad([_p(ws["ctxg"])], D, [_p(ws["d_tb"])], D, 1, 1, b.B, [self.gw("bf_property/kernel")],
+                  [self.gw("bf_property/bias")])
+            wgrad([_p(ws["xa"])], D, [_p(dqk), _p(dqk, D)], 2 * D, 1, 2, R,
+                  [self.gw("global_attention/query/kernel"), self.gw("global_attention/key/kernel")],
+                  [self.gw("global_attention/query/bias"), self.gw("global_attention/key/bias")])
+            wgrad([_p(ws["x"][L])], D, [_p(ws["d_ta"])], D, 1, 1, R, [self.gw("after_Lc/kernel")],
+                  [self.gw("after_Lc/bias")])
         dg_up = None
         for l in range(L - 1, -1, -1):
             la = layer_name("local_attention", l)
@@ -808,8 +813,8 @@ class Engine:
                                                            self.wT(f"{la}/query/kernel")], resid=_p(dx_sc))
             self._chain(with_tail(head, l - 1) if l > 0 else [chain_step(**head, C_=_p(dx))], R)
             dg_up = dg_out
-            # ---- weight gradients of this layer (side stream)
-            if "wgrad" in self._skip:
+            # ---- weight gradients of this layer (side stream), unless they are batched at the end
+            if "wgrad" in self._skip or batched:
                 continue
             fork()
             check(lib.scann_la_wgrad_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
@@ -826,7 +831,55 @@ class Engine:
             wgrad([_p(ws["x"][l])], D, [_p(s_pre), _p(t_sc), _p(dq)], D, 1, 3, R,
                   [self.gw(fg, 0), self.gw(fg, 2 * D * D), self.gw(f"{la}/query/kernel")],
                   [self.gw(f"{la}/filter_geo/bias"), 0, self.gw(f"{la}/query/bias")])
+        if batched and "wgrad" not in self._skip:
+            table, count = self._wgrad_table(b, ws)
+            self._pdl(False)
+            self._ev("wgrad_batch", True)
+            check(lib.scann_wgrad_batch_tc(self.la_grid, _p(table), count, _p(b.ntiles), b.stride, _p(b.pair_c),
+                                           _p(b.pair_j), st), "wgrad_batch_tc")
+            self._ev("wgrad_batch", False)
+            self.launches += 1
         self._backward_tail(b, ws, dg_up, side, main)
+
+    def _wgrad_table(self, b: Batch, ws: dict):
+        """Device table of all dW += X^T Y problems of a train step (pointers into this workspace)."""
+        if "wg_table" in ws:
+            return ws["wg_table"], ws["wg_count"]
+        sp = self.spec
+        L, R = sp.n_attention, b.R
+        probs = []
+
+        def add(X, Y, dW, db=0, xg=0, ldx=D, ldy=D, rows=R):
+            pr = WgradProblem()
+            pr.X, pr.Y, pr.xg, pr.dW, pr.db = X or None, Y or None, xg or None, dW or None, db or None
+            pr.ldx, pr.ldy, pr.rows, pr.pad = ldx, ldy, rows, 0
+            probs.append(pr)
+
+        dqk = ws["d_qk"]
+        add(_p(ws["ctxg"]), _p(ws["d_tb"]), self.gw("bf_property/kernel"), self.gw("bf_property/bias"), rows=b.B)
+        add(_p(ws["xa"]), _p(dqk), self.gw("global_attention/query/kernel"), self.gw("global_attention/query/bias"),
+            ldy=2 * D)
+        add(_p(ws["xa"]), _p(dqk, D), self.gw("global_attention/key/kernel"), self.gw("global_attention/key/bias"),
+            ldy=2 * D)
+        add(_p(ws["x"][L]), _p(ws["d_ta"]), self.gw("after_Lc/kernel"), self.gw("after_Lc/bias"))
+        for l in range(L - 1, -1, -1):
+            la = layer_name("local_attention", l)
+            rn = layer_name("residual_norm", l)
+            fg = f"{la}/filter_geo/kernel"
+            scat = ws["scat"][l]
+            add(_p(ws["g"][l + 1]), _p(ws["kk"][l]), self.gw(f"{la}/key/kernel"), xg=_p(ws["x"][l]), rows=-1)
+            add(_p(ws["g"][l]), _p(ws["pre"][l]), self.gw(fg, D * D), rows=-1)
+            if sp.use_attn_norm:
+                add(_p(ws["h1"][l]), _p(ws["d_v2"][l]), self.gw(f"{rn}/dense_1/kernel"), self.gw(f"{rn}/dense_1/bias"))
+                add(_p(ws["h"][l]), _p(ws["d_t1"][l]), self.gw(f"{rn}/dense/kernel"), self.gw(f"{rn}/dense/bias"))
+            add(_p(ws["x"][l]), _p(scat[0]), self.gw(fg, 0), self.gw(f"{la}/filter_geo/bias"))
+            add(_p(ws["x"][l]), _p(scat[1]), self.gw(fg, 2 * D * D))
+            add(_p(ws["x"][l]), _p(ws["dq"][l]), self.gw(f"{la}/query/kernel"), self.gw(f"{la}/query/bias"))
+        arr = (WgradProblem * len(probs))(*probs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        ws["wg_table"] = host.to(self.device)
+        ws["wg_count"] = len(probs)
+        return ws["wg_table"], ws["wg_count"]
 
     def _backward_prep(self, ws: dict, stream: int) -> None:
         """Work the backward needs that does not depend on the forward: transposed weight blocks and
