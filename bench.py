@@ -284,15 +284,37 @@ def run_ours(args):
     bytes_fwd = 1028.0 * P_valid + 1028.0 * A_valid
     n_bwd, ms_bwd = prof.get("la_backward", (0, float("nan")))
     n_fwd, ms_fwd = prof.get("la_forward", (0, float("nan")))
+    n_wg, ms_wg = prof.get("wgrad_batch", (0, float("nan")))
     ach = bytes_bwd / (ms_bwd * 1e-3) / 1e9
-    kern = ("la_attn_bwd_tc + la_geom_bwd_tc + 2 x la_wgrad_tc (one layer of local-attention backward)"
-            if eng.tc_la_bwd else "la_bwd_simt_kernel")
+    kern = ("la_attn_bwd_tc_kernel + la_geom_bwd_tc_kernel (one scann_la_backward_tc call = one layer of "
+            "local-attention backward)" if eng.tc_la_bwd else "la_bwd_simt_kernel")
+    # DRAM traffic of the same kernels from the committed `ncu --set full` capture (dram__bytes_read.sum +
+    # dram__bytes_write.sum per launch), when the workload matches the capture
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("workload") == f"{args.workload}_train_step_b{B}":
+            traffic = tj.get("la_backward_bytes_per_launch")
+    # tensor-core view of the same kernels: 3xTF32 = 3 tensor-core products per algorithmic product
+    # (two [P,128]x[128,128] input-gradient GEMMs per layer = 65 536 flops per valid pair; the weight
+    # gradients are a separate launch)
+    flops_bwd = 3.0 * 65536.0 * P_valid
     roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+            "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
             "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
             "share_of_step": n_bwd * ms_bwd / args.steps / (dev_ms / args.steps),
+            "algorithmic_bytes_per_launch": bytes_bwd,
+            "tensor_view": {"tf32_tflops_issued": flops_bwd / (ms_bwd * 1e-3) / 1e12,
+                            "note": "3 tf32 products per fp32 product; nominal dense tf32 peak is half the bf16 peak"},
             "la_forward": {"achieved": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "ms_per_launch": ms_fwd,
                            "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
+    if n_wg:
+        # every weight-gradient GEMM of the step in one launch: reads each saved per-pair tensor once
+        bytes_wg = L * (4 * 512.0 * P_valid + 512.0 * P_valid) + L * 8 * 512.0 * A_valid
+        roof["wgrad_batch"] = {"achieved": bytes_wg / (ms_wg * 1e-3) / 1e9, "ms_per_launch": ms_wg,
+                               "frac": bytes_wg / (ms_wg * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     # bounded CPU sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu and args.workload == "qm9":

@@ -170,7 +170,18 @@ int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntile
                                  const int32_t* pair_j, const float* x, const float* proj, const float* pair_d,
                                  const float* pair_w, const float* centers, const float* Wf, const float* bf,
                                  const float* Wk, const float* bk, const float* gamma, const float* beta,
-                                 float* ctx_pre, float* out, float* attn, void* stream);
+                                 float* ctx_pre, float* out, float* attn, float* g_save, float* k_out, void* stream);
+/* Backward of the g_update=False layer: attention part (g_new / kbuf = g' / keys saved by the forward; kbuf <- d_k,
+ * dg <- gradient w.r.t. g', dq / dx_scatter as in scann_la_backward_tc) ... */
+int scann_la_backward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+                                  const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
+                                  const int32_t* pair_j, const float* x, const float* proj, const float* g_new,
+                                  float* kbuf, const float* WkT, const float* d_ctx, float* dg, float* dq,
+                                  float* dx_scatter, float* dbk, void* stream);
+/* ... and the gradient of its geometry filter g' = swish(rbf(d) @ Wf + bf) * w: dWf [20,128], dbf accumulated. */
+int scann_noupdate_geom_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
+                                 const float* pair_d, const float* pair_w, const float* centers_d, const float* Wf,
+                                 const float* bf, const float* dg, float* dWf, float* dbf, void* stream);
 /* Reverse-mode of the above (TF autodiff inside keras fit, scann_model.py:232-241).  d_ctx is the
  * gradient w.r.t. the pre-LN context; dq/s_pre are written for atoms with pairs, t_scatter /
  * dx_scatter are accumulated with atomics (pre-zero them); wpart: grid*2*128*128 floats. */

@@ -297,6 +297,68 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
     }
 }
 
+// g_update = False (attention.py:155): g' = swish(rbf(d) @ Wf + bf) * w is recomputed in every layer; its only
+// trainable inputs are Wf [20,128] and bf.  dWf += rbf^T d_pre, dbf += sum d_pre with
+// d_pre = dg' * w * swish'(pre), pre = rbf @ Wf + bf (recomputed here from the 8 bytes/pair of raw geometry).
+__global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
+                                                                const int32_t* __restrict__ pair_c,
+                                                                const float* __restrict__ pair_d,
+                                                                const float* __restrict__ pair_w,
+                                                                const float* __restrict__ cd,
+                                                                const float* __restrict__ Wf, const float* __restrict__ bf,
+                                                                const float* __restrict__ dg, float* __restrict__ dWf,
+                                                                float* __restrict__ dbf) {
+    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];
+    __shared__ int s_c[SCANN_TILE];
+    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
+    const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
+    float wf[SCANN_RBF], gf[SCANN_RBF];
+#pragma unroll
+    for (int k = 0; k < SCANN_RBF; ++k) { wf[k] = Wf[k * SCANN_D + n]; gf[k] = 0.f; }
+    const float bfn = bf[n];
+    float gb = 0.f;
+    pdl_wait();
+    const int nt = *ntiles;
+    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
+        const size_t base = (size_t)t * stride;
+        __syncthreads();
+        if (t + (int)gridDim.x >= nt) pdl_trigger();
+        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cd, base, stride);   // columns 20..39 unused
+        for (int r8 = half; r8 < stride; r8 += 16) {
+            float dv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dv[q] = dg[(base + r8 + 2 * q) * SCANN_D + n];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int row = r8 + 2 * q;
+                if (s_c[row] < 0) continue;
+                float a = bfn;
+                const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
+                float4 rd[SCANN_RBF / 4];
+#pragma unroll
+                for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                    rd[k4] = rb[k4];
+                    a = fmaf(rd[k4].x, wf[4 * k4], a); a = fmaf(rd[k4].y, wf[4 * k4 + 1], a);
+                    a = fmaf(rd[k4].z, wf[4 * k4 + 2], a); a = fmaf(rd[k4].w, wf[4 * k4 + 3], a);
+                }
+                const float da = dv[q] * s_w[row] * swish_grad_f(a);
+                gb += da;
+#pragma unroll
+                for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                    gf[4 * k4] = fmaf(rd[k4].x, da, gf[4 * k4]); gf[4 * k4 + 1] = fmaf(rd[k4].y, da, gf[4 * k4 + 1]);
+                    gf[4 * k4 + 2] = fmaf(rd[k4].z, da, gf[4 * k4 + 2]); gf[4 * k4 + 3] = fmaf(rd[k4].w, da, gf[4 * k4 + 3]);
+                }
+            }
+        }
+    }
+    pdl_trigger();
+    if ((int)blockIdx.x < nt) {
+#pragma unroll
+        for (int k = 0; k < SCANN_RBF; ++k) atomicAdd(dWf + k * SCANN_D + n, gf[k]);
+        atomicAdd(dbf + n, gb);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Blocked dense GEMM:  C[r, nb*128 + c] = epi( sum_kb A_kb[r,:] @ W[kb*nblk+nb] + bias[nb] )
 // A_kb: [R,128] with row stride lda; W blocks: [128,128] row-major.
@@ -601,6 +663,18 @@ extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, int til
     scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
     return scann_check_launch("scann_geom_init_backward");
+}
+
+// Weight gradient of the g_update = False geometry (see noupdate_geom_bwd_kernel): dWf [20,128], dbf [128]
+// accumulated from dg = gradient w.r.t. g' ([rows,128], left by scann_la_backward_noupdate_tc).
+extern "C" int scann_noupdate_geom_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
+                                            const float* pair_d, const float* pair_w, const float* centers_d,
+                                            const float* Wf, const float* bf, const float* dg, float* dWf, float* dbf,
+                                            void* stream) {
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("noupdate_geom_backward: tile_stride must be 64 or 128"); return 1; }
+    scann_launch(noupdate_geom_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w,
+                 centers_d, Wf, bf, dg, dWf, dbf);
+    return scann_check_launch("scann_noupdate_geom_backward");
 }
 
 // Generic blocked dense: see DenseArgs.  A/W/bias arrays hold kblk / kblk*nblk / nblk entries.

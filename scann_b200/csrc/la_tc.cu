@@ -277,6 +277,7 @@ struct LaAttnArgs {
     float* k_out;            // [rows,128] nullable (keys, saved for backward)
     // g_update = False (attention.py:155): g' = swish(rbf(d) @ Wf[20,128] + bf) * w, computed on the fly
     const float* pair_d; const float* pair_w; const float* centers; const float* Wf; const float* bf;
+    float* g_save;           // [rows,128] nullable: g' of the g_update = False path, saved for the backward pass
 };
 
 template <int NG>
@@ -365,6 +366,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
                     gv[it] = ok ? make_float4(swish_f(acc[it].x) * wgt, swish_f(acc[it].y) * wgt,
                                               swish_f(acc[it].z) * wgt, swish_f(acc[it].w) * wgt)
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.g_save)
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) st4(a.g_save + (rowbase + r) * SCANN_D + (l8 + 8 * it) * 4, gv[it]);
             }
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -488,7 +492,7 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* nti
     if (grid <= 0) return 0;
     LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr};
+                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (tile_stride == 64) {
         scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
         scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
@@ -501,19 +505,20 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* nti
 
 // LocalAttention.call with g_update = False (attention.py:155-216): neighbor_geometry' =
 // swish(rbf(distance) @ Wf + bf) * weight is recomputed per layer from the 8 bytes/pair of raw geometry;
-// proj needs only its query block (columns 256..383).  Inference path (no saves for backward).
+// proj needs only its query block (columns 256..383).  g_save / k_out ([rows,128], nullable): g' and the keys,
+// saved for scann_la_backward_noupdate_tc.
 extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
                                             const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                             const int32_t* pair_c, const int32_t* pair_j, const float* x,
                                             const float* proj, const float* pair_d, const float* pair_w,
                                             const float* centers, const float* Wf, const float* bf, const float* Wk,
                                             const float* bk, const float* gamma, const float* beta, float* ctx_pre,
-                                            float* out, float* attn, void* stream) {
+                                            float* out, float* attn, float* g_save, float* k_out, void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, nullptr, pair_d, pair_w, centers, Wf, bf};
+                  ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save};
     if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     else scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");

@@ -695,6 +695,26 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, const int32_t* nt
     return scann_check_launch("scann_la_backward_tc");
 }
 
+// Backward of LocalAttention.call with g_update = False (attention.py:155-216): the attention kernel only
+// (softmax / context / key projection backward; d_nbr scattered to dx_scatter; dg <- gradient w.r.t.
+// g' = swish(rbf @ Wf + bf) * w, consumed by scann_noupdate_geom_backward).  g_new / kbuf: the g' and keys saved
+// by scann_la_forward_noupdate_tc; kbuf is overwritten with d_k (left operand gradient for the key kernel).
+extern "C" int scann_la_backward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+                                             const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
+                                             const int32_t* pair_c, const int32_t* pair_j, const float* x,
+                                             const float* proj, const float* g_new, float* kbuf, const float* WkT,
+                                             const float* d_ctx, float* dg, float* dq, float* dx_scatter, float* dbk,
+                                             void* stream) {
+    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (la_bwd_configure()) return 1;
+    if (grid <= 0) return 0;
+    LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
+                     0, dq, dx_scatter, dbk};
+    if (tile_stride == 64) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+    else scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+    return scann_check_launch("scann_la_backward_noupdate_tc");
+}
+
 // Pair weight gradients of one LocalAttention layer into wpart[grid][2][128][128] (off the critical path of
 // the backward chain: may run on a side stream once scann_la_backward_tc of the layer has finished):
 //   wpart[.][0] = sum (x[j]*g')^T d_k (-> key/kernel),  wpart[.][1] = sum g^T d_pre (-> filter_geo rows 128..255)

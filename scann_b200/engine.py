@@ -327,7 +327,10 @@ class Engine:
             ws["v2"] = [torch.empty(R, D, **f) for _ in range(L)]
             ws["ta"] = torch.empty(R, D, **f)
             if self.tc_la_bwd:
-                ws["pre"] = [torch.empty(rows, D, **f) for _ in range(L)]     # filter_geo pre-activation -> d_pre
+                if self.spec.g_update:
+                    ws["pre"] = [torch.empty(rows, D, **f) for _ in range(L)]     # filter_geo pre-activation -> d_pre
+                else:
+                    ws["gsave"] = [torch.empty(rows, D, **f) for _ in range(L)]   # g' = swish(rbf Wf + bf) * w
                 ws["kk"] = [torch.empty(rows, D, **f) for _ in range(L)]      # keys -> d_k
             ws["ctxg"] = torch.empty(b.B, D, **f)
             ws["tb"] = torch.empty(b.B, D, **f)
@@ -379,9 +382,9 @@ class Engine:
         L, R = sp.n_attention, b.R
         xs, gs = ws["x"], ws["g"]
         E = sp.embedding_dim
-        if training and (not sp.g_update or sp.use_ring):
-            raise NotImplementedError("training is accelerated for g_update=True, use_ring=False models only; "
-                                      "g_update=False / use_ring=True run the inference path")
+        if training and not sp.g_update and not (self.use_chain and self.tc_la_bwd and self.use_wgrad_batch):
+            raise NotImplementedError("training of g_update=False models needs the tensor-core engine "
+                                      "(SCANN_ENGINE=tc, SCANN_CHAIN=1)")
         ring = sp.use_ring
         self._pdl(False)
         check(lib.scann_embed_forward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
@@ -423,7 +426,7 @@ class Engine:
                     self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
                     _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d), self.w(fg),
                     self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
-                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), st),
+                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), 0, 0, st),
                     "la_forward_noupdate_tc")
                 self.launches += 2
                 if sp.use_attn_norm:
@@ -545,7 +548,8 @@ class Engine:
                     self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
                     self.w(fg), self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
-                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), st),
+                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), _p(attn),
+                    _p(ws["gsave"][l]) if training else 0, _p(ws["kk"][l]) if training else 0, st),
                     "la_forward_noupdate_tc")
                 self.launches += 1
             self._ev("la_forward", False)
@@ -723,7 +727,7 @@ class Engine:
         sp, st = self.spec, self._stream()
         R = b.R
         dx = ws["dx"]
-        if "geom_init" not in self._skip:
+        if sp.g_update and "geom_init" not in self._skip:
           check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                            _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                            self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
@@ -732,9 +736,13 @@ class Engine:
                                            self.gw("neighbor_w/bias"), st), "geom_init_backward")
         self._pdl(False)
         E = sp.embedding_dim
-        check(lib.scann_embed_backward(_p(b.atomic), 0, R, E, sp.n_atoms, self.w("embed_atom/embeddings"), 0, 0,
+        ring = sp.use_ring
+        check(lib.scann_embed_backward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
+                                       self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
+                                       self.w("extra_embed/bias") if ring else 0,
                                        self.w("dense_embed/kernel"), _p(ws["t0"]), _p(dx), _p(ws["G"]),
-                                       self.gw("embed_atom/embeddings"), 0, 0, self.gw("dense_embed/kernel"),
+                                       self.gw("embed_atom/embeddings"), self.gw("extra_embed/kernel") if ring else 0,
+                                       self.gw("extra_embed/bias") if ring else 0, self.gw("dense_embed/kernel"),
                                        self.gw("dense_embed/bias"), st), "embed_backward")
         self.launches += 4
         if side is not main:             # join: the optimiser needs every weight gradient
@@ -796,7 +804,19 @@ class Engine:
             dg_out = ws["dg"][(L - l) % 2]
             dg_buf = ws["dg"][(L - 1 - l) % 2]
             self._ev("la_backward", True)
-            if "la_bwd" not in self._skip:
+            if not sp.g_update:
+                # SCANN without geometry update: attention part only, then the filter_geo [20,128] gradient
+                check(lib.scann_la_backward_noupdate_tc(
+                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["gsave"][l]), _p(ws["kk"][l]),
+                    self.wT(f"{la}/key/kernel"), _p(ws["d_ctx"]), _p(ws["dg"][0]), _p(dq), _p(dx_sc),
+                    self.gw(f"{la}/key/bias"), st), "la_backward_noupdate_tc")
+                check(lib.scann_noupdate_geom_backward(
+                    _p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
+                    self.w(fg), self.w(f"{la}/filter_geo/bias"), _p(ws["dg"][0]), self.gw(fg),
+                    self.gw(f"{la}/filter_geo/bias"), st), "noupdate_geom_backward")
+                self.launches += 2
+            elif "la_bwd" not in self._skip:
                 check(lib.scann_la_backward_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1),
                                                _p(b.cnt), _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
                                                _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
@@ -809,8 +829,11 @@ class Engine:
                 self.launches += 2
             self._ev("la_backward", False)
             # next link of the critical path: gradient w.r.t. the layer input x_l, then the tail of layer l-1
-            head = dict(A=[_p(s_pre), _p(t_sc), _p(dq)], W=[self.wT(fg, 0), self.wT(fg, 2 * D * D),
-                                                           self.wT(f"{la}/query/kernel")], resid=_p(dx_sc))
+            if sp.g_update:
+                head = dict(A=[_p(s_pre), _p(t_sc), _p(dq)], W=[self.wT(fg, 0), self.wT(fg, 2 * D * D),
+                                                               self.wT(f"{la}/query/kernel")], resid=_p(dx_sc))
+            else:
+                head = dict(A=[_p(dq)], W=[self.wT(f"{la}/query/kernel")], resid=_p(dx_sc))
             self._chain(with_tail(head, l - 1) if l > 0 else [chain_step(**head, C_=_p(dx))], R)
             dg_up = dg_out
             # ---- weight gradients of this layer (side stream), unless they are batched at the end
@@ -867,13 +890,17 @@ class Engine:
             rn = layer_name("residual_norm", l)
             fg = f"{la}/filter_geo/kernel"
             scat = ws["scat"][l]
-            add(_p(ws["g"][l + 1]), _p(ws["kk"][l]), self.gw(f"{la}/key/kernel"), xg=_p(ws["x"][l]), rows=-1)
-            add(_p(ws["g"][l]), _p(ws["pre"][l]), self.gw(fg, D * D), rows=-1)
+            if sp.g_update:
+                add(_p(ws["g"][l + 1]), _p(ws["kk"][l]), self.gw(f"{la}/key/kernel"), xg=_p(ws["x"][l]), rows=-1)
+                add(_p(ws["g"][l]), _p(ws["pre"][l]), self.gw(fg, D * D), rows=-1)
+            else:
+                add(_p(ws["gsave"][l]), _p(ws["kk"][l]), self.gw(f"{la}/key/kernel"), xg=_p(ws["x"][l]), rows=-1)
             if sp.use_attn_norm:
                 add(_p(ws["h1"][l]), _p(ws["d_v2"][l]), self.gw(f"{rn}/dense_1/kernel"), self.gw(f"{rn}/dense_1/bias"))
                 add(_p(ws["h"][l]), _p(ws["d_t1"][l]), self.gw(f"{rn}/dense/kernel"), self.gw(f"{rn}/dense/bias"))
-            add(_p(ws["x"][l]), _p(scat[0]), self.gw(fg, 0), self.gw(f"{la}/filter_geo/bias"))
-            add(_p(ws["x"][l]), _p(scat[1]), self.gw(fg, 2 * D * D))
+            if sp.g_update:
+                add(_p(ws["x"][l]), _p(scat[0]), self.gw(fg, 0), self.gw(f"{la}/filter_geo/bias"))
+                add(_p(ws["x"][l]), _p(scat[1]), self.gw(fg, 2 * D * D))
             add(_p(ws["x"][l]), _p(ws["dq"][l]), self.gw(f"{la}/query/kernel"), self.gw(f"{la}/query/bias"))
         arr = (WgradProblem * len(probs))(*probs)
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)

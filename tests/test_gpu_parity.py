@@ -239,8 +239,21 @@ def test_scann_without_geometry_update_and_ring_features():
     eng, b, y, ga = run_forward(spec, arena, inputs)
     assert rel(y, y_ref.ravel()) <= TOL_OUT
     assert rel(ga, ga_ref[..., 0]) <= TOL_OUT
-    with pytest.raises(NotImplementedError):              # training of this variant is not accelerated yet
-        eng.forward(b, training=True)
+    # train step of the same variant: every gradient against the oracle's reverse-mode autodiff
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, _, _, grads = O.loss_and_grads(w, inputs, target, l2n, **kw)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+    lv = eng.loss_value(b.B).cpu().numpy()
+    assert abs(lv[0] - float(loss)) <= 1e-5 * abs(float(loss))
 
 
 def test_malformed_input_is_reported():
