@@ -135,8 +135,14 @@ def cpu_train_step_fn():
     state = {"w": {k: v.copy() for k, v in w.items()}, "m": {k: np.zeros_like(v) for k, v in w.items()},
              "v": {k: np.zeros_like(v) for k, v in w.items()}, "t": 0}
 
+    B_, M_ = inp["atomic"].shape
+    gen = torch.Generator().manual_seed(0)
+
     def step():
-        _, _, _, g = O.loss_and_grads(state["w"], inp, tgt, l2n, dtype=torch.float32, **kw)
+        # training-mode Dropout(0.1) masks (scann_model.py:374, attention.py:29), as in a Keras fit step
+        names = ["dense_embed"] + ["residual_norm" if l == 0 else f"residual_norm_{l}" for l in range(spec.n_attention)]
+        masks = {n: (torch.rand(B_, M_, 128, generator=gen) >= 0.1).float() / 0.9 for n in names}
+        _, _, _, g = O.loss_and_grads(state["w"], inp, tgt, l2n, dtype=torch.float32, drop_masks=masks, **kw)
         state["t"] += 1
         for k in state["w"]:
             state["w"][k], state["m"][k], state["v"][k] = O.adam_legacy_step(
@@ -186,6 +192,9 @@ def run_ours(args):
     model = create_model(CFG, seed=1)
     sdist.attach(model, world)
     eng = model.engine
+    # the Keras train step runs the graph with training=True: Dropout(0.1) after dense_embed and in every
+    # ResidualNorm is part of the measured step (the facade does the same in train_on_batch / fit)
+    eng.train_dropout = True
     inputs, target = make_batch(shape_name, seed=rank, B=B)
     A_valid, P_valid = count_valid(inputs)
     lr = CFG["hyper"]["lr"]
@@ -336,6 +345,7 @@ def run_ours(args):
                    "valid_atoms_per_gpu": A_valid, "valid_pairs_per_gpu": P_valid, "parallelism": f"dp{world}",
                    "l2": "flushed between steps (256 MiB write outside the timed events)",
                    "engine": "tcgen05 3xTF32 (fp32-accurate)" if eng.tc_la_bwd else "fp32 SIMT",
+                   "dropout": eng.dropout_rate if eng.train_dropout else 0.0,
                    "cuda_graphs": bool(eng.use_graphs)},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h)},

@@ -65,11 +65,11 @@ int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, con
  * saved for backward) may be NULL. */
 int scann_embed_forward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
                         const float* Wr, const float* br, const float* We, const float* be, float* t0, float* x0,
-                        int32_t* status, void* stream);
+                        int32_t* status, const void* drop_ctl, void* stream);
 /* Gradients are ACCUMULATED into d_emb, dWr, dbr, dWe, dbe.  G_ws: (n_atoms+3)*128 floats. */
 int scann_embed_backward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
                          const float* Wr, const float* br, const float* We, const float* t0, const float* dx0,
-                         float* G_ws, float* d_emb, float* dWr, float* dbr, float* dWe, float* dbe, void* stream);
+                         float* G_ws, float* d_emb, float* dWr, float* dbr, float* dWe, float* dbe, const void* drop_ctl, void* stream);
 
 /* ---- geometry initialisation: GaussianExpansion x2 + neighbor_d/neighbor_w Dense + Multiply --
  * scann/layers/custom_layers.py:55-65, scann/models/scann_model.py:378-389. */
@@ -121,6 +121,10 @@ int scann_transpose_blocks(const float* src, float* dst, const int32_t* offsets,
  *     C, C2 <- out (nullable);  to_image: out is the A operand of step i+1 (that step has A[0] = NULL, kblk 1;
  *     an operand loaded from global memory also stays resident for later steps with A[0] = NULL).
  *     cnt != NULL: rows with cnt[r] == 0 additionally get np_ctx[r] = V, np_out[r] = LayerNorm(V; gamma, beta).
+ *     drop != NULL (training-mode keras Dropout, attention.py:29, rate 0.1): modes 0-3 multiply (sum + bias) by the
+ *     site's mask before the residual is added; mode 4 writes out to C and out * mask to C2 and the image.
+ *     The mask is a hash of (seed, site, row * 128 + column) kept/scaled per the DEVICE control block
+ *     ScannDropCtl {uint32 seed, threshold = rate * 2^32, float bits of 1/(1-rate), enabled}.
  * `steps` is a HOST array of nsteps structs holding device pointers. */
 typedef struct ScannChainStep {
     const float* A[3];
@@ -138,10 +142,13 @@ typedef struct ScannChainStep {
     const int32_t* cnt;
     float* np_ctx;
     float* np_out;
+    const void* drop;      /* ScannDropCtl* (device) or NULL: training-mode Dropout of site drop_site, see below */
     int lda, ldres, ldpre, ldc, ldc2;
     int kblk;
     int mode;
     int to_image;
+    int drop_site;
+    int pad;
 } ScannChainStep;
 int scann_dense_chain(const ScannChainStep* steps, int nsteps, int R, void* stream);
 

@@ -24,8 +24,8 @@ PROTOTYPES = {
     "scann_device_cc": (ci, []),
     "scann_set_pdl": (ci, [ci]),
     "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
-    "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp]),
-    "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp]),
+    "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp, vp]),
+    "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp, vp]),
     "scann_geom_init_forward": (ci, [vp, ci, ci] + [vp] * 10 + [vp]),
     "scann_geom_init_backward": (ci, [vp, ci, ci] + [vp] * 14 + [vp]),
     "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
@@ -62,12 +62,13 @@ class ChainStep(C.Structure):
     """``ScannChainStep`` of include/scann_b200.h (one step of ``scann_dense_chain``)."""
     _fields_ = ([("A", vp * 3), ("W", vp * 3)] +
                 [(n, vp) for n in ("bias", "resid", "pre_in", "pre_out", "gamma", "beta", "dgamma", "dbeta", "C", "C2",
-                                   "cnt", "np_ctx", "np_out")] +
-                [(n, ci) for n in ("lda", "ldres", "ldpre", "ldc", "ldc2", "kblk", "mode", "to_image")])
+                                   "cnt", "np_ctx", "np_out", "drop")] +
+                [(n, ci) for n in ("lda", "ldres", "ldpre", "ldc", "ldc2", "kblk", "mode", "to_image", "drop_site", "pad")])
 
 
 def chain_step(A=(), W=(), bias=0, resid=0, ldres=128, pre_in=0, pre_out=0, ldpre=128, gamma=0, beta=0, dgamma=0,
-               dbeta=0, C_=0, ldc=128, C2=0, ldc2=128, cnt=0, np_ctx=0, np_out=0, lda=128, mode=0, to_image=False):
+               dbeta=0, C_=0, ldc=128, C2=0, ldc2=128, cnt=0, np_ctx=0, np_out=0, lda=128, mode=0, to_image=False,
+               drop=0, drop_site=0):
     """Builds one ChainStep from integer device addresses (0 = NULL).  ``A`` empty: the operand is the image
     left in shared memory by the previous step."""
     st = ChainStep()
@@ -78,10 +79,10 @@ def chain_step(A=(), W=(), bias=0, resid=0, ldres=128, pre_in=0, pre_out=0, ldpr
     st.kblk = len(W)
     for name, val in (("bias", bias), ("resid", resid), ("pre_in", pre_in), ("pre_out", pre_out), ("gamma", gamma),
                       ("beta", beta), ("dgamma", dgamma), ("dbeta", dbeta), ("C", C_), ("C2", C2), ("cnt", cnt),
-                      ("np_ctx", np_ctx), ("np_out", np_out)):
+                      ("np_ctx", np_ctx), ("np_out", np_out), ("drop", drop)):
         setattr(st, name, val or None)
     st.lda, st.ldres, st.ldpre, st.ldc, st.ldc2 = lda, ldres, ldpre, ldc, ldc2
-    st.mode, st.to_image = mode, 1 if to_image else 0
+    st.mode, st.to_image, st.drop_site, st.pad = mode, 1 if to_image else 0, drop_site, 0
     return st
 
 

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int32_t* __restric
                                                         const float* __restrict__ emb, const float* __restrict__ Wr,
                                                         const float* __restrict__ br, const float* __restrict__ We,
                                                         const float* __restrict__ be, float* __restrict__ t0,
-                                                        float* __restrict__ x0, int32_t* __restrict__ status) {
+                                                        float* __restrict__ x0, int32_t* __restrict__ status,
+                                                        const ScannDropCtl* __restrict__ drop) {
     extern __shared__ float s_cat[];   // [EMB_ROWS][Kin]
     const int Kin = E + (ring ? 10 : 0);
     const int r0 = blockIdx.x * EMB_ROWS;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int32_t* __restric
         int r = r0 + i;
         if (r < R) {
             if (t0) t0[(size_t)r * SCANN_D + n] = acc[i];
-            x0[(size_t)r * SCANN_D + n] = swish_f(acc[i]);
+            x0[(size_t)r * SCANN_D + n] = swish_f(acc[i]) * drop_mult(drop, 0u, (uint32_t)r * SCANN_D + n);
         }
     }
 }
@@ -64,14 +65,15 @@ __global__ void __launch_bounds__(128) embed_bwd_gather_kernel(const int32_t* __
                                                                const float* __restrict__ ring, int R, int n_atoms,
                                                                const float* __restrict__ t0,
                                                                const float* __restrict__ dx0, float* __restrict__ G,
-                                                               int rows_per_cta) {
+                                                               int rows_per_cta, const ScannDropCtl* __restrict__ drop) {
     const int n = threadIdx.x;
     int r0 = blockIdx.x * rows_per_cta, r1 = min(R, r0 + rows_per_cta);
     float all = 0.f, g0 = 0.f, g1 = 0.f;
     float run = 0.f;
     int zrun = -1;
     for (int r = r0; r < r1; ++r) {
-        float d = dx0[(size_t)r * SCANN_D + n] * swish_grad_f(t0[(size_t)r * SCANN_D + n]);
+        float d = dx0[(size_t)r * SCANN_D + n] * drop_mult(drop, 0u, (uint32_t)r * SCANN_D + n) *
+                  swish_grad_f(t0[(size_t)r * SCANN_D + n]);
         int z = atomic[r];
         z = (z < 0 || z >= n_atoms) ? 0 : z;
         if (z != zrun) {
@@ -622,23 +624,25 @@ __global__ void __launch_bounds__(256) transpose_blocks_kernel(const float* __re
 // =============================================================================================
 extern "C" int scann_embed_forward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms,
                                    const float* emb, const float* Wr, const float* br, const float* We,
-                                   const float* be, float* t0, float* x0, int32_t* status, void* stream) {
+                                   const float* be, float* t0, float* x0, int32_t* status, const void* drop_ctl,
+                                   void* stream) {
     int Kin = E + (ring ? 10 : 0);
     size_t smem = (size_t)EMB_ROWS * Kin * sizeof(float);
     scann_launch(embed_fwd_kernel, dim3((R + EMB_ROWS - 1) / EMB_ROWS), dim3(128), smem, stream, atomic, ring, R, E, n_atoms,
-                 emb, Wr, br, We, be, t0, x0, status);
+                 emb, Wr, br, We, be, t0, x0, status, (const ScannDropCtl*)drop_ctl);
     return scann_check_launch("scann_embed_forward");
 }
 
 extern "C" int scann_embed_backward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms,
                                     const float* emb, const float* Wr, const float* br, const float* We,
                                     const float* t0, const float* dx0, float* G_ws, float* d_emb, float* dWr,
-                                    float* dbr, float* dWe, float* dbe, void* stream) {
+                                    float* dbr, float* dWe, float* dbe, const void* drop_ctl, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(G_ws, 0, (size_t)(n_atoms + 3) * SCANN_D * sizeof(float), st);
     int rows_per_cta = 32;
     embed_bwd_gather_kernel<<<(R + rows_per_cta - 1) / rows_per_cta, 128, 0, st>>>(atomic, ring, R, n_atoms, t0, dx0,
-                                                                                  G_ws, rows_per_cta);
+                                                                                  G_ws, rows_per_cta,
+                                                                                  (const ScannDropCtl*)drop_ctl);
     embed_bwd_final_kernel<<<64, 128, 0, st>>>(E, n_atoms, ring ? 1 : 0, emb, Wr, br, We, G_ws, d_emb, dWr, dbr, dWe,
                                                dbe);
     return scann_check_launch("scann_embed_backward");

@@ -45,10 +45,14 @@ struct ChainStep {
     const int32_t* cnt;     // no-pair fix-up (nullable): rows with cnt[r] == 0 get np_ctx[r] = V, np_out[r] = LN(V)
     float* np_ctx;          // [R,128] nullable
     float* np_out;          // [R,128]
+    const ScannDropCtl* drop;   // nullable.  modes 0-3: (sum + bias) is multiplied by the dropout mask of `drop_site`
+                                // before the residual is added.  mode 4: C <- out, C2 and the image <- out * mask.
     int lda, ldres, ldpre, ldc, ldc2;
     int kblk;               // 1..3
     int mode;               // 0 none | 1 swish | 2 * swish'(pre_in) | 3 LayerNorm | 4 LayerNorm backward
     int to_image;           // the output becomes the next step's operand
+    int drop_site;          // dropout site id (mask index = row * 128 + column)
+    int pad;
 };
 struct ChainArgs {
     int nsteps, R;
@@ -239,8 +243,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                     rv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (st.resid && ok) rv = ld4(st.resid + (size_t)r * st.ldres + c0);
                 }
-                v[it][0] = acc.x + bias[it].x + rv.x; v[it][1] = acc.y + bias[it].y + rv.y;
-                v[it][2] = acc.z + bias[it].z + rv.z; v[it][3] = acc.w + bias[it].w + rv.w;
+                float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
+                if (st.drop && mode != 4) {
+                    const uint32_t idx = (uint32_t)r * SCANN_D + c0;
+                    d0 = drop_mult(st.drop, st.drop_site, idx); d1 = drop_mult(st.drop, st.drop_site, idx + 1);
+                    d2 = drop_mult(st.drop, st.drop_site, idx + 2); d3 = drop_mult(st.drop, st.drop_site, idx + 3);
+                }
+                v[it][0] = (acc.x + bias[it].x) * d0 + rv.x; v[it][1] = (acc.y + bias[it].y) * d1 + rv.y;
+                v[it][2] = (acc.z + bias[it].z) * d2 + rv.z; v[it][3] = (acc.w + bias[it].w) * d3 + rv.w;
             }
             if (mode == 1) {
 #pragma unroll
@@ -335,13 +345,24 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
 #pragma unroll
                     for (int q = 0; q < 4; ++q) v[it][q] = inv * (v[it][q] - t1 - x[it][q] * t2);
             }
-            if (ok) {
+            if (ok && st.C) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    st4(st.C + (size_t)r * st.ldc + (l8 + 8 * it) * 4, make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
+            }
+            if (mode == 4 && st.drop) {
+                // gradient through the dropout that follows the Dense of the next (transposed) step
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
-                    const float4 o = make_float4(v[it][0], v[it][1], v[it][2], v[it][3]);
-                    if (st.C) st4(st.C + (size_t)r * st.ldc + (l8 + 8 * it) * 4, o);
-                    if (st.C2) st4(st.C2 + (size_t)r * st.ldc2 + (l8 + 8 * it) * 4, o);
+                    const uint32_t idx = (uint32_t)r * SCANN_D + (l8 + 8 * it) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[it][q] *= drop_mult(st.drop, st.drop_site, idx + q);
                 }
+            }
+            if (ok && st.C2) {
+#pragma unroll
+                for (int it = 0; it < 4; ++it)
+                    st4(st.C2 + (size_t)r * st.ldc2 + (l8 + 8 * it) * 4, make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
             }
             if (st.to_image) {
 #pragma unroll

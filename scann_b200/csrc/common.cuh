@@ -53,6 +53,26 @@ static inline void scann_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, s
 #define SCANN_ERR_BAD_ATOMIC 4      // atomic number outside the embedding table
 #define SCANN_ERR_BAD_NEIGHBOR 8    // neighbour index outside [0, M)
 
+// ---- training-mode Dropout (keras.layers.Dropout: scann_model.py:374 rate 0.1, attention.py:29 rate 0.1) -----
+// Counter-based: the keep decision of element `idx` of dropout site `site` is a hash of (seed, site, idx), so the
+// forward and backward kernels regenerate the same mask without storing it, and a test can rebuild it on the
+// host (scann_b200/dropout.py).  Kept elements are scaled by 1/(1-rate) (inverted dropout, as Keras does).
+// The control block lives in device memory (refreshed by the host before every step, so that a captured CUDA
+// graph sees a new seed on every replay): {seed, threshold = rate * 2^32, float bits of 1/(1-rate), enabled}.
+struct ScannDropCtl { uint32_t seed, threshold, scale_bits, enabled; };
+__device__ __forceinline__ uint32_t drop_hash(uint32_t seed, uint32_t site, uint32_t idx) {
+    uint32_t x = idx * 0x9E3779B1u ^ (seed + site * 0x85EBCA6Bu);
+    x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+    return x;
+}
+// multiplier of element idx: 0 or 1/(1-rate); 1 when ctl is NULL or disabled
+__device__ __forceinline__ float drop_mult(const ScannDropCtl* ctl, uint32_t site, uint32_t idx) {
+    if (!ctl) return 1.0f;
+    const ScannDropCtl c = *ctl;
+    if (!c.enabled) return 1.0f;
+    return drop_hash(c.seed, site, idx) >= c.threshold ? __uint_as_float(c.scale_bits) : 0.0f;
+}
+
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float swish_f(float x) { return x * sigmoid_f(x); }
 // d/dx [x * sigmoid(x)] = s * (1 + x * (1 - s))

@@ -68,8 +68,15 @@ class Engine:
         self.grad_out = torch.zeros(n, dtype=torch.float32, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.adam_scalars = torch.zeros(8, dtype=torch.float32, device=dev)
-        self._adam_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # [0..7] optimiser scalars, [8..11] dropout control block (ScannDropCtl: seed, threshold, scale bits, enabled)
+        self.adam_scalars = torch.zeros(16, dtype=torch.float32, device=dev)
+        self._adam_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        # training-mode Dropout (rate 0.1 after dense_embed and in every ResidualNorm): Keras applies it inside
+        # fit(); the facade switches it on for fit / train_on_batch, direct engine users opt in
+        self.train_dropout = os.environ.get("SCANN_DROPOUT", "0") == "1"
+        self.dropout_rate = 0.1
+        self.dropout_seed = seed
+        self.last_drop_seed = 0
         self._adam_ev = None
         self.step_count = 0
         # RBF centres: np.linspace(0, gaussian_d, 20) / np.linspace(0, 2*pi, 20), float32 (scann_model.py:378,384)
@@ -337,7 +344,7 @@ class Engine:
             # backward temporaries
             for k in ("dx", "d_h", "d_ctx", "d_ta"):
                 ws[k] = torch.empty(R, D, **f)
-            for k in ("d_v2", "d_t1", "dq"):                 # read by the side-stream weight-gradient kernels
+            for k in ("d_v2", "d_v2m", "d_t1", "dq"):        # read by the weight-gradient kernels
                 ws[k] = [torch.empty(R, D, **f) for _ in range(L)]
             ws["scat_all"] = torch.empty(L, 3, R, D, **f)    # s_pre, t_scatter, dx_scatter per layer, zeroed once
             ws["scat"] = [ws["scat_all"][l] for l in range(L)]
@@ -391,7 +398,8 @@ class Engine:
                                       self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
                                       self.w("extra_embed/bias") if ring else 0,
                                       self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
-                                      _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status), st), "embed_forward")
+                                      _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status),
+                                      _p(self.adam_scalars, 8) if training else 0, st), "embed_forward")
         self.launches += 1
         self._pdl(True)
         if sp.g_update and "geom_init" not in self._skip:
@@ -562,7 +570,8 @@ class Engine:
                 steps.append(chain_step(W=[self.w(f"{rn}/dense_1/kernel")], bias=self.w(f"{rn}/dense_1/bias"),
                                         resid=_p(h), mode=3, pre_out=_p(ws["v2"][l]) if training else 0,
                                         gamma=self.w(f"{rn}/layer_norm/gamma"), beta=self.w(f"{rn}/layer_norm/beta"),
-                                        C_=_p(x_out), to_image=True))
+                                        C_=_p(x_out), to_image=True,
+                                        drop=_p(self.adam_scalars, 8) if training else 0, drop_site=1 + l))
                 src = None
             if l + 1 < L:
                 steps += proj_steps(l + 1, src)
@@ -743,7 +752,7 @@ class Engine:
                                        self.w("dense_embed/kernel"), _p(ws["t0"]), _p(dx), _p(ws["G"]),
                                        self.gw("embed_atom/embeddings"), self.gw("extra_embed/kernel") if ring else 0,
                                        self.gw("extra_embed/bias") if ring else 0, self.gw("dense_embed/kernel"),
-                                       self.gw("dense_embed/bias"), st), "embed_backward")
+                                       self.gw("dense_embed/bias"), _p(self.adam_scalars, 8), st), "embed_backward")
         self.launches += 4
         if side is not main:             # join: the optimiser needs every weight gradient
             ev = torch.cuda.Event()
@@ -771,9 +780,12 @@ class Engine:
                 return [chain_step(**head, **la_ln)]
             d_v2, d_t1 = ws["d_v2"][l], ws["d_t1"][l]
             return [
+                # d_v2 (residual branch) and d_v2 * dropout mask (gradient of the dense_1 output, also the operand
+                # of the next step and of the dense_1 weight gradient)
                 chain_step(**head, mode=4, pre_in=_p(ws["v2"][l]), gamma=self.w(f"{rn}/layer_norm/gamma"),
                            dgamma=self.gw(f"{rn}/layer_norm/gamma"), dbeta=self.gw(f"{rn}/layer_norm/beta"),
-                           C_=_p(d_v2), to_image=True),
+                           C_=_p(d_v2), C2=_p(ws["d_v2m"][l]), to_image=True,
+                           drop=_p(self.adam_scalars, 8), drop_site=1 + l),
                 chain_step(W=[self.wT(f"{rn}/dense_1/kernel")], mode=2, pre_in=_p(ws["t1"][l]), C_=_p(d_t1), to_image=True),
                 chain_step(W=[self.wT(f"{rn}/dense/kernel")], resid=_p(d_v2), **la_ln),
             ]
@@ -847,7 +859,7 @@ class Engine:
                                             self.gw(f"{la}/key/kernel"), self.gw(fg, D * D), sst), "la_wpart_reduce")
             self.launches += 3
             if sp.use_attn_norm:
-                wgrad([_p(ws["h1"][l])], D, [_p(d_v2)], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
+                wgrad([_p(ws["h1"][l])], D, [_p(ws["d_v2m"][l])], D, 1, 1, R, [self.gw(f"{rn}/dense_1/kernel")],
                       [self.gw(f"{rn}/dense_1/bias")])
                 wgrad([_p(ws["h"][l])], D, [_p(d_t1)], D, 1, 1, R, [self.gw(f"{rn}/dense/kernel")],
                       [self.gw(f"{rn}/dense/bias")])
@@ -896,7 +908,7 @@ class Engine:
             else:
                 add(_p(ws["gsave"][l]), _p(ws["kk"][l]), self.gw(f"{la}/key/kernel"), xg=_p(ws["x"][l]), rows=-1)
             if sp.use_attn_norm:
-                add(_p(ws["h1"][l]), _p(ws["d_v2"][l]), self.gw(f"{rn}/dense_1/kernel"), self.gw(f"{rn}/dense_1/bias"))
+                add(_p(ws["h1"][l]), _p(ws["d_v2m"][l]), self.gw(f"{rn}/dense_1/kernel"), self.gw(f"{rn}/dense_1/bias"))
                 add(_p(ws["h"][l]), _p(ws["d_t1"][l]), self.gw(f"{rn}/dense/kernel"), self.gw(f"{rn}/dense/bias"))
             if sp.g_update:
                 add(_p(ws["x"][l]), _p(scat[0]), self.gw(fg, 0), self.gw(f"{la}/filter_geo/bias"))
@@ -924,6 +936,12 @@ class Engine:
         if self._adam_ev is not None:
             self._adam_ev.synchronize()
         h[0], h[1], h[2], h[3], h[4], h[5] = alpha, b1, b2, eps, L2_COEF, float(batch_global)
+        hi = h.numpy().view(np.uint32)
+        self.last_drop_seed = (self.dropout_seed * 2654435761 + 40503 * t) & 0xFFFFFFFF
+        hi[8] = self.last_drop_seed
+        hi[9] = min(int(self.dropout_rate * 4294967296.0), 0xFFFFFFFF)
+        hi[10] = np.float32(1.0 / (1.0 - self.dropout_rate)).view(np.uint32)
+        hi[11] = 1 if self.train_dropout else 0
         self.adam_scalars.copy_(h, non_blocking=True)
         self._adam_ev = torch.cuda.Event()
         self._adam_ev.record(torch.cuda.current_stream(self.device))
@@ -944,6 +962,8 @@ class Engine:
         The kernel sequence of a shape class is captured once into a CUDA graph and replayed."""
         if target is not None and target is not b.target:
             self.set_target(b, target)
+        if self.train_dropout and not (self.use_chain and self.tc_la_bwd):
+            raise NotImplementedError("training-mode Dropout needs the chained tensor-core engine (SCANN_CHAIN=1)")
         self._set_adam(lr, batch_global or b.B)
         key = ("train", replan, apply, want_grads, allreduce is not None)
         if not self.use_graphs or self.prof is not None:

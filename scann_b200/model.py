@@ -59,6 +59,9 @@ class ScannKerasModel:
         self.world_size = 1
         self._y_host = None
         self.last_e2e_bytes = (0, 0)
+        # Keras applies the Dropout layers (rate 0.1 after dense_embed and in every ResidualNorm,
+        # scann_model.py:374, attention.py:29) whenever fit / train_on_batch run the graph with training=True
+        self.dropout = True
 
     # ---- inference -------------------------------------------------------------------------
     def predict(self, inputs: Dict[str, object], batch_size: Optional[int] = None, verbose: int = 0):
@@ -94,6 +97,7 @@ class ScannKerasModel:
     def train_on_batch(self, inputs: Dict[str, object], y_true, return_dict: bool = False):
         """One Keras ``train_step``: returns the loss (RMSE + l2 penalties) of the batch."""
         eng = self.engine
+        eng.train_dropout = bool(self.dropout) and eng.use_chain and eng.use_wgrad_batch
         b = eng.load_batch(inputs, plan=False)
         batch_global = b.B * self.world_size
         eng.train_step(b, y_true, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global, replan=True)

@@ -256,6 +256,48 @@ def test_scann_without_geometry_update_and_ring_features():
     assert abs(lv[0] - float(loss)) <= 1e-5 * abs(float(loss))
 
 
+def test_train_step_with_dropout_matches_oracle_with_the_same_masks():
+    """Training-mode Dropout (rate 0.1 after dense_embed, scann_model.py:374, and in every ResidualNorm,
+    attention.py:29): the device masks are a hash of (seed, site, element); the host replica rebuilds them and
+    injects them into the oracle, whose loss and gradients must then agree."""
+    from scann_b200 import dropout as dr
+    spec, lay, arena = small("qm9", L=3, seed=7)
+    inputs, target = make_batch("qm9", 5, B=12)
+    eng = engine_for(spec, arena)
+    eng.train_dropout = True
+    b = eng.load_batch(inputs)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    seed, rate = eng.last_drop_seed, eng.dropout_rate
+    B, M = b.B, b.M
+    masks = {"dense_embed": torch.from_numpy(dr.drop_mask(seed, dr.SITE_DENSE_EMBED, b.R, rate).astype(np.float64)
+                                             .reshape(B, M, 128))}
+    for l in range(spec.n_attention):
+        name = "residual_norm" if l == 0 else f"residual_norm_{l}"
+        masks[name] = torch.from_numpy(dr.drop_mask(seed, dr.site_residual_norm(l), b.R, rate).astype(np.float64)
+                                       .reshape(B, M, 128))
+    kept = float(masks["dense_embed"].gt(0).double().mean())
+    assert 0.88 < kept < 0.92                                   # rate 0.1
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, y_ref, _, grads = O.loss_and_grads(w, inputs, target, l2n, drop_masks=masks, **oracle_kwargs(spec))
+    # the masks matter: without them the oracle's loss differs
+    loss_nodrop, _, _, _ = O.loss_and_grads(w, inputs, target, l2n, **oracle_kwargs(spec))
+    lv = eng.loss_value(b.B).cpu().numpy()
+    assert abs(lv[0] - loss) <= 1e-5 * abs(loss) < abs(loss_nodrop - loss)
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+    # a second step draws different masks
+    eng.step_count += 1
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    assert eng.last_drop_seed != seed
+
+
 def test_malformed_input_is_reported():
     from scann_b200._abi import ScannAbiError
     spec, lay, arena = small("qm9", L=1)
