@@ -152,14 +152,72 @@ class ScannKerasModel:
             raise ValueError(f"expected {len(self.layout.entries)} arrays, got {len(weights)}")
         self.engine.set_params(self.layout.from_dict({e.name: w for e, w in zip(self.layout, weights)}))
 
+    # ---- weights: Keras legacy HDF5 (.h5, what the reference's model.save / ModelCheckpoint / load_model use,
+    #      scann_model.py:79-96,223-230) or .npz with the same names -------------------------------------------
+    def _keras_layers(self):
+        """[(layer name, [(weight name ":0", array)])] in ParamLayout (= Keras layer / weight) order."""
+        d = self.layout.to_dict(self.engine.get_params())
+        layers, index = [], {}
+        for e in self.layout:
+            lname = e.name.split("/")[0]
+            if lname not in index:
+                index[lname] = len(layers)
+                layers.append((lname, []))
+            layers[index[lname]][1].append((e.name + ":0", d[e.name]))
+        return layers
+
     def save_weights(self, path: str) -> None:
+        if path.endswith((".h5", ".hdf5", ".keras")):
+            from . import h5lite
+            h5lite.save_keras_weights(path, self._keras_layers(), full_model=False)
+            return
         d = self.layout.to_dict(self.engine.get_params())
         np.savez(path, **{k.replace("/", "__"): v for k, v in d.items()})
 
+    def save(self, path: str) -> None:
+        """``model.save("...h5")``: full-model layout (weights under /model_weights)."""
+        if path.endswith((".h5", ".hdf5", ".keras")):
+            from . import h5lite
+            h5lite.save_keras_weights(path, self._keras_layers(), full_model=True)
+        else:
+            self.save_weights(path)
+
     def load_weights(self, path: str) -> None:
+        if path.endswith((".h5", ".hdf5", ".keras")):
+            self.engine.set_params(self.layout.from_dict(self._from_keras_h5(path)))
+            return
         with np.load(path) as z:
             d = {k.replace("__", "/"): z[k] for k in z.files}
         self.engine.set_params(self.layout.from_dict(d))
+
+    def _from_keras_h5(self, path: str) -> Dict[str, np.ndarray]:
+        """Maps a Keras-2.10 HDF5 file onto the parameter layout the way ``keras.Model.load_weights`` does:
+        layers are matched by name (the top-level layer names of create_model are explicit or Keras' automatic
+        ``local_attention_<i>`` / ``residual_norm_<i>``), the weights of a layer by ORDER (= creation order of the
+        layer's variables), with every shape checked; layers without weights (Input, Lambda, Dropout, ...) are
+        skipped."""
+        from . import h5lite
+        per_layer = {}
+        for e in self.layout:
+            per_layer.setdefault(e.name.split("/")[0], []).append(e)
+        out, seen = {}, set()
+        for lname, ws in h5lite.load_keras_weights(path):
+            if not ws:
+                continue
+            if lname not in per_layer:
+                raise ValueError(f"{path}: layer {lname!r} with weights is not part of this model configuration")
+            ents = per_layer[lname]
+            if len(ws) != len(ents):
+                raise ValueError(f"{path}: layer {lname!r} has {len(ws)} weights, the model expects {len(ents)}")
+            for (wname, arr), e in zip(ws, ents):
+                if tuple(arr.shape) != e.shape:
+                    raise ValueError(f"{path}: {lname}/{wname} has shape {tuple(arr.shape)}, expected {e.shape} ({e.name})")
+                out[e.name] = np.asarray(arr, np.float32)
+            seen.add(lname)
+        missing = [l for l in per_layer if l not in seen]
+        if missing:
+            raise ValueError(f"{path}: no weights for layers {missing}")
+        return out
 
     def count_params(self) -> int:
         return self.layout.n_params

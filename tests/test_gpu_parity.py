@@ -400,6 +400,13 @@ def test_public_api_predict_and_train(tmp_path):
     assert rel(out[0], y_ref) <= TOL_OUT and rel(out[1], ga_ref) <= TOL_OUT
     yd, gad = infer.predict_data(inputs)
     np.testing.assert_allclose(yd, out[0] * 2.0 + 0.5, rtol=1e-6)
+    # Keras legacy HDF5 (what model.save / ModelCheckpoint write and load_model reads in the reference)
+    h5 = str(tmp_path / "model.h5")
+    trainer.model.save(h5)
+    infer_h5 = SCANN(cfg, pretrained=h5, mode="infer")
+    out_h5 = infer_h5.model.predict(inputs)
+    assert np.array_equal(out_h5[0], out[0]) and np.array_equal(out_h5[1], out[1])
+    assert np.array_equal(infer_h5.model.engine.get_params(), trainer.model.engine.get_params())
 
 
 # ----------------------------------------------------------------------------- layer-level drop-ins
