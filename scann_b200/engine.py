@@ -238,16 +238,26 @@ class Engine:
                 t = t != 0
             dst.copy_(t.reshape(dst.shape), non_blocking=True)
 
-        put(b.atomic, inputs["atomic"], "atomic")
-        put(b.atom_mask, inputs["atom_mask"], "atom_mask")
-        put(b.nbr, nb, "neighbors")
-        put(b.nmask, nmask_in, "neighbor_mask")
-        put(b.weight, inputs["neighbor_weight"], "neighbor_weight")
-        put(b.dist, inputs["neighbor_distance"], "neighbor_distance")
+        items = [("atomic", inputs["atomic"]), ("atom_mask", inputs["atom_mask"]), ("nbr", nb), ("nmask", nmask_in),
+                 ("weight", inputs["neighbor_weight"]), ("dist", inputs["neighbor_distance"])]
         if self.spec.use_ring:
-            if b.ring is None:
-                b.ring = torch.zeros(b.R * 2, dtype=torch.float32, device=dev)
-            put(b.ring, inputs["ring_aromatic"], "ring_aromatic")
+            items.append(("ring", inputs["ring_aromatic"]))
+        if all(isinstance(x, np.ndarray) for _, x in items):
+            # host arrays: fill the pinned mirror now, one asynchronous copy later (_flush_host)
+            self._wait_pin(b)
+            for name, x in items:
+                dst = b.pin_np[name]
+                a = x.view(np.uint8) if x.dtype == np.bool_ else x
+                if dst.dtype == np.uint8 and a.dtype != np.uint8:
+                    a = a != 0
+                if a.size != dst.size:
+                    raise ValueError(f"{name}: expected {dst.size} elements, got {a.size}")
+                np.copyto(dst, a.reshape(dst.shape), casting="unsafe")
+                b.h2d_bytes += x.nbytes
+            b.host_dirty = True
+        else:
+            for name, x in items:
+                put(getattr(b, name), x, name)
         if plan:
             self._plan(b)
         return b
@@ -260,14 +270,25 @@ class Engine:
         rows = b.rows = tile_cap * stride
         i32 = dict(dtype=torch.int32, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        b.atomic = torch.zeros(b.R, **i32)
-        b.atom_mask = torch.zeros(b.R, dtype=torch.uint8, device=dev)
-        b.nbr = torch.zeros(b.R * N, **i32)
-        b.nmask = torch.zeros(b.R * N, dtype=torch.uint8, device=dev)
-        b.weight = torch.zeros(b.R * N, **f32)
-        b.dist = torch.zeros(b.R * N, **f32)
-        b.target = torch.zeros(B, **f32)
+        # every host-provided array lives in ONE device blob mirrored by ONE pinned host blob: a step's inputs
+        # (and its targets) travel in a single host->device copy instead of seven
+        fields = [("atomic", torch.int32, b.R), ("atom_mask", torch.uint8, b.R), ("nbr", torch.int32, b.R * N),
+                  ("nmask", torch.uint8, b.R * N), ("weight", torch.float32, b.R * N), ("dist", torch.float32, b.R * N),
+                  ("target", torch.float32, B)]
+        if self.spec.use_ring:
+            fields.append(("ring", torch.float32, b.R * 2))
+        off, offs = 0, {}
+        for name, dt, n in fields:
+            offs[name] = off
+            off += (n * torch.empty((), dtype=dt).element_size() + 255) // 256 * 256
+        b.blob = torch.zeros(off, dtype=torch.uint8, device=dev)
+        b.blob_pin = torch.zeros(off, dtype=torch.uint8).pin_memory()
+        b.pin_np, b.pin_event, b.host_dirty = {}, None, False
         b.ring = None
+        for name, dt, n in fields:
+            nb = n * torch.empty((), dtype=dt).element_size()
+            setattr(b, name, b.blob[offs[name]:offs[name] + nb].view(dt))
+            b.pin_np[name] = b.blob_pin[offs[name]:offs[name] + nb].view(dt).numpy()
         b.cnt = torch.empty(b.R, **i32)
         b.rowptr = torch.empty(b.R, **i32)
         b.tile_a0 = torch.empty(tile_cap, **i32)
@@ -284,25 +305,38 @@ class Engine:
 
     def set_target(self, b: Batch, y_true) -> None:
         if isinstance(y_true, torch.Tensor):
+            self._flush_host(b)         # the blob copy would overwrite the target region
             b.target.copy_(y_true.reshape(-1), non_blocking=True)
             return
-        a = np.ascontiguousarray(np.asarray(y_true, np.float32).reshape(-1))
+        a = np.asarray(y_true, np.float32).reshape(-1)
         if a.size != b.B:
             raise ValueError("target must have one value per structure")
-        key = (b.B, b.M, b.N, b.tile_cap, b.tile_rows, b.stride)
-        slot = self._pinned.get(("target", key))
-        if slot is None:
-            slot = self._pinned[("target", key)] = [torch.empty(b.B, dtype=torch.float32).pin_memory(), None]
-        pin, ev = slot
-        if ev is not None:
-            ev.synchronize()
-        pin.numpy()[...] = a
-        b.target.copy_(pin, non_blocking=True)
-        slot[1] = torch.cuda.Event()
-        slot[1].record(torch.cuda.current_stream(self.device))
+        if not b.host_dirty:
+            self._wait_pin(b)
+        b.pin_np["target"][...] = a
         b.h2d_bytes += a.nbytes
+        if b.host_dirty:
+            return                      # travels with the inputs in the single blob copy
+        b.target.copy_(torch.from_numpy(b.pin_np["target"]), non_blocking=True)
+        b.pin_event = torch.cuda.Event()
+        b.pin_event.record(torch.cuda.current_stream(self.device))
+
+    def _wait_pin(self, b: Batch) -> None:
+        """The previous asynchronous copy out of the pinned mirror has finished (it may be overwritten)."""
+        if b.pin_event is not None:
+            b.pin_event.synchronize()
+            b.pin_event = None
+
+    def _flush_host(self, b: Batch) -> None:
+        """One host->device copy of everything load_batch / set_target staged in the pinned mirror."""
+        if b.host_dirty:
+            b.blob.copy_(b.blob_pin, non_blocking=True)
+            b.pin_event = torch.cuda.Event()
+            b.pin_event.record(torch.cuda.current_stream(self.device))
+            b.host_dirty = False
 
     def _plan(self, b: Batch) -> None:
+        self._flush_host(b)
         check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
                                    b.tile_rows, b.stride, _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
@@ -385,6 +419,7 @@ class Engine:
     def forward(self, b: Batch, training: bool = False, attn_out: Optional[list] = None):
         """Runs the whole graph; returns (y[B], ga[B*M]) device tensors (views of the workspace)."""
         sp, st = self.spec, self._stream()
+        self._flush_host(b)
         ws = self._workspace(b, training)
         L, R = sp.n_attention, b.R
         xs, gs = ws["x"], ws["g"]
@@ -965,6 +1000,7 @@ class Engine:
         if self.train_dropout and not (self.use_chain and self.tc_la_bwd):
             raise NotImplementedError("training-mode Dropout needs the chained tensor-core engine (SCANN_CHAIN=1)")
         self._set_adam(lr, batch_global or b.B)
+        self._flush_host(b)
         key = ("train", replan, apply, want_grads, allreduce is not None)
         if not self.use_graphs or self.prof is not None:
             self._train_body(b, allreduce, apply, want_grads, replan)
@@ -1015,6 +1051,7 @@ class Engine:
     def predict_step(self, b: Batch, replan: bool = False):
         """Inference forward (plan + graph of kernels) -> (y[B], ga[B*M]) device tensors."""
         key = ("infer", replan)
+        self._flush_host(b)
         if not self.use_graphs or self.prof is not None:
             if replan:
                 self._plan(b)
