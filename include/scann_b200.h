@@ -51,14 +51,17 @@ int scann_set_pdl(int on);
  * padded arrays of DataIterator.__getitem__ (scann/utils/datagenerator.py:80-101):
  * neighbor_mask [B,M,N] uint8, neighbors [B,M,N] int32, dist/weight [B,M,N] fp32.
  * Outputs: cnt[R], rowptr[R], tile_a0/tile_a1[tile_cap] (atom range of each tile), ntiles[1],
- * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*128].  scratch: >= 2*ceil(R/128) int32.
- * tile_rows (<= 128): greedy fill limit per tile, chosen by the caller to balance SM waves. */
+ * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*tile_stride].  scratch: >= 4*ceil(R/128) int32 (2* without valid_rows).
+ * tile_rows (<= tile_stride): greedy fill limit per tile, chosen by the caller to balance SM waves.
+ * valid_rows, valid_j [tile_cap*tile_stride] / nvalid [1] (nullable): compact list of the valid pair rows in tile
+ * order and the neighbour atom row of each, for
+ * consumers that only reduce over pairs (scann_wgrad_batch_tc) and should not pay for padding rows. */
 int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
                      const float* weight, int B, int M, int N, int tile_cap, int tile_rows, int tile_stride,
                      int32_t* cnt, int32_t* rowptr,
                      int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles, int32_t* pair_c, int32_t* pair_j,
-                     int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* scratch, int scratch_len,
-                     int32_t* status, void* stream);
+                     int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* valid_rows, int32_t* valid_j,
+                     int32_t* nvalid, int32_t* scratch, int scratch_len, int32_t* status, void* stream);
 
 /* ---- input embedding: Embedding + (extra_embed) + dense_embed swish -----------------------
  * scann/models/scann_model.py:361-374.  ring may be NULL (use_ring False). t0 (pre-activation,
@@ -223,7 +226,8 @@ int scann_la_wpart_reduce(const float* wpart, const int32_t* ntiles, int grid, i
  * dW += X^T Y for a list of problems (TF autodiff of every Dense / einsum kernel of the graph inside keras fit:
  * scann/layers/attention.py:118-216,25-40, scann/models/scann_model.py:424-447).  rows >= 0: per-atom problem
  * over that many rows; rows < 0: per-pair problem over the tile-padded pair rows (ntiles * tile_stride rows, rows
- * with pair_c < 0 skipped), with X rows multiplied by xg[pair_j[row]] when xg != NULL.  db (nullable) += column
+ * with pair_c < 0 skipped; or, when the plan's compact list valid_rows / nvalid is given, exactly the valid rows),
+ * with X rows multiplied by xg[pair_j[row]] when xg != NULL.  db (nullable) += column
  * sums of Y (bias gradient).  `problems` is a DEVICE array; results are accumulated with atomics. */
 typedef struct ScannWgradProblem {
     const float* X;
@@ -236,7 +240,8 @@ typedef struct ScannWgradProblem {
     int pad;
 } ScannWgradProblem;
 int scann_wgrad_batch_tc(int grid, const ScannWgradProblem* problems, int nprob, const int32_t* ntiles, int tile_stride,
-                         const int32_t* pair_c, const int32_t* pair_j, void* stream);
+                         const int32_t* pair_c, const int32_t* pair_j, const int32_t* valid_rows, const int32_t* valid_j,
+                         const int32_t* nvalid, void* stream);
 
 /* ---- global attention + property head ---------------------------------------------------------
  * GlobalAttention.call (scann/layers/attention.py:267-318) + bf_property / predict_property / mrelu

@@ -23,7 +23,7 @@ PROTOTYPES = {
     "scann_device_sm_count": (ci, []),
     "scann_device_cc": (ci, []),
     "scann_set_pdl": (ci, [ci]),
-    "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci] + [vp] * 10 + [vp, ci, vp, vp]),
+    "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci] + [vp] * 13 + [vp, ci, vp, vp]),
     "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp, vp]),
     "scann_embed_backward": (ci, [vp, vp, ci, ci, ci] + [vp] * 12 + [vp, vp]),
     "scann_geom_init_forward": (ci, [vp, ci, ci] + [vp] * 10 + [vp]),
@@ -43,7 +43,7 @@ PROTOTYPES = {
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
     "scann_la_wgrad_tc": (ci, [ci, ci] + [vp] * 9 + [vp]),
-    "scann_wgrad_batch_tc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp]),
+    "scann_wgrad_batch_tc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, ci, vp, vp, vp]),
     "scann_ga_head_forward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_ga_head_backward": (ci, [vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -36,7 +36,8 @@ __global__ void plan_count_kernel(const uint8_t* __restrict__ nmask, const int32
 // One thread per group of PLAN_GSZ consecutive atom rows: greedy first-fit in order.
 // rowptr[r] <- local_tile*128 + offset (group-local); gtiles[g] <- tiles used by the group.
 __global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ngroups, int tile_rows, int tile_stride,
-                                  int32_t* __restrict__ rowptr, int32_t* __restrict__ gtiles) {
+                                  int32_t* __restrict__ rowptr, int32_t* __restrict__ gtiles,
+                                  int32_t* __restrict__ gcount) {
     __shared__ int32_t s_cnt[32 * (PLAN_GSZ + 1)];
     int g0 = blockIdx.x * 32;
     for (int i = threadIdx.x; i < 32 * PLAN_GSZ; i += blockDim.x) {
@@ -48,9 +49,10 @@ __global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ng
     int g = g0 + threadIdx.x;
     if (threadIdx.x >= 32 || g >= ngroups) return;
     int32_t* sc = s_cnt + threadIdx.x * (PLAN_GSZ + 1);
-    int tile = 0, fill = 0, any = 0;
+    int tile = 0, fill = 0, any = 0, pairs = 0;
     for (int a = 0; a < PLAN_GSZ; ++a) {
         int c = sc[a];
+        pairs += c;
         if (c == 0) { sc[a] = -1; continue; }
         if (fill + c > tile_rows && fill > 0) { ++tile; fill = 0; }
         sc[a] = tile * tile_stride + fill;
@@ -58,6 +60,7 @@ __global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ng
         any = 1;
     }
     gtiles[g] = any ? tile + 1 : 0;
+    if (gcount) gcount[g] = pairs;
     __syncwarp();
     for (int a = 0; a < PLAN_GSZ; ++a) {
         int r = g * PLAN_GSZ + a;
@@ -68,23 +71,33 @@ __global__ void plan_group_kernel(const int32_t* __restrict__ cnt, int R, int ng
 // Exclusive scan of gtiles (single CTA) -> gbase ; total -> ntiles.
 __global__ void plan_scan_kernel(const int32_t* __restrict__ gtiles, int ngroups, int tile_cap,
                                  int32_t* __restrict__ gbase, int32_t* __restrict__ ntiles,
-                                 int32_t* __restrict__ status) {
+                                 int32_t* __restrict__ status, const int32_t* __restrict__ gcount,
+                                 int32_t* __restrict__ gcbase, int32_t* __restrict__ nvalid) {
     __shared__ int32_t s_part[1024];
+    __shared__ int32_t s_cpart[1024];
     int per = (ngroups + blockDim.x - 1) / blockDim.x;
     int lo = threadIdx.x * per, hi = min(lo + per, ngroups);
-    int sum = 0;
-    for (int g = lo; g < hi; ++g) sum += gtiles[g];
+    int sum = 0, csum = 0;
+    for (int g = lo; g < hi; ++g) { sum += gtiles[g]; if (gcount) csum += gcount[g]; }
     s_part[threadIdx.x] = sum;
+    s_cpart[threadIdx.x] = csum;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int run = 0;
-        for (int i = 0; i < (int)blockDim.x; ++i) { int v = s_part[i]; s_part[i] = run; run += v; }
-        if (run > tile_cap) { atomicOr(status, SCANN_ERR_TILE_OVERFLOW); run = 0; }
+        int run = 0, crun = 0;
+        for (int i = 0; i < (int)blockDim.x; ++i) {
+            int v = s_part[i]; s_part[i] = run; run += v;
+            int c = s_cpart[i]; s_cpart[i] = crun; crun += c;
+        }
+        if (run > tile_cap) { atomicOr(status, SCANN_ERR_TILE_OVERFLOW); run = 0; crun = 0; }
         *ntiles = run;
+        if (nvalid) *nvalid = crun;
     }
     __syncthreads();
-    int run = s_part[threadIdx.x];
-    for (int g = lo; g < hi; ++g) { gbase[g] = run; run += gtiles[g]; }
+    int run = s_part[threadIdx.x], crun = s_cpart[threadIdx.x];
+    for (int g = lo; g < hi; ++g) {
+        gbase[g] = run; run += gtiles[g];
+        if (gcount) { gcbase[g] = crun; crun += gcount[g]; }
+    }
 }
 
 __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_t* __restrict__ nbr,
@@ -94,10 +107,27 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
                                  int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_a0,
                                  int32_t* __restrict__ tile_a1, int32_t* __restrict__ pair_c,
                                  int32_t* __restrict__ pair_j, int32_t* __restrict__ pair_slot,
-                                 float* __restrict__ pair_d, float* __restrict__ pair_w) {
+                                 float* __restrict__ pair_d, float* __restrict__ pair_w,
+                                 int32_t* __restrict__ valid_rows, int32_t* __restrict__ valid_j,
+                                 const int32_t* __restrict__ gcbase) {
+    // one CTA = one plan group (blockDim = PLAN_GSZ): the compact position of an atom's pairs is the group's base
+    // plus the exclusive prefix of cnt inside the group, so the compact list follows the tile order (sequential
+    // reads for its consumers)
+    __shared__ int32_t s_wsum[PLAN_GSZ / 32];
     int r = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = r < R ? cnt[r] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)(threadIdx.x & 31) >= o) incl += v;
+    }
+    if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbase += s_wsum[w];
+    const int vbase = valid_rows ? gcbase[blockIdx.x] + wbase + incl - c : 0;
     if (r >= R) return;
-    int c = cnt[r];
     if (c == 0 || *ntiles == 0) { rowptr[r] = 0; return; }
     int rp = gbase[r / PLAN_GSZ] * tile_stride + rowptr[r];
     rowptr[r] = rp;
@@ -110,7 +140,9 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
     for (int n = 0; n < N; ++n) {
         if (m[n]) {
             size_t s = (size_t)r * N + n;
-            int p = rp + k++;
+            int p = rp + k;
+            if (valid_rows) { valid_rows[vbase + k] = p; valid_j[vbase + k] = b * M + nbr[s]; }
+            ++k;
             pair_c[p] = r;
             pair_j[p] = b * M + nbr[s];
             pair_slot[p] = (int32_t)s;
@@ -125,7 +157,9 @@ extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* nei
                                 int tile_stride, int32_t* cnt,
                                 int32_t* rowptr, int32_t* tile_a0, int32_t* tile_a1, int32_t* ntiles,
                                 int32_t* pair_c, int32_t* pair_j, int32_t* pair_slot, float* pair_d,
-                                float* pair_w, int32_t* scratch, int scratch_len, int32_t* status, void* stream_) {
+                                float* pair_w, int32_t* valid_rows, int32_t* valid_j, int32_t* nvalid, int32_t* scratch,
+                                int scratch_len,
+                                int32_t* status, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     long long Rll = (long long)B * M;
     if (Rll <= 0 || N <= 0 || Rll * N > 0x7fffffffLL) { scann_set_error("plan: bad shape B=%d M=%d N=%d", B, M, N); return 1; }
@@ -133,19 +167,24 @@ extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* nei
     if (tile_rows < 1 || tile_rows > tile_stride) { scann_set_error("plan: tile_rows must be in 1..tile_stride"); return 1; }
     int R = (int)Rll;
     int ngroups = (R + PLAN_GSZ - 1) / PLAN_GSZ;
-    if (scratch_len < 2 * ngroups) { scann_set_error("plan: scratch too small (%d < %d)", scratch_len, 2 * ngroups); return 1; }
+    if (valid_rows && !valid_j) { scann_set_error("plan: valid_rows needs valid_j"); return 1; }
+    const int need = (valid_rows ? 4 : 2) * ngroups;
+    if (scratch_len < need) { scann_set_error("plan: scratch too small (%d < %d)", scratch_len, need); return 1; }
     int32_t* gtiles = scratch;
     int32_t* gbase = scratch + ngroups;
+    int32_t* gcount = valid_rows ? scratch + 2 * ngroups : nullptr;
+    int32_t* gcbase = valid_rows ? scratch + 3 * ngroups : nullptr;
     size_t rows = (size_t)tile_cap * tile_stride;
     // padding rows are recognised by pair_c < 0; every consumer guards on it, so the other
     // per-pair arrays need no initialisation.  tile_a1 is built with atomicMax.
     cudaMemsetAsync(pair_c, 0xFF, rows * sizeof(int32_t), st);
     cudaMemsetAsync(tile_a1, 0, (size_t)tile_cap * sizeof(int32_t), st);
     plan_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(neighbor_mask, neighbors, R, M, N, cnt, status);
-    plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, tile_rows, tile_stride, rowptr, gtiles);
-    plan_scan_kernel<<<1, 1024, 0, st>>>(gtiles, ngroups, tile_cap, gbase, ntiles, status);
-    plan_fill_kernel<<<(R + 127) / 128, 128, 0, st>>>(neighbor_mask, neighbors, dist, weight, cnt, gbase, ntiles, R, M,
+    plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, tile_rows, tile_stride, rowptr, gtiles, gcount);
+    plan_scan_kernel<<<1, 1024, 0, st>>>(gtiles, ngroups, tile_cap, gbase, ntiles, status, gcount, gcbase,
+                                         valid_rows ? nvalid : nullptr);
+    plan_fill_kernel<<<(R + PLAN_GSZ - 1) / PLAN_GSZ, PLAN_GSZ, 0, st>>>(neighbor_mask, neighbors, dist, weight, cnt, gbase, ntiles, R, M,
                                                      N, tile_stride, rowptr, tile_a0, tile_a1, pair_c, pair_j, pair_slot, pair_d,
-                                                     pair_w);
+                                                     pair_w, valid_rows, valid_j, gcbase);
     return scann_check_launch("scann_plan_build");
 }

@@ -41,6 +41,9 @@ struct WgArgs {
     int stride;
     const int32_t* pair_c;
     const int32_t* pair_j;
+    const int32_t* valid_rows;   // compact list of the valid pair rows (scann_plan_build), nullable
+    const int32_t* valid_j;      // neighbour atom row of each compact entry
+    const int32_t* nvalid;       // its length (device)
 };
 
 __device__ __forceinline__ void wg_split_store(uint8_t* sHi, uint8_t* sLo, uint32_t off, float4 v) {
@@ -86,7 +89,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
     __shared__ int s_units[WG_MAX_PROBLEMS + 1];        // exclusive prefix of units per problem
     __shared__ WgProblem s_prob[WG_MAX_PROBLEMS];       // the problem table (a dependent global load per unit otherwise)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pair_rows = *a.ntiles * a.stride;
+    // pair problems run over the compact list of valid rows when the plan provides it (independent of how
+    // sparsely the tiles are filled), else over all tile slots with the padding rows skipped
+    const int pair_rows = a.valid_rows ? *a.nvalid : *a.ntiles * a.stride;
     for (int i = tid; i < a.nprob * (int)(sizeof(WgProblem) / 8); i += WG_THREADS)
         reinterpret_cast<uint64_t*>(s_prob)[i] = reinterpret_cast<const uint64_t*>(a.prob)[i];
     __syncthreads();
@@ -140,10 +145,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
         for (int i = 0; i < WG_RPW; ++i) {
             const size_t r = rowbase + warp + WG_WARPS * i;
             if (r < (size_t)nrows) {
-                pcn[i] = 0;
+                pcn[i] = (int)r;                        // source row (>= 0) or -1
                 if (pr.rows < 0) {
-                    pcn[i] = a.pair_c[r];
-                    if (pr.xg) pjx[i] = a.pair_j[r];
+                    if (a.valid_rows) {
+                        pcn[i] = a.valid_rows[r];
+                        if (pr.xg) pjx[i] = a.valid_j[r];         // independent of the load above: one round trip
+                    } else {
+                        if (a.pair_c[r] < 0) pcn[i] = -1;
+                        if (pr.xg) pjx[i] = a.pair_j[r];
+                    }
                 }
             }
         }
@@ -157,13 +167,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
         uint8_t* sRawY = sRawX + WG_STAGE;
         while (u >= s_units[pl + 1]) ++pl;
         const WgProblem& pr = s_prob[pl];
-        const size_t rowbase = (size_t)(u - s_units[pl]) * WG_UR;
 #pragma unroll
         for (int i = 0; i < WG_RPW; ++i) {
             const int rr = warp + WG_WARPS * i;
             const bool ok = pcn[i] >= 0;
             pjn[i] = ok ? pjx[i] : 0;
-            const size_t rs = ok ? rowbase + rr : 0;
+            const size_t rs = ok ? (size_t)pcn[i] : 0;
             cp_async16(smem_u32(sRawX) + rr * 512 + lane * 16, pr.X + rs * pr.ldx + lane * 4, ok ? 16 : 0);
             cp_async16(smem_u32(sRawY) + rr * 512 + lane * 16, pr.Y + rs * pr.ldy + lane * 4, ok ? 16 : 0);
         }
@@ -290,7 +299,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
 // problems: DEVICE array of nprob ScannWgradProblem (include/scann_b200.h).  Gradients are accumulated
 // (atomics) into dW / db, which the caller zeroes at the start of the step.
 extern "C" int scann_wgrad_batch_tc(int grid, const void* problems_dev, int nprob, const int32_t* ntiles, int tile_stride,
-                                    const int32_t* pair_c, const int32_t* pair_j, void* stream) {
+                                    const int32_t* pair_c, const int32_t* pair_j, const int32_t* valid_rows,
+                                    const int32_t* valid_j, const int32_t* nvalid, void* stream) {
     if (nprob < 1 || nprob > WG_MAX_PROBLEMS) { scann_set_error("wgrad_batch_tc: nprob must be in 1..%d", WG_MAX_PROBLEMS); return 1; }
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("wgrad_batch_tc: tile_stride must be 64 or 128"); return 1; }
     static bool configured = false;
@@ -300,7 +310,8 @@ extern "C" int scann_wgrad_batch_tc(int grid, const void* problems_dev, int npro
         configured = true;
     }
     if (grid <= 0) return 0;
-    WgArgs a{(const WgProblem*)problems_dev, nprob, ntiles, tile_stride, pair_c, pair_j};
+    WgArgs a{(const WgProblem*)problems_dev, nprob, ntiles, tile_stride, pair_c, pair_j, valid_rows, valid_j,
+             valid_rows ? nvalid : nullptr};
     wgrad_batch_tc_kernel<<<grid, WG_THREADS, WG_SMEM, (cudaStream_t)stream>>>(a);
     return scann_check_launch("scann_wgrad_batch_tc");
 }

@@ -102,9 +102,11 @@ class Engine:
         self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
         self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
         self.use_side_stream = os.environ.get("SCANN_SIDE_STREAM", "1") == "1"
-        # Opt-in: smaller, wave-balanced tiles.  Measured on QM9/128: local-attention kernels -3 %, but the
-        # kernels whose cost is per tile rather than per row (geom_init, la_wgrad_tc) lose more: 2.06 vs 1.93 ms.
-        self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "0") == "1"
+        # Wave-balanced tiles: rows per tile chosen so that the tile count is a whole number of rounds over the
+        # SMs' warp groups (QM9/128: 592 tiles of ~40 rows instead of 388 of 64: every group runs two short
+        # tiles instead of some running two long ones).  Local-attention backward 74 -> 64 us per layer; the
+        # weight-gradient launch runs over the compact list of valid rows, so it does not pay for the padding.
+        self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "1") == "1"
         # rows per tile slot of the pair plan: 64 = two warp groups per CTA in the tensor-core local-attention
         # kernels (needs <= 64 neighbours per atom), 128 = one tile stream per CTA (also the SIMT engine)
         self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "64"))
@@ -299,7 +301,10 @@ class Engine:
         b.pair_slot = torch.empty(rows, **i32)
         b.pair_d = torch.empty(rows, **f32)
         b.pair_w = torch.empty(rows, **f32)
-        b.scratch = torch.empty(2 * ngroups + 8, **i32)
+        b.valid_rows = torch.empty(rows, **i32)
+        b.valid_j = torch.empty(rows, **i32)
+        b.nvalid = torch.zeros(1, **i32)
+        b.scratch = torch.empty(4 * ngroups + 8, **i32)
         b.graphs = {}
         return b
 
@@ -340,7 +345,8 @@ class Engine:
         check(lib.scann_plan_build(_p(b.nmask), _p(b.nbr), _p(b.dist), _p(b.weight), b.B, b.M, b.N, b.tile_cap,
                                    b.tile_rows, b.stride, _p(b.cnt), _p(b.rowptr), _p(b.tile_a0), _p(b.tile_a1), _p(b.ntiles),
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
-                                   _p(b.scratch), b.scratch.numel(), _p(self.status), self._stream()), "plan_build")
+                                   _p(b.valid_rows), _p(b.valid_j), _p(b.nvalid), _p(b.scratch), b.scratch.numel(), _p(self.status),
+                                   self._stream()), "plan_build")
         self.launches += 4
 
     # ------------------------------------------------------------------ workspaces
@@ -906,7 +912,8 @@ class Engine:
             self._pdl(False)
             self._ev("wgrad_batch", True)
             check(lib.scann_wgrad_batch_tc(self.la_grid, _p(table), count, _p(b.ntiles), b.stride, _p(b.pair_c),
-                                           _p(b.pair_j), st), "wgrad_batch_tc")
+                                           _p(b.pair_j), _p(b.valid_rows), _p(b.valid_j), _p(b.nvalid), st),
+                      "wgrad_batch_tc")
             self._ev("wgrad_batch", False)
             self.launches += 1
         self._backward_tail(b, ws, dg_up, side, main)

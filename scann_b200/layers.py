@@ -130,7 +130,7 @@ class _Plan:
         check(lib.scann_plan_build(_p(mask_u8), _p(neighbors), _p(zeros), _p(zeros), B, M, N, cap, TILE, TILE, _p(self.cnt),
                                    _p(self.rowptr), _p(self.tile_a0), _p(self.tile_a1), _p(self.ntiles),
                                    _p(self.pair_c), _p(self.pair_j), _p(self.pair_slot), _p(self.pair_d),
-                                   _p(self.pair_w), _p(scratch), scratch.numel(), _p(self.status), _stream()),
+                                   _p(self.pair_w), 0, 0, 0, _p(scratch), scratch.numel(), _p(self.status), _stream()),
               "plan_build")
         s = int(self.status.item())
         if s:

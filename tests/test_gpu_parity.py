@@ -89,6 +89,10 @@ def test_plan_gathers_and_masks_bit_exact(shape, B):
     assert np.array_equal(pc[valid], slot[valid] // b.N)
     assert np.array_equal(b.pair_d.cpu().numpy()[valid], inputs["neighbor_distance"].reshape(-1)[slot[valid]])
     assert np.array_equal(b.pair_w.cpu().numpy()[valid], inputs["neighbor_weight"].reshape(-1)[slot[valid]])
+    # compact list of the valid rows
+    nv = int(b.nvalid.item())
+    assert nv == valid.sum()
+    assert np.array_equal(b.valid_rows.cpu().numpy()[:nv], np.flatnonzero(valid))      # in tile order
     cnt = b.cnt.cpu().numpy()
     assert np.array_equal(cnt, inputs["neighbor_mask"].reshape(b.R, -1).sum(1))
     # pairs of one atom are contiguous, in slot order, inside one tile
