@@ -412,6 +412,8 @@ class Engine:
 
     def _chain(self, steps, R):
         """One scann_dense_chain launch: ``steps`` is a list of ChainStep (see include/scann_b200.h)."""
+        if "chain" in self._skip:
+            return
         arr = (ChainStep * len(steps))(*steps)
         check(lib.scann_dense_chain(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, self._stream()), "dense_chain")
         self.launches += 1

@@ -119,7 +119,17 @@ class ScannKerasModel:
         """``model.fit(trainIter, epochs, validation_data=validIter, ...)`` (scann_model.py:232-241) over a
         ``Sequence``-like iterator (``len``, ``__getitem__`` -> (inputs, target), ``on_epoch_end``)."""
         hist = History()
+        callbacks = list(callbacks or [])
+        self.stop_training = False
+        for cb in callbacks:                      # Keras callback protocol (scann_b200/callbacks.py)
+            if hasattr(cb, "set_model"):
+                cb.set_model(self)
+            if hasattr(cb, "on_train_begin"):
+                cb.on_train_begin({})
         for ep in range(epochs):
+            for cb in callbacks:
+                if hasattr(cb, "on_epoch_begin"):
+                    cb.on_epoch_begin(ep, {})
             losses, maes = [], []
             for i in range(len(x)):
                 inputs, target = x[i]
@@ -135,9 +145,15 @@ class ScannKerasModel:
                 x.on_epoch_end()
             if verbose:
                 print(f"Epoch {ep + 1}/{epochs} - " + " - ".join(f"{k}: {vals[-1]:.6f}" for k, vals in hist.history.items()))
-            for cb in callbacks or []:
+            logs = {k: vals[-1] for k, vals in hist.history.items()}
+            for cb in callbacks:
                 if hasattr(cb, "on_epoch_end"):
-                    cb.on_epoch_end(ep, {k: vals[-1] for k, vals in hist.history.items()})
+                    cb.on_epoch_end(ep, logs)
+            if self.stop_training:
+                break
+        for cb in callbacks:
+            if hasattr(cb, "on_train_end"):
+                cb.on_train_end({})
         return hist
 
     # ---- weights ---------------------------------------------------------------------------
@@ -278,6 +294,71 @@ class SCANN:
         if len(out) == 2:
             return out[0] * self.std + self.mean, out[1]
         return out * self.std + self.mean
+
+    # ---- training shell (scann_model.py:163-313) ------------------------------------------------------------
+    def _run_dir(self) -> str:
+        hy = self.config["hyper"]
+        return "{}_{}".format(hy["save_path"], hy["target"])
+
+    def create_callbacks(self):
+        """ModelCheckpoint(best val_mae) + EarlyStopping(patience 200) + SGDRC / lr logging (scann_model.py:163-197)."""
+        from . import callbacks as C
+        hy = self.config["hyper"]
+        cbs = [C.ModelCheckpoint(filepath="{}/models/model_{}.h5".format(self._run_dir(), hy["target"]), monitor="val_mae",
+                                 save_weights_only=False, verbose=2, save_best_only=True),
+               C.EarlyStopping(monitor="val_mae", patience=200)]
+        if hy.get("scheduler") == "sgdr":
+            lr = C.SGDRC(lr_min=hy["min_lr"], lr_max=hy["lr"], t0=50, tmult=2, lr_max_compression=1.2, trigger_val_mae=300)
+            cbs += [lr, C.LearningRateScheduler(lr.lr_scheduler)]
+        else:
+            cbs.append(C.LearningRateLoggingCallback())
+        return cbs
+
+    def train(self, epochs: int = 1000):
+        """``SCANN.train`` (scann_model.py:199-245) for iterators attached as ``self.trainIter`` / ``self.validIter``
+        (``prepare_dataset`` needs pymatgen / the datasets and is outside the accelerated path)."""
+        import yaml
+        if not hasattr(self, "trainIter"):
+            raise RuntimeError("attach trainIter / validIter (DataIterator-like sequences) before train()")
+        os.makedirs(os.path.join(self._run_dir(), "models"), exist_ok=True)
+        with open(os.path.join(self._run_dir(), "config.yaml"), "w") as f:
+            yaml.safe_dump(self.config, f, default_flow_style=False)
+        self.train_iterators(self.trainIter, getattr(self, "validIter", None), epochs, self.create_callbacks())
+
+    def evaluate(self):
+        """``SCANN.evaluate`` (scann_model.py:247-313): best checkpoint -> test predictions -> R2 / MAE report."""
+        hy = self.config["hyper"]
+        if self.model is None:
+            print("Load best validation weight for predicting testset", "\n")
+            self.model = create_model(self.config)
+            self.model.load_weights("{}/models/model_{}.h5".format(self._run_dir(), hy["target"]))
+        data = self.dataIter if hasattr(self, "dataIter") else self.testIter
+        y, y_predict = [], []
+        for i in range(len(data)):
+            inputs, target = data[i]
+            out = self.model.predict(inputs)
+            out = out[0] if isinstance(out, list) else out
+            y.extend(np.asarray(target, np.float64).reshape(-1).tolist())
+            y_predict.extend(np.asarray(out, np.float64).reshape(-1).tolist())
+            if i % 10 == 0:
+                print(f"{i}/{len(data)}")
+        ya, yp = np.asarray(y), np.asarray(y_predict)
+        mae = float(np.abs(ya - yp).mean()) * self.std
+        ss_tot = float(((ya - ya.mean()) ** 2).sum())
+        r2 = 1.0 - float(((ya - yp) ** 2).sum()) / ss_tot if ss_tot > 0 else 0.0     # sklearn.metrics.r2_score
+        print("Result for testset ", hy["target"], " : R2 score: ", r2, " and MAE: ", mae)
+        os.makedirs(self._run_dir(), exist_ok=True)
+        lines = []
+        if hasattr(self, "hist"):
+            np.save(os.path.join(self._run_dir(), "hist_data.npy"),
+                    np.array([y_predict, y, self.hist.history], dtype=object), allow_pickle=True)
+            lines.append("Training MAE: " + str(min(self.hist.history["mae"]) * self.std) + "\n")
+            if "val_mae" in self.hist.history:
+                lines.append("Val MAE: " + str(min(self.hist.history["val_mae"]) * self.std) + "\n")
+        lines.append("Test MAE: " + str(mae) + ", Test R2: " + str(r2))
+        with open(os.path.join(self._run_dir(), "report.txt"), "w") as f:
+            f.writelines(lines)
+        return {"mae": mae, "r2": r2}
 
     def train_iterators(self, train_iter, valid_iter=None, epochs: int = 1000, callbacks=None):
         """``train`` (scann_model.py:199-241) minus dataset loading: lr schedule + compile + fit."""

@@ -20,7 +20,7 @@ e1.record(); torch.cuda.synchronize()
 print(e0.elapsed_time(e1) / 30)
 ''' % here
 base = None
-for skip in ["", "wgrad", "la_fwd", "la_bwd", "la_fwd,la_bwd,wgrad", "rn", "geom_init"]:
+for skip in ["", "wgrad", "la_fwd", "la_bwd", "la_fwd,la_bwd,wgrad", "rn", "geom_init", "chain", "la_fwd,la_bwd,wgrad,chain,geom_init"]:
     env = dict(os.environ, SCANN_DEBUG_SKIP=skip)
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
     try:
