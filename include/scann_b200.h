@@ -63,6 +63,17 @@ int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, con
                      int32_t* pair_slot, float* pair_d, float* pair_w, int32_t* valid_rows, int32_t* valid_j,
                      int32_t* nvalid, int32_t* scratch, int scratch_len, int32_t* status, void* stream);
 
+/* ---- ragged batch -> padded device buffers --------------------------------------------------------
+ * DataIterator.__getitem__ (scann/utils/datagenerator.py:69-135) on the device: the batch arrives as CSR arrays in
+ * one DEVICE blob (byte offsets off_*: struct_atom_off [B+1], atom_nbr_off [A+1], z [A], nbr_idx / nbr_w / nbr_d [P]
+ * int32/float32, ring [A,2] int32 or off < 0, target [B] float32 or off < 0) and is expanded into the padded arrays
+ * of the reference's input dict: neighbour value 1000 = padding marker (mask false, index 0), zero-padded weights
+ * and distances, atom_mask = Z != 0. */
+int scann_pack_batch(const void* csr, long long off_sa, long long off_an, long long off_z, long long off_idx,
+                     long long off_w, long long off_d, long long off_ring, long long off_target, int B, int M, int N,
+                     int32_t* atomic, uint8_t* atom_mask, int32_t* neighbors, uint8_t* neighbor_mask, float* weight,
+                     float* dist, float* ring_out, float* target, void* stream);
+
 /* ---- input embedding: Embedding + (extra_embed) + dense_embed swish -----------------------
  * scann/models/scann_model.py:361-374.  ring may be NULL (use_ring False). t0 (pre-activation,
  * saved for backward) may be NULL. */

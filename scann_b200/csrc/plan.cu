@@ -152,6 +152,65 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ragged (CSR) batch -> padded device buffers: DataIterator.__getitem__ (scann/utils/datagenerator.py:69-135) on
+// the device.  One thread per padded atom row (b, m).  Neighbour value 1000 is the reference's padding marker
+// (mask = idx != 1000, index reset to 0; datagenerator.py:82-90); weights / distances are zero padded;
+// atom_mask = Z != 0.  The CSR arrays arrive in one blob (one host->device copy of the valid data only).
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_batch_kernel(const int32_t* __restrict__ sa, const int32_t* __restrict__ an,
+                                  const int32_t* __restrict__ z, const int32_t* __restrict__ idx,
+                                  const float* __restrict__ w, const float* __restrict__ d,
+                                  const int32_t* __restrict__ ring, const float* __restrict__ tgt, int B, int M, int N,
+                                  int32_t* __restrict__ atomic, uint8_t* __restrict__ atom_mask,
+                                  int32_t* __restrict__ nbr, uint8_t* __restrict__ nmask, float* __restrict__ weight,
+                                  float* __restrict__ dist, float* __restrict__ ring_out, float* __restrict__ target) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tgt && r < B) target[r] = tgt[r];
+    if (r >= B * M) return;
+    const int b = r / M, m = r - b * M;
+    const int a0 = sa[b], n_at = sa[b + 1] - a0;
+    int Z = 0, p0 = 0, k = 0, a = -1;
+    if (m < n_at) { a = a0 + m; Z = z[a]; p0 = an[a]; k = an[a + 1] - p0; }
+    atomic[r] = Z;
+    atom_mask[r] = Z != 0;
+    if (ring_out) {
+        ring_out[(size_t)r * 2] = a >= 0 ? (float)ring[(size_t)a * 2] : 0.f;
+        ring_out[(size_t)r * 2 + 1] = a >= 0 ? (float)ring[(size_t)a * 2 + 1] : 0.f;
+    }
+    for (int n = 0; n < N; ++n) {
+        const size_t s = (size_t)r * N + n;
+        int j = 0;
+        bool valid = false;
+        float wv = 0.f, dv = 0.f;
+        if (n < k) {
+            j = idx[p0 + n];
+            valid = j != 1000;
+            if (!valid) j = 0;
+            wv = w[p0 + n];
+            dv = d[p0 + n];
+        }
+        nbr[s] = j; nmask[s] = valid; weight[s] = wv; dist[s] = dv;
+    }
+}
+
+// csr: device blob; off_*: byte offsets of struct_atom_off [B+1], atom_nbr_off [A+1], z [A], nbr_idx / nbr_w / nbr_d [P],
+// ring [A,2] int32 (or < 0), target [B] (or < 0).  Outputs: the padded arrays of the reference's input dict.
+extern "C" int scann_pack_batch(const void* csr, long long off_sa, long long off_an, long long off_z, long long off_idx,
+                                long long off_w, long long off_d, long long off_ring, long long off_target, int B, int M,
+                                int N, int32_t* atomic, uint8_t* atom_mask, int32_t* neighbors, uint8_t* neighbor_mask,
+                                float* weight, float* dist, float* ring_out, float* target, void* stream) {
+    if (B <= 0 || M <= 0 || N <= 0) { scann_set_error("pack_batch: bad shape B=%d M=%d N=%d", B, M, N); return 1; }
+    const char* p = (const char*)csr;
+    const int R = B * M;
+    pack_batch_kernel<<<(max(R, B) + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        (const int32_t*)(p + off_sa), (const int32_t*)(p + off_an), (const int32_t*)(p + off_z),
+        (const int32_t*)(p + off_idx), (const float*)(p + off_w), (const float*)(p + off_d),
+        off_ring >= 0 ? (const int32_t*)(p + off_ring) : nullptr, off_target >= 0 ? (const float*)(p + off_target) : nullptr,
+        B, M, N, atomic, atom_mask, neighbors, neighbor_mask, weight, dist, off_ring >= 0 ? ring_out : nullptr, target);
+    return scann_check_launch("scann_pack_batch");
+}
+
 extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* neighbors, const float* dist,
                                 const float* weight, int B, int M, int N, int tile_cap, int tile_rows,
                                 int tile_stride, int32_t* cnt,

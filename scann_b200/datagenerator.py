@@ -1,0 +1,136 @@
+"""``DataIterator`` of the reference (scann/utils/datagenerator.py:12-135) on flat CSR arrays.
+
+The reference rebuilds every padded batch from nested Python lists (three list comprehensions over all
+atom-neighbour pairs per ``__getitem__``) -- at 10^5 structures/s on the GPU that host work is the bottleneck.
+Here the ragged data are converted ONCE into CSR arrays (structure -> atoms -> neighbours); a batch is either
+
+* ``__getitem__(i)``: the same padded dict ``(inputs, target)`` the reference returns, packed with vectorised
+  numpy (bit-identical to the reference's padding, tests/test_datagen.py), or
+* ``csr_item(i)``: the CSR slice of the batch, which ``Engine.load_batch_csr`` ships in one host->device copy
+  (only valid atoms / pairs travel) and ``scann_pack_batch`` (csrc/plan.cu) expands into the padded device
+  buffers.
+
+Data format (reference): ``data_neighbor[s][a]`` = list of neighbour tuples ``n`` with ``n[1]`` = neighbour atom
+index, ``n[2]`` = solid angle, ``n[3]`` = normalised solid angle, ``n[-1]`` = distance; ``data_energy[s]`` =
+``(atomic numbers, target[, ring/aromatic flags per atom])``.
+"""
+from __future__ import annotations
+
+from math import ceil
+from typing import Dict, Tuple
+
+import numpy as np
+
+
+class DataIterator:
+    def __init__(self, data_energy, data_neighbor, batch_size=32, converter=False, use_ring=False, shuffle=False,
+                 feature="atomic", g_update=False):
+        if feature != "atomic":
+            raise NotImplementedError("feature='cgcnn' is not on the accelerated path")
+        self.batch_size, self.shuffle, self.use_ring, self.feature = batch_size, shuffle, use_ring, feature
+        self.weight_index = 2 if g_update else 3                       # datagenerator.py:48-50
+        self.converter = 1000 if converter else 1.0                    # :54-57
+        S = len(data_energy)
+        n_atoms = np.fromiter((len(c) for c in data_neighbor), np.int64, S)
+        self.atom_off = np.zeros(S + 1, np.int64)
+        np.cumsum(n_atoms, out=self.atom_off[1:])
+        A = int(self.atom_off[-1])
+        n_nbr = np.fromiter((len(lc) for c in data_neighbor for lc in c), np.int64, A)
+        self.nbr_off = np.zeros(A + 1, np.int64)
+        np.cumsum(n_nbr, out=self.nbr_off[1:])
+        P = int(self.nbr_off[-1])
+        self.nbr_idx = np.fromiter((n[1] for c in data_neighbor for lc in c for n in lc), np.int32, P)
+        wi = self.weight_index
+        self.nbr_w = np.fromiter((n[wi] for c in data_neighbor for lc in c for n in lc), np.float32, P)
+        self.nbr_d = np.fromiter((n[-1] for c in data_neighbor for lc in c for n in lc), np.float32, P)
+        self.z = np.fromiter((z for p in data_energy for z in p[0]), np.int32, A)
+        self.energy = np.array([float(p[1]) * self.converter for p in data_energy], "float32")
+        self.ring = (np.array([r for p in data_energy for r in p[2]], np.int32).reshape(A, 2) if use_ring else None)
+        self.on_epoch_end()
+
+    def on_epoch_end(self):
+        self.indexes = np.arange(len(self.energy))
+        if self.shuffle:
+            np.random.shuffle(self.indexes)
+
+    def __len__(self):
+        return ceil(len(self.energy) / self.batch_size)
+
+    # ------------------------------------------------------------------ CSR slice of one batch
+    def csr_item(self, idx: int) -> Tuple[Dict[str, np.ndarray], np.ndarray]:
+        sel = self.indexes[idx * self.batch_size:(idx + 1) * self.batch_size]
+        a0, a1 = self.atom_off[sel], self.atom_off[sel + 1]
+        n_at = (a1 - a0).astype(np.int64)
+        atoms = np.concatenate([np.arange(s, e) for s, e in zip(a0, a1)]) if len(sel) else np.zeros(0, np.int64)
+        p0, p1 = self.nbr_off[atoms], self.nbr_off[atoms + 1]
+        n_nb = (p1 - p0).astype(np.int64)
+        pairs = np.concatenate([np.arange(s, e) for s, e in zip(p0, p1)]) if len(atoms) else np.zeros(0, np.int64)
+        sa = np.zeros(len(sel) + 1, np.int32)
+        np.cumsum(n_at, out=sa[1:])
+        an = np.zeros(len(atoms) + 1, np.int32)
+        np.cumsum(n_nb, out=an[1:])
+        csr = {"struct_atom_off": sa, "atom_nbr_off": an, "z": self.z[atoms], "nbr_idx": self.nbr_idx[pairs],
+               "nbr_w": self.nbr_w[pairs], "nbr_d": self.nbr_d[pairs],
+               "M": int(n_at.max()) if len(sel) else 0, "N": int(n_nb.max()) if len(atoms) else 0}
+        if self.use_ring:
+            csr["ring"] = self.ring[atoms]
+        return csr, self.energy[sel]
+
+    # ------------------------------------------------------------------ padded batch, as the reference returns it
+    def __getitem__(self, idx: int):
+        csr, energy = self.csr_item(idx)
+        return pack_padded(csr), energy
+
+
+def pack_padded(csr: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """CSR batch -> the padded dict of DataIterator.__getitem__ (vectorised; the device kernel does the same)."""
+    sa, an = csr["struct_atom_off"].astype(np.int64), csr["atom_nbr_off"].astype(np.int64)
+    B, M, N = len(sa) - 1, csr["M"], csr["N"]
+    A = int(sa[-1])
+    b_of_atom = np.repeat(np.arange(B), np.diff(sa))
+    m_of_atom = np.arange(A) - sa[b_of_atom]
+    atomic = np.zeros((B, M), np.int32)
+    atomic[b_of_atom, m_of_atom] = csr["z"]
+    a_of_pair = np.repeat(np.arange(A), np.diff(an))
+    n_of_pair = np.arange(int(an[-1])) - an[a_of_pair]
+    bp, mp = b_of_atom[a_of_pair], m_of_atom[a_of_pair]
+    nbr = np.zeros((B, M, N), np.int32)
+    nmask = np.zeros((B, M, N), bool)
+    w = np.zeros((B, M, N), np.float32)
+    d = np.zeros((B, M, N), np.float32)
+    idx = csr["nbr_idx"]
+    nmask[bp, mp, n_of_pair] = idx != 1000          # the reference pads with 1000 and masks "!= 1000" (:82-90)
+    nbr[bp, mp, n_of_pair] = np.where(idx == 1000, 0, idx)
+    w[bp, mp, n_of_pair] = csr["nbr_w"]
+    d[bp, mp, n_of_pair] = csr["nbr_d"]
+    out = {"atomic": atomic, "atom_mask": (atomic != 0)[..., None], "neighbors": nbr, "neighbor_mask": nmask,
+           "neighbor_weight": w, "neighbor_distance": d}
+    if "ring" in csr:
+        ring = np.zeros((B, M, 2), np.int32)
+        ring[b_of_atom, m_of_atom] = csr["ring"]
+        out["ring_aromatic"] = ring
+    return out
+
+
+def synthetic_ragged(n_struct: int, seed: int = 0, max_atoms: int = 29, max_nbr: int = 16, use_ring: bool = False):
+    """Random data in the reference's nested-list format (for tests and benchmarks)."""
+    rng = np.random.default_rng(seed)
+    data_energy, data_neighbor = [], []
+    for _ in range(n_struct):
+        na = int(rng.integers(2, max_atoms + 1))
+        zs = rng.choice([1, 6, 7, 8, 9], size=na).tolist()
+        rec = [zs, float(rng.standard_normal())]
+        if use_ring:
+            rec.append(rng.integers(0, 2, size=(na, 2)).tolist())
+        data_energy.append(tuple(rec))
+        nb = []
+        for _a in range(na):
+            k = int(rng.integers(1, max_nbr + 1))
+            nb.append([(0, int(rng.integers(0, na)), float(rng.uniform(0.4, 3.0)), float(rng.uniform(0.2, 1.0)),
+                        float(rng.uniform(0.9, 4.0))) for _ in range(k)])
+        data_neighbor.append(nb)
+    de = np.empty(n_struct, object)
+    dn = np.empty(n_struct, object)
+    for i in range(n_struct):
+        de[i], dn[i] = data_energy[i], data_neighbor[i]
+    return de, dn

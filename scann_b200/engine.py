@@ -181,34 +181,17 @@ class Engine:
         pinned staging buffers; CUDA tensors / ``__dlpack__`` objects are copied device-to-device.
         Buffers are persistent per (B, M, N, tile capacity) so that a captured CUDA graph can be
         replayed on every batch of that shape."""
-        dev = self.device
         nb = inputs["neighbors"]
         B, M, N = (int(s) for s in nb.shape)
-        R = B * M
         nmask_in = inputs["neighbor_mask"]
         P_host = int(np.count_nonzero(nmask_in)) if isinstance(nmask_in, np.ndarray) else None
         if P_host is None:
             P_host = pairs_hint
-        P = P_host if P_host is not None else B * M * N
-        ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
-        # rows per tile: fill whole waves of SMs (the kernels' cost per tile scales with its rows, and a
-        # tile count just above a multiple of the SM count costs a whole extra round)
-        stride = 64 if (self.tile_stride_pref == 64 and self.tc_la_fwd and self.tc_la_bwd and N <= 32) else TILE
-        tile_rows = stride
-        if P_host is not None and self.balance_tiles and N <= 64:
-            slots = self.sm_count * (TILE // stride)
-            waves = max(1, -(-P // (stride * slots)))
-            tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
-        # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
-        cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
-        tile_cap = max(64, (cap + 63) // 64 * 64)
-        key = (B, M, N, tile_cap, tile_rows, stride)
-        b = self._batches.get(key)
-        if b is None:
-            b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups, stride)
-            b.tile_rows = tile_rows
+        b = self._get_batch(B, M, N, P_host)
         b.P_host = P_host
         b.h2d_bytes = 0
+        dev = self.device
+        key = (B, M, N, b.tile_cap, b.tile_rows, b.stride)
 
         def put(dst: torch.Tensor, x, name):
             if isinstance(x, torch.Tensor):
@@ -260,6 +243,73 @@ class Engine:
         else:
             for name, x in items:
                 put(getattr(b, name), x, name)
+        if plan:
+            self._plan(b)
+        return b
+
+    def _get_batch(self, B: int, M: int, N: int, P_host: Optional[int]) -> Batch:
+        """Persistent device buffers of the shape class (B, M, N, tile capacity, tile layout)."""
+        R = B * M
+        P = P_host if P_host is not None else B * M * N
+        ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
+        # rows per tile: fill whole waves of SMs (the kernels' cost per tile scales with its rows, and a
+        # tile count just above a multiple of the SM count costs a whole extra round)
+        stride = 64 if (self.tile_stride_pref == 64 and self.tc_la_fwd and self.tc_la_bwd and N <= 32) else TILE
+        tile_rows = stride
+        if P_host is not None and self.balance_tiles and N <= 64:
+            slots = self.sm_count * (TILE // stride)
+            waves = max(1, -(-P // (stride * slots)))
+            tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
+        # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
+        cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
+        tile_cap = max(64, (cap + 63) // 64 * 64)
+        key = (B, M, N, tile_cap, tile_rows, stride)
+        b = self._batches.get(key)
+        if b is None:
+            b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups, stride)
+            b.tile_rows = tile_rows
+        return b
+
+    def load_batch_csr(self, csr: Dict[str, object], target=None, plan: bool = True) -> Batch:
+        """Stage one RAGGED batch (``DataIterator.csr_item`` of scann_b200/datagenerator.py): the CSR arrays travel
+        in one host->device copy (valid atoms / pairs only) and ``scann_pack_batch`` expands them into the padded
+        device buffers -- the device form of the reference's DataIterator.__getitem__."""
+        sa, an = csr["struct_atom_off"], csr["atom_nbr_off"]
+        B, M, N = len(sa) - 1, int(csr["M"]), int(csr["N"])
+        idx = np.asarray(csr["nbr_idx"], np.int32)
+        P_host = int(np.count_nonzero(idx != 1000))
+        b = self._get_batch(B, M, N, P_host)
+        b.P_host = P_host
+        segs = [("sa", np.asarray(sa, np.int32)), ("an", np.asarray(an, np.int32)), ("z", np.asarray(csr["z"], np.int32)),
+                ("idx", idx), ("w", np.asarray(csr["nbr_w"], np.float32)), ("d", np.asarray(csr["nbr_d"], np.float32))]
+        if self.spec.use_ring:
+            segs.append(("ring", np.asarray(csr["ring"], np.int32).reshape(-1)))
+        if target is not None:
+            segs.append(("target", np.asarray(target, np.float32).reshape(-1)))
+        offs, off = {}, 0
+        for name, a in segs:
+            offs[name] = off
+            off += (a.nbytes + 15) // 16 * 16
+        if getattr(b, "csr_pin", None) is None or b.csr_pin.numel() < off:
+            cap = max(off, 4 * (B + 2 + 3 * b.R + 3 * b.R * N + b.R * 2 + B) + 256)
+            b.csr_pin = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            b.csr_dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+            b.csr_event = None
+        if b.csr_event is not None:
+            b.csr_event.synchronize()
+        host = b.csr_pin.numpy()
+        for name, a in segs:
+            host[offs[name]:offs[name] + a.nbytes] = a.view(np.uint8).reshape(-1)
+        b.csr_dev[:off].copy_(b.csr_pin[:off], non_blocking=True)
+        b.csr_event = torch.cuda.Event()
+        b.csr_event.record(torch.cuda.current_stream(self.device))
+        b.h2d_bytes = off
+        b.host_dirty = False
+        check(lib.scann_pack_batch(_p(b.csr_dev), offs["sa"], offs["an"], offs["z"], offs["idx"], offs["w"], offs["d"],
+                                   offs.get("ring", -1), offs.get("target", -1), B, M, N, _p(b.atomic), _p(b.atom_mask),
+                                   _p(b.nbr), _p(b.nmask), _p(b.weight), _p(b.dist), _p(b.ring), _p(b.target),
+                                   self._stream()), "pack_batch")
+        self.launches += 1
         if plan:
             self._plan(b)
         return b

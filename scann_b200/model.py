@@ -68,7 +68,8 @@ class ScannKerasModel:
         """Keras ``Model.predict``: numpy in, numpy out.  Keras would split the batch into
         sub-batches of 32; structures are independent so one pass gives identical results."""
         eng = self.engine
-        b = eng.load_batch(inputs, plan=False)
+        # a ragged CSR batch (DataIterator.csr_item) is expanded to the padded layout on the device
+        b = eng.load_batch_csr(inputs, plan=False) if "struct_atom_off" in inputs else eng.load_batch(inputs, plan=False)
         y, ga = eng.predict_step(b, replan=True)
         y_h = y.cpu().numpy().reshape(b.B, 1)          # synchronises the stream
         eng.check_status()
@@ -98,7 +99,11 @@ class ScannKerasModel:
         """One Keras ``train_step``: returns the loss (RMSE + l2 penalties) of the batch."""
         eng = self.engine
         eng.train_dropout = bool(self.dropout) and eng.use_chain and eng.use_wgrad_batch
-        b = eng.load_batch(inputs, plan=False)
+        if "struct_atom_off" in inputs:           # ragged CSR batch: inputs and targets in one copy, packed on device
+            b = eng.load_batch_csr(inputs, target=y_true, plan=False)
+            y_true = b.target
+        else:
+            b = eng.load_batch(inputs, plan=False)
         batch_global = b.B * self.world_size
         eng.train_step(b, y_true, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global, replan=True)
         out = eng.loss_value(batch_global).cpu().numpy()       # synchronises the stream
@@ -132,7 +137,8 @@ class ScannKerasModel:
                     cb.on_epoch_begin(ep, {})
             losses, maes = [], []
             for i in range(len(x)):
-                inputs, target = x[i]
+                # iterators that can hand out the ragged CSR form skip the host-side padding altogether
+                inputs, target = x.csr_item(i) if hasattr(x, "csr_item") else x[i]
                 out = self.train_on_batch(inputs, target, return_dict=True)
                 losses.append(out["loss"])
                 maes.append(out["mae"])
