@@ -52,3 +52,6 @@ def attach(model, world: int) -> None:
     if world > 1:
         model.allreduce = allreduce_sum
         model.world_size = world
+        # every rank draws its own Dropout masks (its shard holds different structures)
+        rank = env_world()[0]
+        model.engine.dropout_seed = (model.engine.dropout_seed + 7919 * rank) & 0x7FFFFFFF
