@@ -153,19 +153,22 @@ __global__ void __launch_bounds__(128) embed_bwd_final_kernel(int E, int n_atoms
 // Geometry initialisation (g_update): g0 = swish(rbf_d Wd + bd) * swish(rbf_w Ww + bw)
 // rbf_x[k] = exp(-(x - c_k)^2 / 0.25)                 (scann_model.py:378-389, custom_layers.py:55-65)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF], int* s_c, float* s_d, float* s_w,
+// returns the tile's fill (valid rows are a prefix of the tile slot; wave-balanced plans leave the tail empty)
+__device__ __forceinline__ int geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF], int* s_c, float* s_d, float* s_w,
                                                const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
                                                const float* __restrict__ pair_w, const float* __restrict__ cd,
                                                const float* __restrict__ cw, size_t base, int stride) {
     // per-tile pair data -> smem (one coalesced pass), then the 2 x 20 Gaussians of every row
+    int valid = 0;
     if ((int)threadIdx.x < stride) {
         const int c = pair_c[base + threadIdx.x];
         s_c[threadIdx.x] = c;
         s_d[threadIdx.x] = c >= 0 ? pair_d[base + threadIdx.x] : 0.f;
         s_w[threadIdx.x] = c >= 0 ? pair_w[base + threadIdx.x] : 0.f;
+        valid = c >= 0;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < stride * 2 * SCANN_RBF; i += blockDim.x) {
+    const int fill = __syncthreads_count(valid);
+    for (int i = threadIdx.x; i < fill * 2 * SCANN_RBF; i += blockDim.x) {
         const int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
         const float x = (k < SCANN_RBF) ? s_d[row] : s_w[row];
         const float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
@@ -173,6 +176,7 @@ __device__ __forceinline__ void geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF], in
         s_rbf[row][k] = s_c[row] >= 0 ? expf(-(df * df) / 0.25f) : 0.f;
     }
     __syncthreads();
+    return fill;
 }
 
 __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __restrict__ ntiles, int stride,
@@ -200,9 +204,10 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
         const size_t base = (size_t)t * stride;
         __syncthreads();
         if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
+        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
+        for (int row = fill + half; row < stride; row += 2) g0[(base + row) * SCANN_D + n] = 0.f;   // empty tail
 #pragma unroll 4
-        for (int row = half; row < stride; row += 2) {
+        for (int row = half; row < fill; row += 2) {
             float a = bdn, b = bwn;
             const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
 #pragma unroll
@@ -250,9 +255,9 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
         const size_t base = (size_t)t * stride;
         __syncthreads();
         if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
+        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
         // the gradient rows of this thread's half are independent loads: keep 8 in flight
-        for (int r8 = half; r8 < stride; r8 += 16) {
+        for (int r8 = half; r8 < fill; r8 += 16) {
             float dv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) dv[q] = dg0[(base + r8 + 2 * q) * SCANN_D + n];
@@ -325,8 +330,8 @@ __global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* _
         const size_t base = (size_t)t * stride;
         __syncthreads();
         if (t + (int)gridDim.x >= nt) pdl_trigger();
-        geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cd, base, stride);   // columns 20..39 unused
-        for (int r8 = half; r8 < stride; r8 += 16) {
+        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cd, base, stride);   // columns 20..39 unused
+        for (int r8 = half; r8 < fill; r8 += 16) {
             float dv[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) dv[q] = dg[(base + r8 + 2 * q) * SCANN_D + n];
