@@ -178,7 +178,7 @@ int scann_la_forward(int grid, const int32_t* ntiles, const int32_t* tile_a0, co
                      const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, void* stream);
 /* Same forward on the tcgen05 tensor cores (3xTF32; two kernels: geometry update, attention).
  * pre_out / k_out ([rows,128], nullable) save the filter_geo pre-activation and the keys. */
-int scann_la_forward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                         const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
                         const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
                         const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
@@ -186,7 +186,7 @@ int scann_la_forward_tc(int grid, int tile_stride, const int32_t* ntiles, const 
                         float* k_out, void* stream);
 /* LocalAttention.call with g_update=False (attention.py:155): geometry' = swish(rbf(d) @ Wf + bf) * w is
  * recomputed per layer from pair_d / pair_w; proj needs only its query block.  Inference only. */
-int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                                  const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
                                  const int32_t* pair_j, const float* x, const float* proj, const float* pair_d,
                                  const float* pair_w, const float* centers, const float* Wf, const float* bf,
@@ -194,7 +194,7 @@ int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntile
                                  float* ctx_pre, float* out, float* attn, float* g_save, float* k_out, void* stream);
 /* Backward of the g_update=False layer: attention part (g_new / kbuf = g' / keys saved by the forward; kbuf <- d_k,
  * dg <- gradient w.r.t. g', dq / dx_scatter as in scann_la_backward_tc) ... */
-int scann_la_backward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                   const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
                                   const int32_t* pair_j, const float* x, const float* proj, const float* g_new,
                                   float* kbuf, const float* WkT, const float* d_ctx, float* dg, float* dq,
@@ -217,7 +217,7 @@ int scann_la_backward(int grid, const int32_t* ntiles, const int32_t* tile_a0, c
  * kbuf / prebuf: in = keys / filter_geo pre-activation saved by scann_la_forward_tc, out = d_k / d_pre.
  * dg: gradient w.r.t. g' from the next layer (dg_has_up != 0, updated in place) or scratch.
  * Two kernels (attention, geometry); the pair weight gradients are scann_la_wgrad_tc. */
-int scann_la_backward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
                          const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
                          const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
                          float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,

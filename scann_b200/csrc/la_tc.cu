@@ -73,10 +73,10 @@ __device__ __forceinline__ void weightT_to_tmem(const float* __restrict__ W, uin
 // Fully unrolled with the descriptors advanced by immediates: a single thread issues all MMAs, so
 // every extra instruction per MMA shows up as tensor-pipe idle time (measured: 107 cycles per MMA
 // with descriptors rebuilt in the loop vs the 64-cycle math floor of a 128x128x8 tf32 MMA).
-template <int TR>
+// nrows (multiple of 16, <= tile slot): rows of the tile that can hold pairs = N extent of the MMAs
 __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
-                                             uint32_t t_dc, uint64_t* bar) {
-    const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
+                                             uint32_t t_dc, uint64_t* bar, int nrows) {
+    const uint32_t idesc = tc_idesc_tf32(128, nrows, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
@@ -90,12 +90,13 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uin
 // accumulators (lane = feature n, column = row r) -> S[r][n] (+ bias[n]); warp w of its group: lanes 32*(w%4)..,
 // rows 32*(w/4)..  (the group's 16/NG warps cover its 128/NG rows)
 __device__ __forceinline__ void tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8_t* S, const float* __restrict__ bias,
-                                             int warp, int lane) {
+                                             int warp, int lane, int nrows) {
     const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 32;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const float b = bias ? __ldg(bias + n) : 0.f;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if (rbase + h * 16 >= nrows) break;              // warp-uniform: rows beyond nrows are never valid
         float m[16], c[16];
         tmem_ld16(t_dm + lane_base + rbase + h * 16, m);
         tmem_ld16(t_dc + lane_base + rbase + h * 16, c);
@@ -116,6 +117,7 @@ struct LaGeomArgs {
     const float* gamma_g; const float* beta_g;
     float* g_out;            // [rows,128]
     float* pre_out;          // [rows,128] pre-activation of filter_geo (nullable; saved for backward)
+    int mma_rows;            // rows of a tile slot that can hold pairs (multiple of 16): wave-balanced plans fill less
 };
 
 template <int NG>
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int i = gtid + it * GT;
-                v[it] = ld4(a.g_in + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
+                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((i >> 5) < a.mma_rows) v[it] = ld4(a.g_in + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         if (t == t_first) DBG_CLK(2);
         if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);
+            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar, a.mma_rows);
         }
         if (t == t_first) DBG_CLK(3);
         // ---- while the tensor core works: indices and gathered projections of this warp's rows
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc_kernel(const La
         tc_fence_after();
         if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
         if (t == t_first) DBG_CLK(5);
-        tmem_to_rows(t_dm, t_dc, sS, nullptr, wg, lane);
+        tmem_to_rows(t_dm, t_dc, sS, nullptr, wg, lane, a.mma_rows);
         tc_fence_before();
         group_sync(grp, GT);
         if (t == t_first) DBG_CLK(6);
@@ -278,6 +281,7 @@ struct LaAttnArgs {
     // g_update = False (attention.py:155): g' = swish(rbf(d) @ Wf[20,128] + bf) * w, computed on the fly
     const float* pair_d; const float* pair_w; const float* centers; const float* Wf; const float* bf;
     float* g_save;           // [rows,128] nullable: g' of the g_update = False path, saved for the backward pass
+    int mma_rows;            // see LaGeomArgs
 };
 
 template <int NG>
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         group_sync(grp, GT);
         if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);
+            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar, a.mma_rows);
         }
         // ---- prefetch the queries of this warp's rows while the tensor core works
         float4 qv[2][4];
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
         phase ^= 1;
         tc_fence_after();
         if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
-        tmem_to_rows(t_dm, t_dc, sS, a.bk, wg, lane);            // keys k = a @ Wk + bk
+        tmem_to_rows(t_dm, t_dc, sS, a.bk, wg, lane, a.mma_rows);            // keys k = a @ Wk + bk
         tc_fence_before();
         group_sync(grp, GT);
         // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = chunks 4h..4h+3 = 4 adjacent lanes)
@@ -480,7 +484,7 @@ static int la_fwd_configure() {
 // scann_la_forward plus the optional training saves pre_out / k_out ([rows,128] each).
 // tile_stride = rows per tile slot of the pair plan (scann_plan_build): 128 (one tile stream per CTA) or
 // 64 (two warp groups per CTA, each streaming 64-row tiles).
-extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+extern "C" int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                    const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                    const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
                                    const float* g_in, const float* W2, const float* Wk, const float* bk,
@@ -488,11 +492,12 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* nti
                                    float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
                                    void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_tc: mma_rows must be a multiple of 16 in 16..tile_stride"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
-    LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out};
+    LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out, mma_rows};
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mma_rows};
     if (tile_stride == 64) {
         scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
         scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
@@ -507,7 +512,7 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, const int32_t* nti
 // swish(rbf(distance) @ Wf + bf) * weight is recomputed per layer from the 8 bytes/pair of raw geometry;
 // proj needs only its query block (columns 256..383).  g_save / k_out ([rows,128], nullable): g' and the keys,
 // saved for scann_la_backward_noupdate_tc.
-extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                             const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                             const int32_t* pair_c, const int32_t* pair_j, const float* x,
                                             const float* proj, const float* pair_d, const float* pair_w,
@@ -515,10 +520,11 @@ extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, const int
                                             const float* bk, const float* gamma, const float* beta, float* ctx_pre,
                                             float* out, float* attn, float* g_save, float* k_out, void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save};
+                  ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save, mma_rows};
     if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     else scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");

@@ -49,10 +49,9 @@ __device__ __forceinline__ void b_weightT_to_tmem(const float* __restrict__ W, u
     tmem_st_wait();
 }
 
-template <int TR>
 __device__ __forceinline__ void b_issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uint32_t xh, uint32_t xl, uint32_t t_dm,
-                                               uint32_t t_dc, uint64_t* bar) {
-    const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
+                                               uint32_t t_dc, uint64_t* bar, int nrows) {
+    const uint32_t idesc = tc_idesc_tf32(128, nrows, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
 #pragma unroll
     for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
@@ -63,11 +62,12 @@ __device__ __forceinline__ void b_issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, u
     tc_commit(bar);
 }
 
-__device__ __forceinline__ void b_tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8_t* S, int warp, int lane) {
+__device__ __forceinline__ void b_tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8_t* S, int warp, int lane, int nrows) {
     const int n = (warp & 3) * 32 + lane, rbase = (warp >> 2) * 32;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+        if (rbase + h * 16 >= nrows) break;              // warp-uniform: rows beyond nrows are never valid
         float m[16], c[16];
         tmem_ld16(t_dm + lane_base + rbase + h * 16, m);
         tmem_ld16(t_dc + lane_base + rbase + h * 16, c);
@@ -101,6 +101,7 @@ struct LaAttnBwdArgs {
     float* dq;               // [R,128] <- d_ctx + 0.25 sum_n de k   (atoms with pairs)
     float* dx_scatter;       // [R,128] += d_a * g' at the neighbour rows
     float* dbk;              // [128]   += column sums of d_k
+    int mma_rows;            // rows of a tile slot that can hold pairs (multiple of 16)
 };
 
 template <int NG>
@@ -247,13 +248,13 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
         group_sync(grp, GT);
         if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            b_issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);     // d_a^T = Wk dk^T
+            b_issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar, a.mma_rows);     // d_a^T = Wk dk^T
         }
         mbar_wait(bar, phase);
         phase ^= 1;
         tc_fence_after();
         if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
-        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane);
+        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane, a.mma_rows);
         tc_fence_before();
         group_sync(grp, GT);
         // ---- phase D: d_nbr = d_a * g' -> dx[j] ; dg' (+)= d_a * x[j]
@@ -313,6 +314,7 @@ struct LaGeomBwdArgs {
     float* s_pre;            // [R,128]  <- sum_n d_pre (atoms with pairs)
     float* t_scatter;        // [R,128]  += d_pre at the neighbour rows
     float* dgamma_g; float* dbeta_g;
+    int mma_rows;
 };
 
 template <int NG>
@@ -423,7 +425,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
         group_sync(grp, GT);
         if (wg == 0 && tc_elect_one()) {
             tc_fence_after();
-            b_issue_3xtf32<TR>(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar);     // W2 d_pre^T
+            b_issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar, a.mma_rows);     // W2 d_pre^T
         }
         // ---- phase B (warp per atom, overlaps the MMA): s_pre[c] = sum_n d_pre
         const int a0 = a.tile_a0[t], a1 = a.tile_a1[t];
@@ -443,7 +445,7 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_bwd_tc_kernel(const La
         phase ^= 1;
         tc_fence_after();
         if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
-        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane);
+        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane, a.mma_rows);
         tc_fence_before();
         group_sync(grp, GT);
         // ---- phase C: dg = d_z + d_pre @ W2^T
@@ -670,7 +672,7 @@ static int la_bwd_configure() {
     return 0;
 }
 
-extern "C" int scann_la_backward_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                     const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                     const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
                                     const float* g_in, const float* g_new, float* kbuf, float* prebuf, const float* W2T,
@@ -679,12 +681,13 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, const int32_t* nt
                                     float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream) {
     (void)wpart;
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
-                     dg_has_up, dq, dx_scatter, dbk};
+                     dg_has_up, dq, dx_scatter, dbk, mma_rows};
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
-                     s_pre, t_scatter, dgamma_g, dbeta_g};
+                     s_pre, t_scatter, dgamma_g, dbeta_g, mma_rows};
     if (tile_stride == 64) {
         scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
         scann_launch(la_geom_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
@@ -699,17 +702,18 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, const int32_t* nt
 // (softmax / context / key projection backward; d_nbr scattered to dx_scatter; dg <- gradient w.r.t.
 // g' = swish(rbf @ Wf + bf) * w, consumed by scann_noupdate_geom_backward).  g_new / kbuf: the g' and keys saved
 // by scann_la_forward_noupdate_tc; kbuf is overwritten with d_k (left operand gradient for the key kernel).
-extern "C" int scann_la_backward_noupdate_tc(int grid, int tile_stride, const int32_t* ntiles, const int32_t* tile_a0,
+extern "C" int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                              const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                              const int32_t* pair_c, const int32_t* pair_j, const float* x,
                                              const float* proj, const float* g_new, float* kbuf, const float* WkT,
                                              const float* d_ctx, float* dg, float* dq, float* dx_scatter, float* dbk,
                                              void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
-                     0, dq, dx_scatter, dbk};
+                     0, dq, dx_scatter, dbk, mma_rows};
     if (tile_stride == 64) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     else scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     return scann_check_launch("scann_la_backward_noupdate_tc");

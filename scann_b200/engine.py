@@ -268,6 +268,9 @@ class Engine:
         if b is None:
             b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups, stride)
             b.tile_rows = tile_rows
+            # rows of a tile slot that can hold pairs, rounded up to the MMA granularity: the N extent of the
+            # local-attention MMAs (a wave-balanced plan fills ~40 of 64 rows)
+            b.mma_rows = min(stride, (tile_rows + 15) // 16 * 16)
         return b
 
     def load_batch_csr(self, csr: Dict[str, object], target=None, plan: bool = True) -> Batch:
@@ -524,7 +527,7 @@ class Engine:
                 check(lib.scann_la_nopair_forward(_p(b.cnt), _p(proj), R, self.w(f"{la}/layer_norm/gamma"),
                                                   self.w(f"{la}/layer_norm/beta"), 0, _p(out), st), "la_nopair")
                 check(lib.scann_la_forward_noupdate_tc(
-                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
+                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
                     _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d), self.w(fg),
                     self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                     self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), 0, 0, st),
@@ -555,7 +558,7 @@ class Engine:
                 pass
             elif self.tc_la_fwd:
                 save = training and self.tc_la_bwd
-                check(lib.scann_la_forward_tc(self.la_grid, b.stride, *la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
+                check(lib.scann_la_forward_tc(self.la_grid, b.stride, b.mma_rows, *la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
                                               st), "la_forward_tc")
                 self.launches += 1
             else:
@@ -637,7 +640,7 @@ class Engine:
                 g_out = gs[l + 1] if training else gs[(l + 1) % 2]
                 save = training and self.tc_la_bwd
                 check(lib.scann_la_forward_tc(
-                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in), self.w(fg, D * D),
                     self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"), self.w(f"{la}/layer_norm_g/gamma"),
                     self.w(f"{la}/layer_norm_g/beta"), self.w(f"{la}/layer_norm/gamma"),
@@ -646,7 +649,7 @@ class Engine:
                 self.launches += 2
             else:
                 check(lib.scann_la_forward_noupdate_tc(
-                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
                     self.w(fg), self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                     self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), _p(attn),
@@ -774,7 +777,7 @@ class Engine:
                 pass
             elif self.tc_la_bwd:
                 dg_buf = ws["dg"][(L - 1 - l) % 2]
-                check(lib.scann_la_backward_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
+                check(lib.scann_la_backward_tc(self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
                                                _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
                                                _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
                                                _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
@@ -912,7 +915,7 @@ class Engine:
             if not sp.g_update:
                 # SCANN without geometry update: attention part only, then the filter_geo [20,128] gradient
                 check(lib.scann_la_backward_noupdate_tc(
-                    self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["gsave"][l]), _p(ws["kk"][l]),
                     self.wT(f"{la}/key/kernel"), _p(ws["d_ctx"]), _p(ws["dg"][0]), _p(dq), _p(dx_sc),
                     self.gw(f"{la}/key/bias"), st), "la_backward_noupdate_tc")
@@ -922,7 +925,7 @@ class Engine:
                     self.gw(f"{la}/filter_geo/bias"), st), "noupdate_geom_backward")
                 self.launches += 2
             elif "la_bwd" not in self._skip:
-                check(lib.scann_la_backward_tc(self.la_grid, b.stride, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1),
+                check(lib.scann_la_backward_tc(self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1),
                                                _p(b.cnt), _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
                                                _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
                                                _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
