@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                     if (r0 + r < a.R) xv[it] = ld4(A + (size_t)(r0 + r) * st.lda + c4 * 4);
                 }
             }
-            if (WPREF && kb == 0 && have_next) chain_weight_store(wnext, t_whi, t_wlo, warp);
+            if (WPREF && kb == 0 && have_next) { /* staged behind the previous step's epilogue */ }
             else if (si > 0 || kb > 0) chain_weight_to_tmem(st.W[kb], t_whi, t_wlo, warp, lane);
             if (A) {
 #pragma unroll
@@ -180,8 +180,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                 for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
                 tc_commit(&bar);
             }
+            if (WPREF && kb == st.kblk - 1) {
+                // while the tensor core works: the next step's first weight block -> registers ...
+                have_next = si + 1 < a.nsteps;
+                if (have_next) chain_weight_load(a.s[si + 1].W[0], wnext, warp, lane);
+            }
             if (kb == st.kblk - 1) {
-                // while the tensor core works: the global rows the first epilogue step needs
+                // ... and the global rows the first epilogue step needs
                 const int rr = warp * (TR / (CH_THREADS / 32)) + rsub, r = r0 + rr;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
@@ -199,11 +204,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
             __syncthreads();
         }
         CCLK(4 + si * 4);
-        if constexpr (WPREF) {
-            // the weights in tensor memory are free now: fetch the next step's first block behind the epilogue
-            have_next = si + 1 < a.nsteps;
-            if (have_next) chain_weight_load(a.s[si + 1].W[0], wnext, warp, lane);
-        }
         if (si == a.nsteps - 1) pdl_trigger();      // only the last epilogue is left
         // ------------------------------------------------------------------ epilogue 1: D^T -> S[r][n]
         {
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
             }
         }
         if (st.mode == 4 && tid < SCANN_D) { s_dg[tid] = 0.f; s_db[tid] = 0.f; }
+        if (WPREF && have_next) chain_weight_store(wnext, t_whi, t_wlo, warp);   // drains behind the row epilogue
         tc_fence_before();
         __syncthreads();
         CCLK(5 + si * 4);
