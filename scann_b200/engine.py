@@ -258,7 +258,7 @@ class Engine:
         tile_rows = stride
         if P_host is not None and self.balance_tiles and N <= 64:
             slots = self.sm_count * (TILE // stride)
-            waves = max(1, -(-P // (stride * slots)))
+            waves = max(1, -(-P // (stride * slots)))      # more, smaller tiles only add per-tile latency (measured)
             tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
         # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
         cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
