@@ -183,7 +183,9 @@ int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, const int32_t* 
                         const float* x, const float* proj, const float* g_in, const float* W2, const float* Wk,
                         const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
                         const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out,
-                        float* k_out, void* stream);
+                        float* k_out, const void* attn_drop, int drop_site, void* stream);
+/* attn_drop (ScannDropCtl*, device, nullable) / drop_site: training-mode Dropout(0.05) on the attention
+ * probabilities of use_drop models (attention.py:115-116,191-192); mask index = pair row * 8 + head. */
 /* LocalAttention.call with g_update=False (attention.py:155): geometry' = swish(rbf(d) @ Wf + bf) * w is
  * recomputed per layer from pair_d / pair_w; proj needs only its query block.  Inference only. */
 int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
@@ -191,14 +193,14 @@ int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_rows, const 
                                  const int32_t* pair_j, const float* x, const float* proj, const float* pair_d,
                                  const float* pair_w, const float* centers, const float* Wf, const float* bf,
                                  const float* Wk, const float* bk, const float* gamma, const float* beta,
-                                 float* ctx_pre, float* out, float* attn, float* g_save, float* k_out, void* stream);
+                                 float* ctx_pre, float* out, float* attn, float* g_save, float* k_out, const void* attn_drop, int drop_site, void* stream);
 /* Backward of the g_update=False layer: attention part (g_new / kbuf = g' / keys saved by the forward; kbuf <- d_k,
  * dg <- gradient w.r.t. g', dq / dx_scatter as in scann_la_backward_tc) ... */
 int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                   const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c,
                                   const int32_t* pair_j, const float* x, const float* proj, const float* g_new,
                                   float* kbuf, const float* WkT, const float* d_ctx, float* dg, float* dq,
-                                  float* dx_scatter, float* dbk, void* stream);
+                                  float* dx_scatter, float* dbk, const void* attn_drop, int drop_site, void* stream);
 /* ... and the gradient of its geometry filter g' = swish(rbf(d) @ Wf + bf) * w: dWf [20,128], dbf accumulated. */
 int scann_noupdate_geom_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
                                  const float* pair_d, const float* pair_w, const float* centers_d, const float* Wf,
@@ -222,7 +224,7 @@ int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t*
                          const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
                          float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
                          float* dg, int dg_has_up, float* dg_out, float* dq, float* s_pre, float* t_scatter,
-                         float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream);
+                         float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop, int drop_site, void* stream);
 /* Pair weight gradients of one layer (3xTF32, MN-major operands) into wpart[grid][2][128][128]:
  * slot 0 = (x[j]*g')^T d_k (key/kernel), slot 1 = g^T d_pre (filter_geo rows 128..255).  Needs the d_k /
  * d_pre that scann_la_backward_tc left in kbuf / prebuf; off the critical path (side stream). */

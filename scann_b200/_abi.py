@@ -37,12 +37,12 @@ PROTOTYPES = {
     "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
     "scann_transpose_blocks": (ci, [vp, vp, vp, ci, vp]),
     "scann_la_forward": (ci, [ci] + [vp] * 21 + [vp]),
-    "scann_la_forward_tc": (ci, [ci, ci, ci] + [vp] * 23 + [vp]),
-    "scann_la_forward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 23 + [vp]),
-    "scann_la_backward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 17 + [vp]),
+    "scann_la_forward_tc": (ci, [ci, ci, ci] + [vp] * 23 + [vp, ci, vp]),
+    "scann_la_forward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 23 + [vp, ci, vp]),
+    "scann_la_backward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 17 + [vp, ci, vp]),
     "scann_noupdate_geom_backward": (ci, [vp, ci, ci] + [vp] * 9 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
-    "scann_la_backward_tc": (ci, [ci, ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp]),
+    "scann_la_backward_tc": (ci, [ci, ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp, ci, vp]),
     "scann_la_wgrad_tc": (ci, [ci, ci] + [vp] * 9 + [vp]),
     "scann_wgrad_batch_tc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, ci, vp, vp, vp]),

@@ -282,6 +282,10 @@ struct LaAttnArgs {
     const float* pair_d; const float* pair_w; const float* centers; const float* Wf; const float* bf;
     float* g_save;           // [rows,128] nullable: g' of the g_update = False path, saved for the backward pass
     int mma_rows;            // see LaGeomArgs
+    // training-mode Dropout(0.05) on the attention probabilities (attention.py:115-116,191-192; use_drop): the
+    // multiplier of (pair row, head) is drop_mult(drop, drop_site, row * 8 + head); NULL = off
+    const ScannDropCtl* drop;
+    int drop_site;
 };
 
 template <int NG>
@@ -439,12 +443,15 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
             for (int r = 0; r < n; ++r) {
                 float p = __expf(Es[(r0 + r) * 8 + h] - m);
                 float4 kv = *reinterpret_cast<const float4*>(sS + tc_off4(r0 + r, lane));
-                s += p;
+                s += p;                                             // the softmax is normalised before the dropout
+                p *= drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
                 c0 = fmaf(p, kv.x, c0); c1 = fmaf(p, kv.y, c1); c2 = fmaf(p, kv.z, c2); c3 = fmaf(p, kv.w, c3);
             }
             const float is = 1.0f / s;
             if (a.attn && (lane & 3) == 0)
-                for (int r = 0; r < n; ++r) a.attn[(rowbase + r0 + r) * 8 + h] = __expf(Es[(r0 + r) * 8 + h] - m) * is;
+                for (int r = 0; r < n; ++r)
+                    a.attn[(rowbase + r0 + r) * 8 + h] = __expf(Es[(r0 + r) * 8 + h] - m) * is *
+                                                       drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
             c0 = c0 * is + q.x; c1 = c1 * is + q.y; c2 = c2 * is + q.z; c3 = c3 * is + q.w;
             if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
             float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
@@ -490,14 +497,15 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, cons
                                    const float* g_in, const float* W2, const float* Wk, const float* bk,
                                    const float* gamma_g, const float* beta_g, const float* gamma, const float* beta,
                                    float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
-                                   void* stream) {
+                                   const void* attn_drop, int drop_site, void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_tc: tile_stride must be 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_tc: mma_rows must be a multiple of 16 in 16..tile_stride"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out, mma_rows};
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mma_rows};
+                  ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mma_rows,
+                  (const ScannDropCtl*)attn_drop, drop_site};
     if (tile_stride == 64) {
         scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
         scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
@@ -518,13 +526,15 @@ extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_r
                                             const float* proj, const float* pair_d, const float* pair_w,
                                             const float* centers, const float* Wf, const float* bf, const float* Wk,
                                             const float* bk, const float* gamma, const float* beta, float* ctx_pre,
-                                            float* out, float* attn, float* g_save, float* k_out, void* stream) {
+                                            float* out, float* attn, float* g_save, float* k_out, const void* attn_drop,
+                                            int drop_site, void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
-                  ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save, mma_rows};
+                  ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save, mma_rows,
+                  (const ScannDropCtl*)attn_drop, drop_site};
     if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     else scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");

@@ -102,6 +102,8 @@ struct LaAttnBwdArgs {
     float* dx_scatter;       // [R,128] += d_a * g' at the neighbour rows
     float* dbk;              // [128]   += column sums of d_k
     int mma_rows;            // rows of a tile slot that can hold pairs (multiple of 16)
+    const ScannDropCtl* drop;    // attention-probability Dropout of the forward pass (see LaAttnArgs), NULL = off
+    int drop_site;
 };
 
 template <int NG>
@@ -187,6 +189,9 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                 for (int r = rs; r < n; r += 4) {
                     float p = __expf(Es[(r0 + r) * 8 + h] - m);
                     s += p;
+                    // gradient w.r.t. the softmax output = (gradient w.r.t. the dropped probabilities) * mask
+                    const float dm = drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
+                    Ds[(r0 + r) * 8 + h] *= dm;
                     dot = fmaf(p, Ds[(r0 + r) * 8 + h], dot);
                 }
                 s += __shfl_xor_sync(0xffffffffu, s, 8);     s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -196,7 +201,8 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                 for (int r = rs; r < n; r += 4) {
                     float p = __expf(Es[(r0 + r) * 8 + h] - m) * is;
                     float dp = Ds[(r0 + r) * 8 + h];
-                    Es[(r0 + r) * 8 + h] = p;
+                    // d_k uses the dropped probabilities, the softmax backward the undropped ones
+                    Es[(r0 + r) * 8 + h] = p * drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
                     Ds[(r0 + r) * 8 + h] = p * (dp - dot);
                 }
             }
@@ -678,14 +684,15 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, con
                                     const float* g_in, const float* g_new, float* kbuf, float* prebuf, const float* W2T,
                                     const float* WkT, const float* gamma_g, const float* d_ctx, float* dg, int dg_has_up,
                                     float* dg_out, float* dq, float* s_pre, float* t_scatter, float* dx_scatter,
-                                    float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, void* stream) {
+                                    float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop,
+                                    int drop_site, void* stream) {
     (void)wpart;
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_tc: tile_stride must be 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
-                     dg_has_up, dq, dx_scatter, dbk, mma_rows};
+                     dg_has_up, dq, dx_scatter, dbk, mma_rows, (const ScannDropCtl*)attn_drop, drop_site};
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g, mma_rows};
     if (tile_stride == 64) {
@@ -707,13 +714,13 @@ extern "C" int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_
                                              const int32_t* pair_c, const int32_t* pair_j, const float* x,
                                              const float* proj, const float* g_new, float* kbuf, const float* WkT,
                                              const float* d_ctx, float* dg, float* dq, float* dx_scatter, float* dbk,
-                                             void* stream) {
+                                             const void* attn_drop, int drop_site, void* stream) {
     if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
-                     0, dq, dx_scatter, dbk, mma_rows};
+                     0, dq, dx_scatter, dbk, mma_rows, (const ScannDropCtl*)attn_drop, drop_site};
     if (tile_stride == 64) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     else scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     return scann_check_launch("scann_la_backward_noupdate_tc");

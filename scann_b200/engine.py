@@ -146,6 +146,13 @@ class Engine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def _adrop(self, training: bool, layer: int):
+        """(control block, site) of the attention-probability Dropout(0.05) of ``use_drop`` models
+        (attention.py:115-116,191-192); (NULL, 0) outside training."""
+        if training and self.spec.use_drop:
+            return _p(self.adam_scalars, 12), 64 + layer
+        return 0, 0
+
     def _pdl(self, on: bool) -> None:
         """Programmatic dependent launch for the following kernel launches of this thread.  Only switched
         on between two kernels of this library on the same stream (never right after a memset, a torch
@@ -530,7 +537,7 @@ class Engine:
                     self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c),
                     _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d), self.w(fg),
                     self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
-                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), 0, 0, st),
+                    self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), 0, _p(out), _p(attn), 0, 0, *self._adrop(training, l), st),
                     "la_forward_noupdate_tc")
                 self.launches += 2
                 if sp.use_attn_norm:
@@ -559,7 +566,7 @@ class Engine:
             elif self.tc_la_fwd:
                 save = training and self.tc_la_bwd
                 check(lib.scann_la_forward_tc(self.la_grid, b.stride, b.mma_rows, *la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
-                                              st), "la_forward_tc")
+                                              *self._adrop(training, l), st), "la_forward_tc")
                 self.launches += 1
             else:
                 check(lib.scann_la_forward(self.la_grid, *la_args, st), "la_forward")
@@ -645,7 +652,7 @@ class Engine:
                     self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"), self.w(f"{la}/layer_norm_g/gamma"),
                     self.w(f"{la}/layer_norm_g/beta"), self.w(f"{la}/layer_norm/gamma"),
                     self.w(f"{la}/layer_norm/beta"), _p(g_out), _p(ctxpre), _p(out), _p(attn),
-                    _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, st), "la_forward_tc")
+                    _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, *self._adrop(training, l), st), "la_forward_tc")
                 self.launches += 2
             else:
                 check(lib.scann_la_forward_noupdate_tc(
@@ -653,7 +660,7 @@ class Engine:
                     _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
                     self.w(fg), self.w(f"{la}/filter_geo/bias"), self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"),
                     self.w(f"{la}/layer_norm/gamma"), self.w(f"{la}/layer_norm/beta"), _p(ctxpre), _p(out), _p(attn),
-                    _p(ws["gsave"][l]) if training else 0, _p(ws["kk"][l]) if training else 0, st),
+                    _p(ws["gsave"][l]) if training else 0, _p(ws["kk"][l]) if training else 0, *self._adrop(training, l), st),
                     "la_forward_noupdate_tc")
                 self.launches += 1
             self._ev("la_forward", False)
@@ -785,7 +792,7 @@ class Engine:
                                                _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
                                                _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc), 0,
                                                self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
-                                               self.gw(f"{la}/key/bias"), st), "la_backward_tc")
+                                               self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_tc")
                 self.launches += 2
             else:
                 check(lib.scann_la_backward(self.la_grid, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt),
@@ -918,7 +925,7 @@ class Engine:
                     self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["gsave"][l]), _p(ws["kk"][l]),
                     self.wT(f"{la}/key/kernel"), _p(ws["d_ctx"]), _p(ws["dg"][0]), _p(dq), _p(dx_sc),
-                    self.gw(f"{la}/key/bias"), st), "la_backward_noupdate_tc")
+                    self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_noupdate_tc")
                 check(lib.scann_noupdate_geom_backward(
                     _p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
                     self.w(fg), self.w(f"{la}/filter_geo/bias"), _p(ws["dg"][0]), self.gw(fg),
@@ -933,7 +940,7 @@ class Engine:
                                                _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
                                                _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc), 0,
                                                self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
-                                               self.gw(f"{la}/key/bias"), st), "la_backward_tc")
+                                               self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_tc")
                 self.launches += 2
             self._ev("la_backward", False)
             # next link of the critical path: gradient w.r.t. the layer input x_l, then the tail of layer l-1
@@ -1039,6 +1046,10 @@ class Engine:
         hi[9] = min(int(self.dropout_rate * 4294967296.0), 0xFFFFFFFF)
         hi[10] = np.float32(1.0 / (1.0 - self.dropout_rate)).view(np.uint32)
         hi[11] = 1 if self.train_dropout else 0
+        hi[12] = self.last_drop_seed                       # attention-probability Dropout (use_drop): rate 0.05
+        hi[13] = min(int(0.05 * 4294967296.0), 0xFFFFFFFF)
+        hi[14] = np.float32(1.0 / (1.0 - 0.05)).view(np.uint32)
+        hi[15] = 1 if (self.train_dropout and self.spec.use_drop) else 0
         self.adam_scalars.copy_(h, non_blocking=True)
         self._adam_ev = torch.cuda.Event()
         self._adam_ev.record(torch.cuda.current_stream(self.device))

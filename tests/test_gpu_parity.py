@@ -302,6 +302,50 @@ def test_train_step_with_dropout_matches_oracle_with_the_same_masks():
     assert eng.last_drop_seed != seed
 
 
+def test_attention_dropout_matches_oracle_with_the_same_masks():
+    """use_drop=True: Dropout(0.05) on the attention probabilities (attention.py:115-116,191-192) on top of the
+    rate-0.1 dropouts.  The device mask of (pair row, head) is rebuilt on the host through the pair plan."""
+    from scann_b200 import dropout as dr
+    cfg = get_config("qm9", use_drop=True)
+    cfg["model"]["n_attention"] = 2
+    spec = model_spec(cfg)
+    assert spec.use_drop
+    lay = ParamLayout(spec)
+    arena = lay.randomize_arena(9)
+    inputs, target = make_batch("qm9", 6, B=10)
+    eng = engine_for(spec, arena)
+    eng.train_dropout = True
+    b = eng.load_batch(inputs)
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    seed = eng.last_drop_seed
+    B, M, N = b.B, b.M, b.N
+    masks = {"dense_embed": torch.from_numpy(dr.drop_mask(seed, 0, b.R, 0.1).astype(np.float64).reshape(B, M, 128))}
+    pc, slot = b.pair_c.cpu().numpy(), b.pair_slot.cpu().numpy()
+    rows = np.flatnonzero(pc >= 0)
+    for l in range(spec.n_attention):
+        rn = "residual_norm" if l == 0 else f"residual_norm_{l}"
+        la = "local_attention" if l == 0 else f"local_attention_{l}"
+        masks[rn] = torch.from_numpy(dr.drop_mask(seed, 1 + l, b.R, 0.1).astype(np.float64).reshape(B, M, 128))
+        full = dr.drop_mask(seed, 64 + l, len(pc), 0.05, cols=8)               # [padded pair row, head]
+        am = np.ones((B * M * N, 8))
+        am[slot[rows]] = full[rows]
+        masks[la] = torch.from_numpy(am.reshape(B, M, N, 8).transpose(0, 3, 1, 2).copy())      # [B,H,M,N]
+    assert 0.93 < float((masks["local_attention"] > 0).double().mean()) <= 1.0
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, _, _, grads = O.loss_and_grads(w, inputs, target, l2n, drop_masks=masks, **oracle_kwargs(spec))
+    lv = eng.loss_value(b.B).cpu().numpy()
+    assert abs(lv[0] - loss) <= 1e-5 * abs(loss)
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+
+
 def test_malformed_input_is_reported():
     from scann_b200._abi import ScannAbiError
     spec, lay, arena = small("qm9", L=1)
