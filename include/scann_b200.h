@@ -79,7 +79,15 @@ int scann_pack_batch(const void* csr, long long off_sa, long long off_an, long l
  * saved for backward) may be NULL. */
 int scann_embed_forward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
                         const float* Wr, const float* br, const float* We, const float* be, float* t0, float* x0,
-                        int32_t* status, const void* drop_ctl, void* stream);
+                        int32_t* status, const void* drop_ctl, const float* emb_rows, void* stream);
+/* feature == "cgcnn" (scann_model.py:364-365): embed_atom is Dense(92 -> E) over per-atom feature vectors.
+ * emb_rows [R,E] = atomic92 @ W + b is passed to scann_embed_forward (emb_rows != NULL replaces the lookup). */
+int scann_cgcnn_embed_forward(const float* atomic92, const float* W, const float* b, int R, int F, int E,
+                              float* emb_rows, void* stream);
+int scann_cgcnn_embed_backward(const float* atomic92, const float* emb_rows, const float* ring, int R, int F, int E,
+                               const float* Wr, const float* br, const float* We, const float* t0, const float* dx0,
+                               float* d_cat_ws, float* dWemb, float* dbemb, float* dWr, float* dbr, float* dWe, float* dbe,
+                               const void* drop_ctl, void* stream);
 /* Gradients are ACCUMULATED into d_emb, dWr, dbr, dWe, dbe.  G_ws: (n_atoms+3)*128 floats. */
 int scann_embed_backward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms, const float* emb,
                          const float* Wr, const float* br, const float* We, const float* t0, const float* dx0,

@@ -174,10 +174,12 @@ def forward(w: Dict[str, torch.Tensor], inputs: Dict[str, torch.Tensor], *, n_at
     """
     dm = drop_masks or {}
     dtype = inputs["neighbor_distance"].dtype
-    atomic = inputs["atomic"].long()
     atom_mask = inputs["atom_mask"].to(dtype)
     nmask = inputs["neighbor_mask"].to(dtype)
-    x = w["embed_atom/embeddings"][atomic]                                             # :362
+    if "embed_atom/kernel" in w:                       # feature == "cgcnn": [B,M,92] features, Dense embedding
+        x = dense(inputs["atomic"].to(dtype), w, "embed_atom")                         # :364-365
+    else:
+        x = w["embed_atom/embeddings"][inputs["atomic"].long()]                        # :362
     if use_ring:
         ring = dense(inputs["ring_aromatic"].to(dtype), w, "extra_embed")              # :368
         x = torch.cat([x, ring], -1)                                                   # :371
@@ -245,7 +247,7 @@ def to_torch_inputs(inputs_np: Dict[str, np.ndarray], dtype=torch.float64) -> Di
     out = {}
     for k, v in inputs_np.items():
         v = np.asarray(v)
-        if k in ("atomic", "neighbors"):
+        if k == "neighbors" or (k == "atomic" and v.ndim == 2):
             out[k] = torch.tensor(v.astype(np.int64))
         else:
             out[k] = torch.tensor(v.astype(np.float64)).to(dtype)

@@ -99,5 +99,5 @@ def check_kernel_support(spec: ModelSpec) -> None:
         raise NotImplementedError("kernels are specialised for local_dim = global_dim = dense_out = 128")
     if spec.num_head != N_HEAD:
         raise NotImplementedError("kernels are specialised for num_head = 8")
-    if spec.feature != "atomic":
-        raise NotImplementedError("feature='cgcnn' (92-vector input) is not on the accelerated path yet")
+    if spec.embedding_dim > 128:
+        raise NotImplementedError("embedding_dim must be <= 128")

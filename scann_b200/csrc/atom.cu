@@ -17,7 +17,8 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int32_t* __restric
                                                         const float* __restrict__ br, const float* __restrict__ We,
                                                         const float* __restrict__ be, float* __restrict__ t0,
                                                         float* __restrict__ x0, int32_t* __restrict__ status,
-                                                        const ScannDropCtl* __restrict__ drop) {
+                                                        const ScannDropCtl* __restrict__ drop,
+                                                        const float* __restrict__ emb_rows) {
     extern __shared__ float s_cat[];   // [EMB_ROWS][Kin]
     const int Kin = E + (ring ? 10 : 0);
     const int r0 = blockIdx.x * EMB_ROWS;
@@ -27,7 +28,9 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int32_t* __restric
         int rr = i / Kin, k = i % Kin, r = r0 + rr;
         float v = 0.f;
         if (r < R) {
-            if (k < E) {
+            if (k < E && emb_rows) {
+                v = emb_rows[(size_t)r * E + k];            // feature == "cgcnn": Dense(92 -> E) output of this row
+            } else if (k < E) {
                 int z = atomic[r];
                 if (z < 0 || z >= n_atoms) { atomicOr(status, SCANN_ERR_BAD_ATOMIC); z = 0; }
                 v = emb[(size_t)z * E + k];
@@ -146,6 +149,94 @@ __global__ void __launch_bounds__(128) embed_bwd_final_kernel(int E, int n_atoms
         __syncthreads();
         if (n == 0) *dst += s_red[0] + s_red[1] + s_red[2] + s_red[3];
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature == "cgcnn" (scann_model.py:364-365): embed_atom = Dense(92 -> E) over per-atom feature vectors instead
+// of an Embedding lookup.  Small general kernels (this variant is rare; nothing here is performance critical).
+// ---------------------------------------------------------------------------------------------
+#define CG_KMAX 144        // embedding_dim (<= 128) + 10 ring columns, rounded up: row stride of d_cat
+// out[r, k] = sum_f A[r, f] W[f, k] + b[k]      (A [R,F], W [F,K], K <= 128)
+__global__ void __launch_bounds__(128) small_dense_fwd_kernel(const float* __restrict__ A, const float* __restrict__ W,
+                                                              const float* __restrict__ b, int R, int F, int K,
+                                                              float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    const int k = threadIdx.x;
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        if (k >= K) continue;
+        float acc = b ? b[k] : 0.f;
+        for (int f = 0; f < F; ++f) acc = fmaf(A[(size_t)r * F + f], W[(size_t)f * K + k], acc);
+        out[(size_t)r * K + k] = acc;
+    }
+}
+// General embedding backward, stage 1 (32 rows per CTA): d_t0 = dx0 * dropout * swish'(t0);
+// dWe[k, :] += cat[r, k] d_t0[r, :], dbe += d_t0, d_cat[r, k] = <d_t0[r, :], We[k, :]>  with
+// cat[r, :] = [emb_rows[r, :E] | br + ring[r] @ Wr].
+__global__ void __launch_bounds__(128) embed_bwd_rows_kernel(const float* __restrict__ emb_rows,
+                                                             const float* __restrict__ ring, int R, int E,
+                                                             const float* __restrict__ Wr, const float* __restrict__ br,
+                                                             const float* __restrict__ We, const float* __restrict__ t0,
+                                                             const float* __restrict__ dx0, float* __restrict__ d_cat,
+                                                             float* __restrict__ dWe, float* __restrict__ dbe,
+                                                             const ScannDropCtl* __restrict__ drop) {
+    __shared__ float s_dt[32][SCANN_D];
+    __shared__ float s_cat[32][CG_KMAX];
+    const int n = threadIdx.x, Kin = E + (ring ? 10 : 0);
+    const int r0 = blockIdx.x * 32;
+    float bsum = 0.f;
+    for (int i = 0; i < 32; ++i) {
+        const int r = r0 + i;
+        float d = 0.f;
+        if (r < R)
+            d = dx0[(size_t)r * SCANN_D + n] * drop_mult(drop, 0u, (uint32_t)r * SCANN_D + n) *
+                swish_grad_f(t0[(size_t)r * SCANN_D + n]);
+        s_dt[i][n] = d;
+        bsum += d;
+        for (int k = n; k < Kin; k += 128) {
+            float c = 0.f;
+            if (r < R) {
+                if (k < E) c = emb_rows[(size_t)r * E + k];
+                else { const int kk = k - E; c = br[kk] + ring[(size_t)r * 2] * Wr[kk] + ring[(size_t)r * 2 + 1] * Wr[10 + kk]; }
+            }
+            s_cat[i][k] = c;
+        }
+    }
+    __syncthreads();
+    atomicAdd(dbe + n, bsum);
+    for (int k = 0; k < Kin; ++k) {
+        float acc = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) acc = fmaf(s_cat[i][k], s_dt[i][n], acc);
+        atomicAdd(dWe + (size_t)k * SCANN_D + n, acc);
+    }
+    // d_cat[r, k]: thread k, loop over the CTA's rows
+    for (int k = n; k < Kin; k += 128) {
+        for (int i = 0; i < 32 && r0 + i < R; ++i) {
+            float acc = 0.f;
+            for (int c = 0; c < SCANN_D; ++c) acc = fmaf(s_dt[i][c], We[(size_t)k * SCANN_D + c], acc);
+            d_cat[(size_t)(r0 + i) * CG_KMAX + k] = acc;
+        }
+    }
+}
+// stage 2: dW_emb[f, k] += sum_r A92[r, f] d_cat[r, k] ; db_emb[k] += sum_r d_cat[r, k] ; ring Dense likewise.
+// grid = F + 1 (+ 3 with ring) CTAs, 128 threads (k).
+__global__ void __launch_bounds__(128) embed_bwd_cols_kernel(const float* __restrict__ A92, const float* __restrict__ ring,
+                                                            int R, int F, int E, const float* __restrict__ d_cat,
+                                                            float* __restrict__ dWemb, float* __restrict__ dbemb,
+                                                            float* __restrict__ dWr, float* __restrict__ dbr) {
+    const int k = threadIdx.x, f = blockIdx.x;
+    float acc = 0.f;
+    if (f <= F) {
+        if (k >= E) return;
+        for (int r = 0; r < R; ++r) acc = fmaf(f < F ? A92[(size_t)r * F + f] : 1.0f, d_cat[(size_t)r * CG_KMAX + k], acc);
+        if (f < F) dWemb[(size_t)f * E + k] += acc; else dbemb[k] += acc;
+    } else {
+        const int c = f - F - 1;          // 0, 1: ring rows of Wr ; 2: br
+        if (k >= 10) return;
+        for (int r = 0; r < R; ++r) acc = fmaf(c < 2 ? ring[(size_t)r * 2 + c] : 1.0f, d_cat[(size_t)r * CG_KMAX + E + k], acc);
+        if (c < 2) dWr[c * 10 + k] += acc; else dbr[k] += acc;
     }
 }
 
@@ -630,11 +721,11 @@ __global__ void __launch_bounds__(256) transpose_blocks_kernel(const float* __re
 extern "C" int scann_embed_forward(const int32_t* atomic, const float* ring, int R, int E, int n_atoms,
                                    const float* emb, const float* Wr, const float* br, const float* We,
                                    const float* be, float* t0, float* x0, int32_t* status, const void* drop_ctl,
-                                   void* stream) {
+                                   const float* emb_rows, void* stream) {
     int Kin = E + (ring ? 10 : 0);
     size_t smem = (size_t)EMB_ROWS * Kin * sizeof(float);
     scann_launch(embed_fwd_kernel, dim3((R + EMB_ROWS - 1) / EMB_ROWS), dim3(128), smem, stream, atomic, ring, R, E, n_atoms,
-                 emb, Wr, br, We, be, t0, x0, status, (const ScannDropCtl*)drop_ctl);
+                 emb, Wr, br, We, be, t0, x0, status, (const ScannDropCtl*)drop_ctl, emb_rows);
     return scann_check_launch("scann_embed_forward");
 }
 
@@ -651,6 +742,30 @@ extern "C" int scann_embed_backward(const int32_t* atomic, const float* ring, in
     embed_bwd_final_kernel<<<64, 128, 0, st>>>(E, n_atoms, ring ? 1 : 0, emb, Wr, br, We, G_ws, d_emb, dWr, dbr, dWe,
                                                dbe);
     return scann_check_launch("scann_embed_backward");
+}
+
+// feature == "cgcnn": emb_rows [R,E] = atomic92 [R,92] @ embed_atom/kernel + bias (feeds scann_embed_forward).
+extern "C" int scann_cgcnn_embed_forward(const float* atomic92, const float* W, const float* b, int R, int F, int E,
+                                         float* emb_rows, void* stream) {
+    if (E > 128 || E < 1 || F < 1) { scann_set_error("cgcnn_embed_forward: bad sizes F=%d E=%d", F, E); return 1; }
+    if (R <= 0) return 0;
+    scann_launch(small_dense_fwd_kernel, dim3(R < 592 ? R : 592), dim3(128), 0, stream, atomic92, W, b, R, F, E, emb_rows);
+    return scann_check_launch("scann_cgcnn_embed_forward");
+}
+
+// Backward of the cgcnn embedding path: gradients of dense_embed (dWe, dbe), embed_atom Dense (dWemb, dbemb) and
+// extra_embed (dWr, dbr, nullable) ACCUMULATED; d_cat_ws: R*144 floats of workspace.
+extern "C" int scann_cgcnn_embed_backward(const float* atomic92, const float* emb_rows, const float* ring, int R, int F,
+                                          int E, const float* Wr, const float* br, const float* We, const float* t0,
+                                          const float* dx0, float* d_cat_ws, float* dWemb, float* dbemb, float* dWr,
+                                          float* dbr, float* dWe, float* dbe, const void* drop_ctl, void* stream) {
+    if (E > 128) { scann_set_error("cgcnn_embed_backward: embedding width %d too large", E); return 1; }
+    if (R <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    embed_bwd_rows_kernel<<<(R + 31) / 32, 128, 0, st>>>(emb_rows, ring, R, E, Wr, br, We, t0, dx0, d_cat_ws, dWe, dbe,
+                                                       (const ScannDropCtl*)drop_ctl);
+    embed_bwd_cols_kernel<<<F + 1 + (ring ? 3 : 0), 128, 0, st>>>(atomic92, ring, R, F, E, d_cat_ws, dWemb, dbemb, dWr, dbr);
+    return scann_check_launch("scann_cgcnn_embed_backward");
 }
 
 extern "C" int scann_geom_init_forward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c, const float* pair_d,

@@ -230,7 +230,9 @@ class Engine:
                 t = t != 0
             dst.copy_(t.reshape(dst.shape), non_blocking=True)
 
-        items = [("atomic", inputs["atomic"]), ("atom_mask", inputs["atom_mask"]), ("nbr", nb), ("nmask", nmask_in),
+        cg = self.spec.feature == "cgcnn"         # "atomic" then holds [B,M,92] feature vectors (datagenerator.py:109-110)
+        items = [("atomic92" if cg else "atomic", inputs["atomic"]), ("atom_mask", inputs["atom_mask"]), ("nbr", nb),
+                 ("nmask", nmask_in),
                  ("weight", inputs["neighbor_weight"]), ("dist", inputs["neighbor_distance"])]
         if self.spec.use_ring:
             items.append(("ring", inputs["ring_aromatic"]))
@@ -339,6 +341,8 @@ class Engine:
                   ("target", torch.float32, B)]
         if self.spec.use_ring:
             fields.append(("ring", torch.float32, b.R * 2))
+        if self.spec.feature == "cgcnn":
+            fields.append(("atomic92", torch.float32, b.R * 92))
         off, offs = 0, {}
         for name, dt, n in fields:
             offs[name] = off
@@ -496,13 +500,22 @@ class Engine:
             raise NotImplementedError("training of g_update=False models needs the tensor-core engine "
                                       "(SCANN_ENGINE=tc, SCANN_CHAIN=1)")
         ring = sp.use_ring
+        cg = sp.feature == "cgcnn"
         self._pdl(False)
+        if cg:
+            if "emb_rows" not in ws:
+                ws["emb_rows"] = torch.empty(R, E, dtype=torch.float32, device=self.device)
+                ws["d_cat"] = torch.empty(R, 144, dtype=torch.float32, device=self.device)
+            check(lib.scann_cgcnn_embed_forward(_p(b.atomic92), self.w("embed_atom/kernel"), self.w("embed_atom/bias"),
+                                                R, 92, E, _p(ws["emb_rows"]), st), "cgcnn_embed_forward")
+            self.launches += 1
         check(lib.scann_embed_forward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
-                                      self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
+                                      0 if cg else self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
                                       self.w("extra_embed/bias") if ring else 0,
                                       self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
                                       _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status),
-                                      _p(self.adam_scalars, 8) if training else 0, st), "embed_forward")
+                                      _p(self.adam_scalars, 8) if training else 0, _p(ws["emb_rows"]) if cg else 0, st),
+              "embed_forward")
         self.launches += 1
         self._pdl(True)
         if sp.g_update and "geom_init" not in self._skip:
@@ -849,6 +862,20 @@ class Engine:
         self._pdl(False)
         E = sp.embedding_dim
         ring = sp.use_ring
+        if sp.feature == "cgcnn":
+            check(lib.scann_cgcnn_embed_backward(
+                _p(b.atomic92), _p(ws["emb_rows"]), _p(b.ring) if ring else 0, R, 92, E,
+                self.w("extra_embed/kernel") if ring else 0, self.w("extra_embed/bias") if ring else 0,
+                self.w("dense_embed/kernel"), _p(ws["t0"]), _p(dx), _p(ws["d_cat"]), self.gw("embed_atom/kernel"),
+                self.gw("embed_atom/bias"), self.gw("extra_embed/kernel") if ring else 0,
+                self.gw("extra_embed/bias") if ring else 0, self.gw("dense_embed/kernel"), self.gw("dense_embed/bias"),
+                _p(self.adam_scalars, 8), st), "cgcnn_embed_backward")
+            self.launches += 2
+            if side is not main:
+                ev = torch.cuda.Event()
+                ev.record(side)
+                main.wait_event(ev)
+            return
         check(lib.scann_embed_backward(_p(b.atomic), _p(b.ring) if ring else 0, R, E, sp.n_atoms,
                                        self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
                                        self.w("extra_embed/bias") if ring else 0,

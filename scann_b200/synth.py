@@ -51,8 +51,16 @@ SHAPES: Dict[str, Shape] = {
 }
 
 
+def cgcnn_table(n_species: int = 100, seed: int = 1234) -> np.ndarray:
+    """Stand-in for the reference's ``atomic_features`` JSON (scann/utils/dataset.py): one 92-vector per atomic
+    number (0/1 entries like the CGCNN one-hot blocks); row 0 (padding) is all zeros."""
+    t = (np.random.default_rng(seed).random((n_species, 92)) < 0.15).astype(np.float32)
+    t[0] = 0.0
+    return t
+
+
 def make_batch(shape: Shape | str, seed: int = 0, B: Optional[int] = None, use_ring: bool = False,
-               full: bool = False) -> Tuple[Dict[str, np.ndarray], np.ndarray]:
+               full: bool = False, feature: str = "atomic") -> Tuple[Dict[str, np.ndarray], np.ndarray]:
     """Return ``(inputs, target)`` like ``DataIterator.__getitem__``.
 
     ``full=True`` fills every atom / neighbour slot (the upper-bound shape BASELINE.md
@@ -115,6 +123,8 @@ def make_batch(shape: Shape | str, seed: int = 0, B: Optional[int] = None, use_r
     }
     if use_ring:
         inputs["ring_aromatic"] = (rng.integers(0, 2, size=(B, M, 2)) * (atomic != 0)[..., None]).astype(np.int32)
+    if feature == "cgcnn":          # DataIterator replaces the atomic numbers by their feature vectors (:109-110)
+        inputs["atomic"] = cgcnn_table()[atomic]
     target = rng.standard_normal(B).astype(np.float32)
     return inputs, target
 

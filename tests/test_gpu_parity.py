@@ -346,6 +346,37 @@ def test_attention_dropout_matches_oracle_with_the_same_masks():
         assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
 
 
+@pytest.mark.parametrize("cfg_name,shape", [("qm9", "qm9"), ("mp2018", "mp2018")])
+def test_cgcnn_feature_embedding_forward_and_gradients(cfg_name, shape):
+    """feature='cgcnn' (scann_model.py:334-335,364-365): ``atomic`` holds [B,M,92] feature vectors and embed_atom is a
+    Dense layer; forward, loss and every gradient against the oracle."""
+    cfg = get_config(cfg_name, feature="cgcnn")
+    cfg["model"]["n_attention"] = 2
+    spec = model_spec(cfg)
+    assert spec.feature == "cgcnn"
+    lay = ParamLayout(spec)
+    assert "embed_atom/kernel" in lay and lay["embed_atom/kernel"].shape == (92, spec.embedding_dim)
+    arena = lay.randomize_arena(13)
+    inputs, target = make_batch(shape, 8, B=5, feature="cgcnn")
+    assert inputs["atomic"].shape[-1] == 92
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, y_ref, ga_ref, grads = O.loss_and_grads(w, inputs, target, l2n, **oracle_kwargs(spec))
+    eng, b, y, ga = run_forward(spec, arena, inputs)
+    assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= TOL_OUT
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+    lv = eng.loss_value(b.B).cpu().numpy()
+    assert abs(lv[0] - float(loss)) <= 1e-5 * abs(float(loss))
+
+
 def test_malformed_input_is_reported():
     from scann_b200._abi import ScannAbiError
     spec, lay, arena = small("qm9", L=1)
