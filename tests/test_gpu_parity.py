@@ -34,6 +34,14 @@ def engine_for(spec, arena):
     return Engine(spec, arena)
 
 
+def needs_default_engine(eng):
+    """Dropout, g_update=False training and the 64-row tile layout exist only in the default engine (tensor-core
+    kernels, chained Dense launches, batched weight gradients); the SCANN_ENGINE / SCANN_CHAIN / SCANN_WGRAD_BATCH
+    fallbacks refuse them loudly."""
+    if not (eng.use_chain and eng.use_wgrad_batch and eng.tc_la_bwd):
+        pytest.skip("needs the default tensor-core engine")
+
+
 def run_forward(spec, arena, inputs):
     eng = engine_for(spec, arena)
     b = eng.load_batch(inputs)
@@ -139,6 +147,8 @@ def test_both_tile_layouts_match_golden(monkeypatch, stride, balance):
     cfg, spec, lay, arena, inputs, target = build_case(name)
     z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
     eng = engine_for(spec, arena)
+    if stride == 64:
+        needs_default_engine(eng)
     b = eng.load_batch(inputs)
     assert b.stride == stride
     y, ga = eng.forward(b)
@@ -243,6 +253,7 @@ def test_scann_without_geometry_update_and_ring_features():
     eng, b, y, ga = run_forward(spec, arena, inputs)
     assert rel(y, y_ref.ravel()) <= TOL_OUT
     assert rel(ga, ga_ref[..., 0]) <= TOL_OUT
+    needs_default_engine(eng)
     # train step of the same variant: every gradient against the oracle's reverse-mode autodiff
     w = lay.to_dict(arena)
     l2n = [e.name for e in lay if e.l2]
@@ -268,6 +279,7 @@ def test_train_step_with_dropout_matches_oracle_with_the_same_masks():
     spec, lay, arena = small("qm9", L=3, seed=7)
     inputs, target = make_batch("qm9", 5, B=12)
     eng = engine_for(spec, arena)
+    needs_default_engine(eng)
     eng.train_dropout = True
     b = eng.load_batch(inputs)
     eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
@@ -314,6 +326,7 @@ def test_attention_dropout_matches_oracle_with_the_same_masks():
     arena = lay.randomize_arena(9)
     inputs, target = make_batch("qm9", 6, B=10)
     eng = engine_for(spec, arena)
+    needs_default_engine(eng)
     eng.train_dropout = True
     b = eng.load_batch(inputs)
     eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
