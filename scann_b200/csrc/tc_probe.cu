@@ -51,13 +51,14 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float* __restric
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t d_tmem = tmem, a_tmem = tmem + 128, d2_tmem = tmem + 256;
-    const int np = nprod == 4 ? 3 : nprod;
+    const int np = nprod >= 4 ? 3 : nprod;       // nprod 5: one accumulator, the two correction products FIRST
     const bool a_mn = layout == 1, b_mn = layout == 1;
     const uint32_t idesc = tc_idesc_tf32(128, 128, a_mn, b_mn);
     uint32_t phase = 0;
     for (int p = 0; p < np; ++p) {
-        const int pa = nprod == 1 ? 0 : (p == 1 ? 2 : 1);     // hi, lo, hi
-        const int pw = nprod == 1 ? 0 : (p == 2 ? 2 : 1);     // hi, hi, lo
+        int pa = nprod == 1 ? 0 : (p == 1 ? 2 : 1);     // hi, lo, hi
+        int pw = nprod == 1 ? 0 : (p == 2 ? 2 : 1);     // hi, hi, lo
+        if (nprod == 5) { pa = p == 0 ? 2 : 1; pw = p == 1 ? 2 : 1; }      // (lo,hi), (hi,lo), (hi,hi)
         if (layout == 3) {
             // A -> tensor memory, thread = row, 128 fp32 columns
             const int row = tid;
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float* __restric
 
 // Diagnostic entry point: D[128,128] = op(A)[128,128] @ op(W)[128,128] on the tensor cores.
 extern "C" int scann_tc_probe(const float* A, const float* W, float* D, int layout, int nprod, void* stream) {
-    if (layout < 0 || layout > 3 || (nprod != 1 && nprod != 3 && nprod != 4)) { scann_set_error("tc_probe: bad arguments"); return 1; }
+    if (layout < 0 || layout > 3 || (nprod != 1 && nprod != 3 && nprod != 4 && nprod != 5)) { scann_set_error("tc_probe: bad arguments"); return 1; }
     size_t smem = 2 * TC_TILE_BYTES + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { scann_set_error("tc_probe: %s", cudaGetErrorString(e)); return 1; }
