@@ -78,12 +78,16 @@ __device__ __forceinline__ void issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, uin
                                              uint32_t t_dc, uint64_t* bar, int nrows) {
     const uint32_t idesc = tc_idesc_tf32(128, nrows, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
+    // ONE accumulator, the two correction products first: the small terms are summed among themselves before the
+    // large hi*hi terms arrive, which is as accurate as a separate correction accumulator (tc_probe nprod 5:
+    // 3.7e-6 vs 3.4e-6; main-first 1.5e-5) and halves the accumulator columns and the read-back
+    (void)t_dc;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, true);
     tc_commit(bar);
 }
 
@@ -97,12 +101,12 @@ __device__ __forceinline__ void tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uint8
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         if (rbase + h * 16 >= nrows) break;              // warp-uniform: rows beyond nrows are never valid
-        float m[16], c[16];
+        float m[16];
+        (void)t_dc;
         tmem_ld16(t_dm + lane_base + rbase + h * 16, m);
-        tmem_ld16(t_dc + lane_base + rbase + h * 16, c);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(S + tc_off(rbase + h * 16 + q, n)) = m[q] + c[q] + b;
+        for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(S + tc_off(rbase + h * 16 + q, n)) = m[q] + b;
     }
 }
 

@@ -53,12 +53,14 @@ __device__ __forceinline__ void b_issue_3xtf32(uint32_t t_whi, uint32_t t_wlo, u
                                                uint32_t t_dc, uint64_t* bar, int nrows) {
     const uint32_t idesc = tc_idesc_tf32(128, nrows, false, false);
     const uint64_t dh = tc_desc_kmajor(xh, 0), dl = tc_desc_kmajor(xl, 0);
+    // one accumulator, correction products first (see la_tc.cu)
+    (void)t_dc;
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, ks != 0);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
 #pragma unroll
-    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
+    for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, true);
     tc_commit(bar);
 }
 
@@ -68,12 +70,12 @@ __device__ __forceinline__ void b_tmem_to_rows(uint32_t t_dm, uint32_t t_dc, uin
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         if (rbase + h * 16 >= nrows) break;              // warp-uniform: rows beyond nrows are never valid
-        float m[16], c[16];
+        float m[16];
+        (void)t_dc;
         tmem_ld16(t_dm + lane_base + rbase + h * 16, m);
-        tmem_ld16(t_dc + lane_base + rbase + h * 16, c);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(S + tc_off(rbase + h * 16 + q, n)) = m[q] + c[q];
+        for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(S + tc_off(rbase + h * 16 + q, n)) = m[q];
     }
 }
 
