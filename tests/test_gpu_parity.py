@@ -390,6 +390,31 @@ def test_cgcnn_feature_embedding_forward_and_gradients(cfg_name, shape):
     assert abs(lv[0] - float(loss)) <= 1e-5 * abs(float(loss))
 
 
+@pytest.mark.parametrize("N,nbrs", [(40, (1, 40)), (100, (30, 100))])
+def test_many_neighbours_use_the_128_row_tile_layout(N, nbrs):
+    """Atoms with more than 32 neighbours (dense periodic cells) fall back to 128-row tile slots / one tile stream
+    per CTA; forward and gradients must still match the oracle."""
+    from scann_b200.synth import Shape
+    shape = Shape("dense_cell", 4, 12, N, (5, 12), (1, 6, 7, 8, 9), None, nbrs, (0.9, 4.0), (0.4, 3.0))
+    spec, lay, arena = small("qm9", L=2, seed=17)
+    inputs, target = make_batch(shape, 2, B=4)
+    w = lay.to_dict(arena)
+    l2n = [e.name for e in lay if e.l2]
+    loss, y_ref, ga_ref, grads = O.loss_and_grads(w, inputs, target, l2n, **oracle_kwargs(spec))
+    eng, b, y, ga = run_forward(spec, arena, inputs)
+    assert b.stride == 128
+    assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= TOL_OUT
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = lay.to_dict(eng.grad_out.cpu().numpy())
+    gmax = max(np.abs(v).max() for v in grads.values())
+    for e in lay:
+        ref = grads[e.name]
+        err = np.abs(g[e.name].astype(np.float64) - ref).max()
+        assert err <= TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), e.name
+
+
 def test_malformed_input_is_reported():
     from scann_b200._abi import ScannAbiError
     spec, lay, arena = small("qm9", L=1)
