@@ -31,18 +31,6 @@
 #define LTC_WARPS 16
 #define LTC_RPW 8                          // rows per warp in the row-wise epilogue (= TR / warps per group)
 
-template <int NG>
-struct LaGroups {
-    static constexpr int TR = SCANN_TILE / NG;                     // pair rows per tile (MMA N extent)
-    static constexpr int WG = LTC_WARPS / NG;                      // warps per group
-    static constexpr int GT = LTC_THREADS / NG;                    // threads per group
-    static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;   // bytes of one K-major image of TR rows
-};
-// barrier among the GT threads of warp group g (barrier 0 stays __syncthreads)
-__device__ __forceinline__ void group_sync(int g, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
-}
-
 // phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks: development aid
 __device__ long long g_dbg_clk[32];
 #define DBG_CLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_clk[i] = clock64(); } while (0)

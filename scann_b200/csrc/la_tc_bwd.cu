@@ -18,18 +18,6 @@
 #define LTC_WARPS 16
 #define LTC_RPW 8
 
-// warp groups: see la_tc.cu
-template <int NG>
-struct LaGroups {
-    static constexpr int TR = SCANN_TILE / NG;
-    static constexpr int WG = LTC_WARPS / NG;
-    static constexpr int GT = LTC_THREADS / NG;
-    static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;
-};
-__device__ __forceinline__ void group_sync(int g, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
-}
-
 // ---- helpers shared with la_tc.cu (kept static to this translation unit) ----
 __device__ __forceinline__ void b_weightT_to_tmem(const float* __restrict__ W, uint32_t t_hi, uint32_t t_lo, int warp,
                                                   int lane) {

@@ -161,3 +161,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+// ---- warp groups of the local-attention kernels (la_tc.cu, la_tc_bwd.cu) ----
+// The 16 warps of a CTA split into NG independent groups; each group owns its own tile stream, operand images,
+// mbarrier and accumulator columns and synchronises with a named barrier (see the header of la_tc.cu).
+#define LTC_GROUP_THREADS 512
+#define LTC_GROUP_WARPS 16
+template <int NG>
+struct LaGroups {
+    static constexpr int TR = 128 / NG;                     // pair rows per tile (MMA N extent)
+    static constexpr int WG = LTC_GROUP_WARPS / NG;                      // warps per group
+    static constexpr int GT = LTC_GROUP_THREADS / NG;                    // threads per group
+    static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;   // bytes of one K-major image of TR rows
+};
+// barrier among the GT threads of warp group g (barrier 0 stays __syncthreads)
+__device__ __forceinline__ void group_sync(int g, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
+
