@@ -112,6 +112,32 @@ def pack_padded(csr: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     return out
 
 
+def padded_to_csr(inputs: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """Inverse of ``pack_padded`` for batches whose valid atoms / neighbour slots are prefixes (what
+    DataIterator.__getitem__ produces): padded dict -> CSR batch for ``Engine.load_batch_csr``."""
+    am = inputs["atom_mask"][..., 0].astype(bool)
+    nm = inputs["neighbor_mask"].astype(bool)
+    B, M, N = nm.shape
+    n_at = am.sum(1)
+    if not (np.array_equal(am, np.arange(M)[None, :] < n_at[:, None])):
+        raise ValueError("valid atoms must be a prefix of every structure")
+    n_nb = nm.sum(2)
+    if not np.array_equal(nm, np.arange(N)[None, None, :] < n_nb[..., None]):
+        raise ValueError("valid neighbour slots must be a prefix of every atom")
+    sa = np.zeros(B + 1, np.int32)
+    np.cumsum(n_at, out=sa[1:])
+    cnt = n_nb[am]
+    an = np.zeros(len(cnt) + 1, np.int32)
+    np.cumsum(cnt, out=an[1:])
+    sel = nm & am[..., None]
+    csr = {"struct_atom_off": sa, "atom_nbr_off": an, "z": inputs["atomic"][am].astype(np.int32),
+           "nbr_idx": inputs["neighbors"][sel].astype(np.int32), "nbr_w": inputs["neighbor_weight"][sel].astype(np.float32),
+           "nbr_d": inputs["neighbor_distance"][sel].astype(np.float32), "M": M, "N": N}
+    if "ring_aromatic" in inputs:
+        csr["ring"] = inputs["ring_aromatic"][am].astype(np.int32)
+    return csr
+
+
 def synthetic_ragged(n_struct: int, seed: int = 0, max_atoms: int = 29, max_nbr: int = 16, use_ring: bool = False):
     """Random data in the reference's nested-list format (for tests and benchmarks)."""
     rng = np.random.default_rng(seed)
