@@ -112,6 +112,11 @@ class Engine:
         self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "64"))
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
+        # pipelined input feed (facade fit): a step's host->device copy runs on its own stream into a staging
+        # blob while the previous step computes; the main stream only does a device-to-device hand-over
+        self.overlap_h2d = False
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._loss_ring: list = []
         # programmatic dependent launch along the forward / backward kernel chain (include/scann_b200.h)
         self.use_pdl = os.environ.get("SCANN_PDL", "1") == "1"
         # development aid: kernels to leave out of the step (results are then meaningless; only the timing
@@ -312,9 +317,21 @@ class Engine:
         host = b.csr_pin.numpy()
         for name, a in segs:
             host[offs[name]:offs[name] + a.nbytes] = a.view(np.uint8).reshape(-1)
-        b.csr_dev[:off].copy_(b.csr_pin[:off], non_blocking=True)
-        b.csr_event = torch.cuda.Event()
-        b.csr_event.record(torch.cuda.current_stream(self.device))
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap_h2d:
+            # the copy overlaps the previous step: it only has to wait for that step's scann_pack_batch
+            cs = self.copy_stream
+            if getattr(b, "csr_packed", None) is not None:
+                cs.wait_event(b.csr_packed)
+            with torch.cuda.stream(cs):
+                b.csr_dev[:off].copy_(b.csr_pin[:off], non_blocking=True)
+                b.csr_event = torch.cuda.Event()
+                b.csr_event.record(cs)
+            main.wait_event(b.csr_event)
+        else:
+            b.csr_dev[:off].copy_(b.csr_pin[:off], non_blocking=True)
+            b.csr_event = torch.cuda.Event()
+            b.csr_event.record(main)
         b.h2d_bytes = off
         b.host_dirty = False
         check(lib.scann_pack_batch(_p(b.csr_dev), offs["sa"], offs["an"], offs["z"], offs["idx"], offs["w"], offs["d"],
@@ -322,6 +339,9 @@ class Engine:
                                    _p(b.nbr), _p(b.nmask), _p(b.weight), _p(b.dist), _p(b.ring), _p(b.target),
                                    self._stream()), "pack_batch")
         self.launches += 1
+        if self.overlap_h2d:
+            b.csr_packed = torch.cuda.Event()
+            b.csr_packed.record(main)
         if plan:
             self._plan(b)
         return b
@@ -398,11 +418,31 @@ class Engine:
 
     def _flush_host(self, b: Batch) -> None:
         """One host->device copy of everything load_batch / set_target staged in the pinned mirror."""
-        if b.host_dirty:
+        if not b.host_dirty:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self.overlap_h2d and not torch.cuda.is_current_stream_capturing():
+            # copy stream: pinned mirror -> staging blob (overlaps the previous step's kernels); main stream:
+            # staging blob -> the blob the captured graph reads (a ~1 us device copy)
+            if getattr(b, "blob_stage", None) is None:
+                b.blob_stage = torch.empty_like(b.blob)
+                b.stage_event = None
+            cs = self.copy_stream
+            if b.stage_event is not None:
+                cs.wait_event(b.stage_event)        # the previous hand-over out of the staging blob has finished
+            with torch.cuda.stream(cs):
+                b.blob_stage.copy_(b.blob_pin, non_blocking=True)
+                b.pin_event = torch.cuda.Event()
+                b.pin_event.record(cs)
+            main.wait_event(b.pin_event)
+            b.blob.copy_(b.blob_stage, non_blocking=True)
+            b.stage_event = torch.cuda.Event()
+            b.stage_event.record(main)
+        else:
             b.blob.copy_(b.blob_pin, non_blocking=True)
             b.pin_event = torch.cuda.Event()
-            b.pin_event.record(torch.cuda.current_stream(self.device))
-            b.host_dirty = False
+            b.pin_event.record(main)
+        b.host_dirty = False
 
     def _plan(self, b: Batch) -> None:
         self._flush_host(b)
@@ -1088,6 +1128,20 @@ class Engine:
                                    L2_COEF, _p(self.loss_out), self._stream()), "loss_value")
         self.launches += 1
         return self.loss_out
+
+    def loss_value_async(self, batch_global: int, slots: int = 8):
+        """``loss_value`` followed by an asynchronous device->host copy into a ring of pinned slots: returns
+        ``(pinned tensor, event)``; the values are valid once the event has completed.  A slot is reused after
+        ``slots`` further calls (read it before)."""
+        lv = self.loss_value(batch_global)
+        if len(self._loss_ring) < slots:
+            self._loss_ring.append(torch.zeros(4, dtype=torch.float32).pin_memory())
+        self._loss_pos = (getattr(self, "_loss_pos", -1) + 1) % slots
+        pin = self._loss_ring[self._loss_pos]
+        pin.copy_(lv, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return pin, ev
 
     def train_step(self, b: Batch, target, lr: float, allreduce=None, batch_global: Optional[int] = None,
                    apply: bool = True, want_grads: bool = False, replan: bool = False) -> None:

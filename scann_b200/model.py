@@ -95,6 +95,23 @@ class ScannKerasModel:
     def _lr_now(self) -> float:
         return float(self.lr(self.engine.step_count)) if callable(self.lr) else float(self.lr)
 
+    def _train_on_batch_async(self, inputs: Dict[str, object], y_true):
+        """``train_on_batch`` without the blocking read: the step is queued and ``(pinned [loss, rmse, mae, _],
+        event)`` is returned (Engine.loss_value_async).  ``fit`` uses it to keep one step queued behind the running
+        one: the next batch's host->device copy overlaps the kernels, the losses are read at the end of the epoch
+        -- Keras' fit does the same with its asynchronous metric tensors."""
+        eng = self.engine
+        eng.train_dropout = bool(self.dropout) and eng.use_chain and eng.use_wgrad_batch
+        if "struct_atom_off" in inputs:
+            b = eng.load_batch_csr(inputs, target=y_true, plan=False)
+            y_true = b.target
+        else:
+            b = eng.load_batch(inputs, plan=False)
+        batch_global = b.B * self.world_size
+        eng.train_step(b, y_true, self._lr_now(), allreduce=self.allreduce, batch_global=batch_global, replan=True)
+        self.last_e2e_bytes = (b.h2d_bytes, 16)
+        return eng.loss_value_async(batch_global)
+
     def train_on_batch(self, inputs: Dict[str, object], y_true, return_dict: bool = False):
         """One Keras ``train_step``: returns the loss (RMSE + l2 penalties) of the batch."""
         eng = self.engine
@@ -135,13 +152,27 @@ class ScannKerasModel:
             for cb in callbacks:
                 if hasattr(cb, "on_epoch_begin"):
                     cb.on_epoch_begin(ep, {})
-            losses, maes = [], []
-            for i in range(len(x)):
-                # iterators that can hand out the ragged CSR form skip the host-side padding altogether
-                inputs, target = x.csr_item(i) if hasattr(x, "csr_item") else x[i]
-                out = self.train_on_batch(inputs, target, return_dict=True)
-                losses.append(out["loss"])
-                maes.append(out["mae"])
+            losses, maes, pending = [], [], []
+
+            def harvest(upto: int) -> None:
+                while len(pending) > upto:
+                    pin, ev = pending.pop(0)
+                    ev.synchronize()
+                    losses.append(float(pin[0]))
+                    maes.append(float(pin[2]))
+
+            eng = self.engine
+            eng.overlap_h2d = True
+            try:
+                for i in range(len(x)):
+                    # iterators that can hand out the ragged CSR form skip the host-side padding altogether
+                    inputs, target = x.csr_item(i) if hasattr(x, "csr_item") else x[i]
+                    pending.append(self._train_on_batch_async(inputs, target))
+                    harvest(4)                    # results older than 4 steps (long finished; ring of 8 slots)
+                harvest(0)
+            finally:
+                eng.overlap_h2d = False
+            eng.check_status()
             hist.add("loss", float(np.mean(losses)))
             hist.add("mae", float(np.mean(maes)))
             if validation_data is not None:

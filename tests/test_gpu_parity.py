@@ -553,6 +553,35 @@ def test_training_shell_fit_checkpoint_evaluate(tmp_path):
     assert fresh.model.get_weights()[0].shape == best.shape
 
 
+@pytest.mark.parametrize("ragged", [False, True])
+def test_pipelined_fit_equals_blocking_train_on_batch(ragged):
+    """fit keeps one step queued behind the running one (copy-stream input feed, losses read at the end of the
+    epoch); the numbers must be those of a loop of blocking train_on_batch calls over the same batches."""
+    from scann_b200.datagenerator import padded_to_csr
+    from scann_b200.model import create_model
+
+    class Iter(list):
+        pass
+
+    cfg = get_config("qm9")
+    cfg["model"]["n_attention"] = 2
+    # batches of different shape classes and a repeated one (its pinned / staging buffers are reused back to back)
+    batches = [make_batch("qm9", s, B=B) for s, B in [(1, 8), (2, 8), (2, 8), (3, 12), (1, 8), (4, 8)]]
+    if ragged:
+        batches = [(padded_to_csr(i), t) for i, t in batches]
+    a, b = create_model(cfg, seed=5), create_model(cfg, seed=5)
+    ref_losses = [a.train_on_batch(i, t, return_dict=True) for i, t in batches]
+    it = Iter(batches)
+    if ragged:
+        it.csr_item = lambda k: batches[k]
+    hist = b.fit(it, epochs=1, verbose=0)
+    assert b.engine.step_count == a.engine.step_count == len(batches)
+    assert abs(hist.history["loss"][0] - np.mean([r["loss"] for r in ref_losses])) <= 1e-5 * abs(hist.history["loss"][0])
+    assert abs(hist.history["mae"][0] - np.mean([r["mae"] for r in ref_losses])) <= 1e-5 * abs(hist.history["mae"][0])
+    pa, pb = a.engine.get_params(), b.engine.get_params()
+    assert rel(pb, pa.astype(np.float64)) <= 1e-5            # weight-gradient atomics: summation order varies
+
+
 @pytest.mark.parametrize("use_ring", [False, True])
 def test_device_batch_assembly_is_bit_exact(use_ring):
     """Ragged CSR batch -> padded device buffers (scann_pack_batch) == DataIterator.__getitem__ of the reference
