@@ -43,6 +43,11 @@ int scann_device_cc(void);
  * prologue (tensor-memory allocation, weights -> tensor memory) overlaps the tail of its stream predecessor.
  * Switch it off for a launch whose stream predecessor is not a kernel of this library (memset, event join). */
 int scann_set_pdl(int on);
+/* Local-attention kernels with four warp groups per CTA (per calling thread; returns the previous mask).  Bit 0
+ * geometry forward, 1 attention forward, 2 attention backward, 3 geometry backward: a set bit makes
+ * scann_la_forward_tc / scann_la_backward_tc run that kernel with four tile streams per SM whenever the pair plan
+ * has tile_stride 64 and mma_rows <= 48 (same results; a scheduling choice, not a numerical one). */
+int scann_set_la_groups4(int mask);
 
 /* ---- batch plan ---------------------------------------------------------------------------
  * Replaces the mask / index bookkeeping the reference does with dense padded tensors:

@@ -23,6 +23,7 @@ PROTOTYPES = {
     "scann_device_sm_count": (ci, []),
     "scann_device_cc": (ci, []),
     "scann_set_pdl": (ci, [ci]),
+    "scann_set_la_groups4": (ci, [ci]),
     "scann_plan_build": (ci, [vp, vp, vp, vp, ci, ci, ci, ci, ci, ci] + [vp] * 13 + [vp, ci, vp, vp]),
     "scann_pack_batch": (ci, [vp] + [C.c_longlong] * 8 + [ci, ci, ci] + [vp] * 8 + [vp]),
     "scann_embed_forward": (ci, [vp, vp, ci, ci, ci] + [vp] * 7 + [vp, vp, vp, vp]),

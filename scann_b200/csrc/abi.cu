@@ -36,6 +36,16 @@ extern "C" int scann_set_pdl(int on) {
     return prev;
 }
 
+// Local-attention kernels with four warp groups per CTA (la_tc.cu, "tc4"): bit mask of the kernels that use them
+// when the pair plan's tiles hold at most 48 rows; per calling thread, returns the previous mask.
+static thread_local int g_la4 = 0;
+int scann_la_tc4_mask() { return g_la4; }
+extern "C" int scann_set_la_groups4(int mask) {
+    int prev = g_la4;
+    g_la4 = mask & 31;      // bit 4 (development): stagger the start of the groups
+    return prev;
+}
+
 extern "C" int scann_version(void) { return 100; }   // 0.1.0
 
 // Number of SMs of the current device, or -1 (with the error string set) when no CUDA device

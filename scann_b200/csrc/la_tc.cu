@@ -110,6 +110,7 @@ struct LaGeomArgs {
     float* g_out;            // [rows,128]
     float* pre_out;          // [rows,128] pre-activation of filter_geo (nullable; saved for backward)
     int mma_rows;            // rows of a tile slot that can hold pairs (multiple of 16): wave-balanced plans fill less
+    int skew;                // tc4 kernels: stagger the start of the warp groups
 };
 
 template <int NG>
@@ -461,6 +462,205 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_fwd_tc_kernel(const La
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================
+// Four warp groups per CTA ("tc4" kernels)
+// =============================================================================================
+// A wave-balanced plan fills at most 48 of the 64 rows of a tile slot (QM9 / 128 structures: 592 tiles of ~40
+// rows).  With two groups per CTA those tiles take two rounds; the per-tile cost is mostly latency (global loads,
+// barriers, the MMA pipeline, TMEM read-back), so the tc4 kernels run FOUR groups of 4 warps per CTA, each on its
+// own tile: one round instead of two and twice as many independent instruction streams per SM.  Shared memory:
+// a group owns TWO 48-row images instead of three 64-row ones -- the transposed accumulator S is written over
+// the hi image once the MMAs have consumed it (and, where the epilogue needs the operand itself, hi + lo = the
+// exact fp32 value is written over the lo image in the same pass).  Tensor memory: 256 weight columns + 4 x 48
+// accumulator columns.  Rows per warp: 12 = 3 row-group steps of 4 rows (8 lanes per row).
+#define L4_WG 4
+#define L4_GT 128
+#define L4_ROWS 48
+#define L4_IMG (6u * TC_RG_STRIDE)
+#define L4_SLOT 64                          // rows per tile slot of the plan (tile_stride)
+
+// accumulator (lane = feature n, column = row r) -> S[r][n] (+ bias) written over the hi image; with KEEP the lo
+// image receives hi + lo (= the staged fp32 operand, exactly).  Warp wg of its group owns lane quarter wg.
+template <bool KEEP>
+__device__ __forceinline__ void tmem_to_rows4(uint32_t t_dm, uint8_t* sHi, uint8_t* sLo, const float* __restrict__ bias,
+                                              int wg, int lane, int nrows) {
+    const int n = wg * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(wg * 32) << 16;
+    const float b = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        if (h * 16 >= nrows) break;
+        float m[16];
+        tmem_ld16(t_dm + lane_base + h * 16, m);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const uint32_t off = tc_off(h * 16 + q, n);
+            if (KEEP) {
+                const float x = *reinterpret_cast<const float*>(sHi + off) + *reinterpret_cast<const float*>(sLo + off);
+                *reinterpret_cast<float*>(sLo + off) = x;
+            }
+            *reinterpret_cast<float*>(sHi + off) = m[q] + b;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LTC_THREADS, 1) la_geom_fwd_tc4_kernel(const LaGeomArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bars[4];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2, wg = warp & 3, gtid = tid & (L4_GT - 1);
+    uint8_t* sHi = smem + (size_t)grp * 2 * L4_IMG;      // hi image, later S
+    uint8_t* sLo = sHi + L4_IMG;                         // lo image, later g
+    uint64_t* bar = &bars[grp];
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    if (tid < 4) mbar_init(&bars[tid], 1);
+    if (tid == 0) mbar_fence_init();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256 + grp * L4_ROWS;
+    DBG_CLK(0);
+    weightT_to_tmem(a.W2, t_whi, t_wlo, warp, lane);
+    pdl_wait();
+    const int nt = *a.ntiles;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    DBG_CLK(1);
+    uint32_t phase = 0;
+    // tile t -> group (t / grid) % 4 of CTA t % grid: a tile count below 4 x grid still spreads over all SMs
+    const int t_first = blockIdx.x + grp * gridDim.x, t_step = gridDim.x * 4;
+    const int l8 = lane & 7, rsub = lane >> 3;
+    float4 gm[4], bt[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) { gm[it] = ldg4(a.gamma_g + (l8 + 8 * it) * 4); bt[it] = ldg4(a.beta_g + (l8 + 8 * it) * 4); }
+    for (int t = t_first; t < nt; t += t_step) {
+        const size_t rowbase = (size_t)t * L4_SLOT;
+        // start-up skew: the groups of a CTA (and, after a kernel boundary, all CTAs of the grid) would otherwise
+        // walk load -> MMA -> read-back -> epilogue in lock-step and queue up on one resource after the other;
+        // group g starts loading when group g-1 has its tile, and the groups stay out of phase from there
+        if (t == t_first && grp > 0 && a.skew) bar_sync(4 + grp, 2 * L4_GT);
+        // ---- stage the geometry tile (48 rows x 32 chunks over 128 threads)
+        {
+            float4 v[12];
+#pragma unroll
+            for (int it = 0; it < 12; ++it) {
+                const int i = gtid + it * L4_GT;
+                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((i >> 5) < a.mma_rows) v[it] = ld4(a.g_in + (rowbase + (i >> 5)) * SCANN_D + (i & 31) * 4);
+            }
+#pragma unroll
+            for (int it = 0; it < 12; ++it) {
+                const int i = gtid + it * L4_GT;
+                float4 h, l;
+                tf32_split(v[it].x, h.x, l.x); tf32_split(v[it].y, h.y, l.y);
+                tf32_split(v[it].z, h.z, l.z); tf32_split(v[it].w, h.w, l.w);
+                const uint32_t off = tc_off4(i >> 5, i & 31);
+                *reinterpret_cast<float4*>(sHi + off) = h;
+                *reinterpret_cast<float4*>(sLo + off) = l;
+            }
+        }
+        if (t == t_first && grp < 3 && a.skew) bar_arrive(5 + grp, 2 * L4_GT);
+        fence_async_smem();
+        tc_fence_before();
+        group_sync(grp, L4_GT);
+        if (t == t_first) DBG_CLK(2);
+        if (wg == 0 && tc_elect_one()) {
+            tc_fence_after();
+            issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, 0, bar, a.mma_rows);
+        }
+        if (t == t_first) DBG_CLK(3);
+        // ---- while the tensor core works: indices of this warp's 12 rows, gathered projections of the first 8
+        int pc[3], pj[3];
+#pragma unroll
+        for (int sp = 0; sp < 3; ++sp) {
+            const int r = sp * 16 + wg * 4 + rsub;
+            pc[sp] = a.pair_c[rowbase + r];
+            pj[sp] = pc[sp] >= 0 ? a.pair_j[rowbase + r] : 0;
+        }
+        auto gather = [&](int sp, float4 (&p)[4]) {
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) return;
+            const int c = pc[sp] >= 0 ? pc[sp] : 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int c0 = (l8 + 8 * it) * 4;
+                p[it] = f4add(ld4(a.proj + (size_t)c * 3 * SCANN_D + c0),
+                              ld4(a.proj + (size_t)pj[sp] * 3 * SCANN_D + SCANN_D + c0));
+            }
+        };
+        float4 pa[4], pb[4];
+        gather(0, pa);
+        gather(1, pb);
+        if (t == t_first) DBG_CLK(4);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        if (t + t_step >= nt) pdl_trigger();
+        if (t == t_first) DBG_CLK(5);
+        tmem_to_rows4<true>(t_dm, sHi, sLo, nullptr, wg, lane, a.mma_rows);
+        tc_fence_before();
+        group_sync(grp, L4_GT);
+        if (t == t_first) DBG_CLK(6);
+        // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g'
+        auto epi = [&](int sp, const float4 (&p13)[4]) {
+            if (__all_sync(0xffffffffu, pc[sp] < 0)) return;
+            const int r = sp * 16 + wg * 4 + rsub;
+            float z[4][4], pre[4][4];
+            float s1 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const uint32_t off = tc_off4(r, l8 + 8 * it);
+                const float4 acc = *reinterpret_cast<const float4*>(sHi + off);
+                const float4 g = *reinterpret_cast<const float4*>(sLo + off);
+                pre[it][0] = acc.x + p13[it].x; pre[it][1] = acc.y + p13[it].y;
+                pre[it][2] = acc.z + p13[it].z; pre[it][3] = acc.w + p13[it].w;
+                z[it][0] = swish_fast(pre[it][0]) + g.x; z[it][1] = swish_fast(pre[it][1]) + g.y;
+                z[it][2] = swish_fast(pre[it][2]) + g.z; z[it][3] = swish_fast(pre[it][3]) + g.w;
+                s1 += z[it][0] + z[it][1] + z[it][2] + z[it][3];
+            }
+            const float sh = __shfl_sync(0xffffffffu, s1, lane & 24) * (1.0f / 16.0f);
+            float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { z[it][q] -= sh; m1 += z[it][q]; m2 = fmaf(z[it][q], z[it][q], m2); }
+            oct_sum2(m1, m2);
+            m1 *= (1.0f / SCANN_D);
+            const float inv = rsqrtf(fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f) + SCANN_LN_EPS);
+            const bool ok = pc[sp] >= 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int c0 = (l8 + 8 * it) * 4;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
+                if (ok) {
+                    o = make_float4((z[it][0] - m1) * inv * gm[it].x + bt[it].x, (z[it][1] - m1) * inv * gm[it].y + bt[it].y,
+                                    (z[it][2] - m1) * inv * gm[it].z + bt[it].z, (z[it][3] - m1) * inv * gm[it].w + bt[it].w);
+                    po = make_float4(pre[it][0], pre[it][1], pre[it][2], pre[it][3]);
+                }
+                st4(a.g_out + (rowbase + r) * SCANN_D + c0, o);
+                if (a.pre_out) st4(a.pre_out + (rowbase + r) * SCANN_D + c0, po);
+            }
+        };
+        epi(0, pa);
+        gather(2, pa);                   // in flight behind the second step
+        epi(1, pb);
+        epi(2, pa);
+        group_sync(grp, L4_GT);          // the images are rewritten by the next tile
+        if (t == t_first) DBG_CLK(7);
+    }
+    DBG_CLK(8);
+    pdl_trigger();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+#define LA4_GEOM_SMEM (4 * 2 * L4_IMG)
+#define LA4_ATTN_SMEM (4 * 2 * L4_IMG + 4 * L4_ROWS * 8 * sizeof(float))
+
 #define LA_GEOM_SMEM (3 * TC_TILE_BYTES)
 #define LA_ATTN_SMEM (3 * TC_TILE_BYTES + SCANN_TILE * 8 * sizeof(float))
 
@@ -474,6 +674,8 @@ static int la_fwd_configure() {
         e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_geom_fwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA4_GEOM_SMEM);
     if (e != cudaSuccess) { scann_set_error("la_forward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
     configured = true;
     return 0;
@@ -494,12 +696,16 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, cons
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_tc: mma_rows must be a multiple of 16 in 16..tile_stride"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
-    LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out, mma_rows};
+    LaGeomArgs ga{ntiles, pair_c, pair_j, proj, g_in, W2, gamma_g, beta_g, g_out, pre_out, mma_rows,
+                  (scann_la_tc4_mask() >> 4) & 1};
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mma_rows,
                   (const ScannDropCtl*)attn_drop, drop_site};
     if (tile_stride == 64) {
-        scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
+        // four warp groups per CTA when the plan's tiles hold at most 48 rows (see the tc4 section above)
+        const int m4 = mma_rows <= L4_ROWS ? scann_la_tc4_mask() : 0;
+        if (m4 & 1) scann_launch(la_geom_fwd_tc4_kernel, dim3(grid), dim3(LTC_THREADS), LA4_GEOM_SMEM, stream, ga);
+        else scann_launch(la_geom_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
         scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     } else {
         scann_launch(la_geom_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);

@@ -174,6 +174,13 @@ struct LaGroups {
     static constexpr int GT = LTC_GROUP_THREADS / NG;                    // threads per group
     static constexpr uint32_t IMG = (uint32_t)(TR / 8) * TC_RG_STRIDE;   // bytes of one K-major image of TR rows
 };
+// producer / consumer halves of a named barrier (ids 5..7 hand the start-up skew from group g to group g+1)
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 // barrier among the GT threads of warp group g (barrier 0 stays __syncthreads)
 __device__ __forceinline__ void group_sync(int g, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");

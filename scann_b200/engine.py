@@ -112,6 +112,10 @@ class Engine:
         self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "64"))
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
+        # local-attention kernels with four warp groups per CTA where the plan's tiles hold <= 48 rows (bit mask:
+        # 1 geometry forward, 2 attention forward, 4 attention backward, 8 geometry backward)
+        self.la_groups4 = int(os.environ.get("SCANN_LA4", "0"))
+        lib.scann_set_la_groups4(self.la_groups4)
         # pipelined input feed (facade fit): a step's host->device copy runs on its own stream into a staging
         # blob while the previous step computes; the main stream only does a device-to-device hand-over
         self.overlap_h2d = False
