@@ -54,40 +54,50 @@ __device__ __forceinline__ void wg_split_store(uint8_t* sHi, uint8_t* sLo, uint3
 }
 
 #define WG_UR 32                       // rows per unit (= K extent of one MMA group)
-#define WG_NSTAGE 2                    // staging buffers of raw rows (units u, u+1 in flight / being consumed)
 #define WG_NIMG 2                      // operand image sets: the split of unit u+1 overlaps the MMAs of unit u
 #define WG_RPW (WG_UR / WG_WARPS)      // rows per warp per unit
 #define WG_MNB ((uint32_t)WG_UR * 128u)          // one column block of an MN-major image: [UR rows x 32 columns]
 #define WG_MNT (4u * WG_MNB)                     // one image [UR x 128] fp32 = 32 KB
-#define WG_STAGE ((uint32_t)WG_UR * 512u)        // raw rows of one operand of one unit (a stage holds X then Y)
 
 __device__ __forceinline__ uint32_t wg_mn_off(int r, int c) {
     return (uint32_t)(c >> 5) * WG_MNB + (uint32_t)r * 128u + (((((uint32_t)c >> 3) & 3u) ^ ((uint32_t)r & 3u)) << 5) +
            ((uint32_t)c & 7u) * 4u;
 }
 __device__ __forceinline__ uint64_t wg_mn_desc(uint32_t saddr) { return tc_desc(saddr, WG_MNB, 512u) | ((uint64_t)1 << 61); }
-// 16-byte asynchronous global -> shared copy; nbytes = 0 zero-fills the destination
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int nbytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Pipeline per CTA (the inputs come from HBM: 13 % L2 hit rate measured, so the loads of the next unit must be in
-// flight while the current one is split and multiplied):
-//   cp.async raw rows of units u+1..u+3 -> staging ring | staging(u) -> hi/lo split -> 4 MN-major images -> MMAs
-// Every thread copies and later reads the SAME 16-byte chunks, so cp.async.wait_group is the only synchronisation
-// the staging ring needs; the images are single-buffered (the split of unit u+1 waits for the MMAs of unit u).
+// The problem a cursor currently points at, cached in registers: the table lives in shared memory and the shared-
+// memory data pipe is this kernel's busiest unit (ncu, first version: LSU wavefronts 64 % + tensor-core operand
+// reads 22 % of its peak), so it is only touched when a unit crosses a problem boundary (~50 times per CTA).
+struct WgCursor {
+    int p, ubase, uend;            // problem index, its first unit, one past its last unit
+    const float *X, *Y, *xg;
+    int ldx, ldy, nrows;
+    bool pair;
+};
+// The raw operand rows of one unit, held in registers from the moment their loads are issued (two units ahead of
+// their use) until they are split into the operand images.
+struct WgRegs {
+    float4 x[WG_RPW], y[WG_RPW], nb[WG_RPW];
+    bool has_xg;
+};
+
+// Pipeline per CTA.  The inputs come from HBM (6 % L2 hit rate measured), so the loads of the next units must be
+// in flight while the current one is split and multiplied:
+//   LDG.128 of units u+1, u+2 in registers (64 KB in flight per SM) | regs(u) -> hi/lo split -> 4 MN-major images
+//   (set u % 2) -> MMAs;  the split of unit u+1 overlaps the MMAs of unit u.
+// The first version staged the raw rows through shared memory with cp.async; per unit that cost 256 wavefronts
+// for the copies, 256 for reading them back and ~200 for the dummy LDS the compiler wraps around LDGSTS, on top of
+// the 512 (split stores) + 752 (tensor-core reads) that are inherent: the kernel ran at 2.4 TB/s, bound by the
+// shared-memory pipe, not by HBM.
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     // the BASE32B swizzle is a function of the absolute shared address: align the images to 1024 bytes
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sRaw = smem + WG_NIMG * 4 * WG_MNT;        // WG_NSTAGE x [X rows | Y rows]
     __shared__ uint64_t bars[WG_NIMG];
     __shared__ uint32_t tmem_base_s;
     __shared__ float s_db[SCANN_D];
     __shared__ int s_units[WG_MAX_PROBLEMS + 1];        // exclusive prefix of units per problem
-    __shared__ WgProblem s_prob[WG_MAX_PROBLEMS];       // the problem table (a dependent global load per unit otherwise)
+    __shared__ WgProblem s_prob[WG_MAX_PROBLEMS];       // the problem table
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // pair problems run over the compact list of valid rows when the plan provides it (independent of how
     // sparsely the tiles are filled), else over all tile slots with the padding rows skipped
@@ -121,63 +131,67 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
 #pragma unroll
     for (int b = 0; b < WG_NIMG; ++b) { phase[b] = 0; pending[b] = false; }
     bool first = true;              // no MMA has been issued into the accumulators of the current problem
-    int p = 0, pl = 0;              // problem of the unit being multiplied / being loaded
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    int pjq[WG_NSTAGE][WG_RPW];     // neighbour indices of the units in flight (pjq[k] belongs to unit u + k)
-#pragma unroll
-    for (int k = 0; k < WG_NSTAGE; ++k)
-#pragma unroll
-        for (int i = 0; i < WG_RPW; ++i) pjq[k][i] = 0;
 
-    // Indices (pair_c, pair_j) of the unit that will be loaded NEXT are fetched one call ahead: otherwise every
-    // iteration starts with two dependent L2 round trips before its cp.async can be issued.
-    int pi = 0;                     // problem of the unit whose indices are being fetched
-    int pcn[WG_RPW], pjx[WG_RPW];
-    auto prefetch_idx = [&](int u) {
+    auto seek = [&](WgCursor& c, int u) {           // make c describe the problem of unit u (u < total)
+        if (u < c.uend) return;
+        while (u >= c.uend) { ++c.p; c.ubase = c.uend; c.uend = s_units[c.p + 1]; }
+        const WgProblem& pr = s_prob[c.p];
+        c.X = pr.X; c.Y = pr.Y; c.xg = pr.xg; c.ldx = pr.ldx; c.ldy = pr.ldy;
+        c.pair = pr.rows < 0;
+        c.nrows = c.pair ? pair_rows : pr.rows;
+    };
+    WgCursor ci{-1, 0, 0, nullptr, nullptr, nullptr, 0, 0, 0, false};      // indices are fetched for its unit
+    WgCursor cl = ci;                                                      // loads are issued for its unit
+    int pc = -1, pc_uend = 0;                                              // problem being multiplied
+
+    // Source rows (and neighbour rows) of the unit that will be loaded NEXT, fetched one call ahead: otherwise
+    // every load would start with a dependent L2 round trip.
+    int src[WG_RPW], nbj[WG_RPW];
+    auto fetch_idx = [&](int u) {
 #pragma unroll
-        for (int i = 0; i < WG_RPW; ++i) { pcn[i] = -1; pjx[i] = 0; }
+        for (int i = 0; i < WG_RPW; ++i) { src[i] = -1; nbj[i] = 0; }
         if (u >= u_hi) return;
-        while (u >= s_units[pi + 1]) ++pi;
-        const WgProblem& pr = s_prob[pi];
-        const int nrows = pr.rows < 0 ? pair_rows : pr.rows;
-        const size_t rowbase = (size_t)(u - s_units[pi]) * WG_UR;
+        seek(ci, u);
+        const int rowbase = (u - ci.ubase) * WG_UR;
 #pragma unroll
         for (int i = 0; i < WG_RPW; ++i) {
-            const size_t r = rowbase + warp + WG_WARPS * i;
-            if (r < (size_t)nrows) {
-                pcn[i] = (int)r;                        // source row (>= 0) or -1
-                if (pr.rows < 0) {
+            const int r = rowbase + warp + WG_WARPS * i;
+            if (r < ci.nrows) {
+                src[i] = r;
+                if (ci.pair) {
                     if (a.valid_rows) {
-                        pcn[i] = a.valid_rows[r];
-                        if (pr.xg) pjx[i] = a.valid_j[r];         // independent of the load above: one round trip
+                        src[i] = a.valid_rows[r];
+                        if (ci.xg) nbj[i] = a.valid_j[r];         // independent of the load above: one round trip
                     } else {
-                        if (a.pair_c[r] < 0) pcn[i] = -1;
-                        if (pr.xg) pjx[i] = a.pair_j[r];
+                        if (a.pair_c[r] < 0) src[i] = -1;
+                        if (ci.xg) nbj[i] = a.pair_j[r];
                     }
                 }
             }
         }
     };
-    // asynchronous copy of the raw operand rows of unit u into its staging slot (+ neighbour indices into pjn);
-    // always commits a group (possibly empty) so that the group count per iteration is constant.  Calls are made
-    // for consecutive units; each call leaves the indices of unit u+1 in flight.
-    auto issue_load = [&](int u, int (&pjn)[WG_RPW]) {
-        if (u >= u_hi) { cp_async_commit(); return; }
-        uint8_t* sRawX = sRaw + (size_t)(u % WG_NSTAGE) * 2 * WG_STAGE;
-        uint8_t* sRawY = sRawX + WG_STAGE;
-        while (u >= s_units[pl + 1]) ++pl;
-        const WgProblem& pr = s_prob[pl];
+    // issue the loads of unit u into `s` (zeros for rows that do not exist), then fetch the indices of unit u + 1
+    auto issue_load = [&](int u, WgRegs& s) {
+        s.has_xg = false;
 #pragma unroll
         for (int i = 0; i < WG_RPW; ++i) {
-            const int rr = warp + WG_WARPS * i;
-            const bool ok = pcn[i] >= 0;
-            pjn[i] = ok ? pjx[i] : 0;
-            const size_t rs = ok ? (size_t)pcn[i] : 0;
-            cp_async16(smem_u32(sRawX) + rr * 512 + lane * 16, pr.X + rs * pr.ldx + lane * 4, ok ? 16 : 0);
-            cp_async16(smem_u32(sRawY) + rr * 512 + lane * 16, pr.Y + rs * pr.ldy + lane * 4, ok ? 16 : 0);
+            s.x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s.y[i] = s.x[i];
+            s.nb[i] = s.x[i];
         }
-        cp_async_commit();
-        prefetch_idx(u + 1);
+        if (u >= u_hi) return;
+        seek(cl, u);
+        s.has_xg = cl.xg != nullptr;
+#pragma unroll
+        for (int i = 0; i < WG_RPW; ++i) {
+            if (src[i] >= 0) {
+                s.x[i] = ld4(cl.X + (size_t)src[i] * cl.ldx + lane * 4);
+                s.y[i] = ld4(cl.Y + (size_t)src[i] * cl.ldy + lane * 4);
+                if (s.has_xg) s.nb[i] = ld4(cl.xg + (size_t)nbj[i] * SCANN_D + lane * 4);
+            }
+        }
+        fetch_idx(u + 1);
     };
     // accumulators -> gradient arena (vector atomics), column sums -> bias gradient
     auto flush = [&](const WgProblem& pr) {
@@ -211,60 +225,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
         first = true;
         colsum = make_float4(0.f, 0.f, 0.f, 0.f);
     };
-
-    prefetch_idx(u_lo);
-#pragma unroll
-    for (int k = 0; k < WG_NSTAGE - 1; ++k) issue_load(u_lo + k, pjq[k]);
-#pragma unroll 1
-    for (int u = u_lo; u < u_hi; ++u) {
-        while (u >= s_units[p + 1]) {        // next problem: hand over what was accumulated for the previous one
-            flush(s_prob[p]);
-            ++p;
+    // one unit: registers -> operand images of set ib, refill the registers with unit u + 2, MMAs
+    auto step = [&](int u, WgRegs& s, const int ib) {
+        if (u >= pc_uend) {                  // next problem: hand over what was accumulated for the previous one
+            while (u >= pc_uend) {
+                if (pc >= 0) flush(s_prob[pc]);
+                ++pc;
+                pc_uend = s_units[pc + 1];
+            }
         }
-        const float* xg = s_prob[p].xg;
-        // refill the slot that was consumed in the previous iteration (this thread's own chunks)
-        issue_load(u + WG_NSTAGE - 1, pjq[WG_NSTAGE - 1]);
-        // neighbour rows x[j] (L2 resident) while the asynchronous copies land
-        float4 nb[WG_RPW];
-        if (xg) {
-#pragma unroll
-            for (int i = 0; i < WG_RPW; ++i) nb[i] = ld4(xg + (size_t)pjq[0][i] * SCANN_D + lane * 4);
-        }
-        asm volatile("cp.async.wait_group %0;" ::"n"(WG_NSTAGE - 1) : "memory");      // unit u has landed
-        const uint8_t* sRawX = sRaw + (size_t)(u % WG_NSTAGE) * 2 * WG_STAGE;
-        const uint8_t* sRawY = sRawX + WG_STAGE;
-        float4 xv[WG_RPW], yv[WG_RPW];
-#pragma unroll
-        for (int i = 0; i < WG_RPW; ++i) {
-            const int rr = warp + WG_WARPS * i;
-            xv[i] = *reinterpret_cast<const float4*>(sRawX + rr * 512 + lane * 16);
-            yv[i] = *reinterpret_cast<const float4*>(sRawY + rr * 512 + lane * 16);
-            if (xg) xv[i] = make_float4(xv[i].x * nb[i].x, xv[i].y * nb[i].y, xv[i].z * nb[i].z, xv[i].w * nb[i].w);
-            colsum = make_float4(colsum.x + yv[i].x, colsum.y + yv[i].y, colsum.z + yv[i].z, colsum.w + yv[i].w);
-        }
-#pragma unroll
-        for (int k = 0; k + 1 < WG_NSTAGE; ++k)
-#pragma unroll
-            for (int i = 0; i < WG_RPW; ++i) pjq[k][i] = pjq[k + 1][i];
-        const int ib = u & (WG_NIMG - 1);
         uint8_t* sXh = smem + (size_t)ib * 4 * WG_MNT;
         uint8_t* sXl = sXh + WG_MNT;
         uint8_t* sYh = sXh + 2 * WG_MNT;
         uint8_t* sYl = sXh + 3 * WG_MNT;
-#pragma unroll
-        for (int b = 0; b < WG_NIMG; ++b)
-            if (b == ib && pending[b]) {      // the MMAs of unit u - 2 still read this image set
-                mbar_wait(&bars[b], phase[b]);
-                phase[b] ^= 1;
-                tc_fence_after();
-                pending[b] = false;
-            }
+        if (pending[ib]) {                   // the MMAs of unit u - 2 still read this image set
+            mbar_wait(&bars[ib], phase[ib]);
+            phase[ib] ^= 1;
+            tc_fence_after();
+            pending[ib] = false;
+        }
 #pragma unroll
         for (int i = 0; i < WG_RPW; ++i) {
+            float4 xv = s.x[i];
+            const float4 yv = s.y[i];
+            if (s.has_xg) xv = make_float4(xv.x * s.nb[i].x, xv.y * s.nb[i].y, xv.z * s.nb[i].z, xv.w * s.nb[i].w);
+            colsum = make_float4(colsum.x + yv.x, colsum.y + yv.y, colsum.z + yv.z, colsum.w + yv.w);
             const uint32_t off = wg_mn_off(warp + WG_WARPS * i, lane * 4);
-            wg_split_store(sXh, sXl, off, xv[i]);
-            wg_split_store(sYh, sYl, off, yv[i]);
+            wg_split_store(sXh, sXl, off, xv);
+            wg_split_store(sYh, sYl, off, yv);
         }
+        issue_load(u + 2, s);                // the registers are free again: two units stay in flight
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -283,18 +273,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
                 tc_mma_ss(t_dc, dxl + (uint64_t)(ks * 64), dyh + (uint64_t)(ks * 64), idesc, true);
             tc_commit(&bars[ib]);
         }
-#pragma unroll
-        for (int b = 0; b < WG_NIMG; ++b)
-            if (b == ib) pending[b] = true;
+        pending[ib] = true;
         first = false;
+    };
+
+    WgRegs ra, rb;
+    fetch_idx(u_lo);
+    issue_load(u_lo, ra);
+    issue_load(u_lo + 1, rb);
+#pragma unroll 1
+    for (int u = u_lo; u < u_hi; u += 2) {
+        step(u, ra, 0);
+        if (u + 1 < u_hi) step(u + 1, rb, 1);
     }
-    if (u_hi > u_lo) flush(s_prob[p]);
+    if (u_hi > u_lo) flush(s_prob[pc]);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base_s, 256);
 }
 
-#define WG_SMEM (WG_NIMG * 4 * WG_MNT + WG_NSTAGE * 2 * WG_STAGE + 1024)
+#define WG_SMEM (WG_NIMG * 4 * WG_MNT + 1024)
 
 // problems: DEVICE array of nprob ScannWgradProblem (include/scann_b200.h).  Gradients are accumulated
 // (atomics) into dW / db, which the caller zeroes at the start of the step.
