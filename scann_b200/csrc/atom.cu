@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
 }
 
 // Backward: accumulates dWd, dbd, dWw, dbw from d_g0 (no gradient flows to distances/weights).
-__global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
+__global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
                                                             const int32_t* __restrict__ pair_c,
                                                             const float* __restrict__ pair_d,
                                                             const float* __restrict__ pair_w,
@@ -358,27 +358,28 @@ __global__ void __launch_bounds__(256) geom_init_bwd_kernel(const int32_t* __res
                 if (s_c[row] < 0) continue;
                 float a = bdn, b = bwn;
                 const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
-                float4 rd[SCANN_RBF / 4], rw[SCANN_RBF / 4];
 #pragma unroll
                 for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
-                    rd[k4] = rb[k4];
-                    rw[k4] = rb[SCANN_RBF / 4 + k4];
-                    a = fmaf(rd[k4].x, wd[4 * k4], a); a = fmaf(rd[k4].y, wd[4 * k4 + 1], a);
-                    a = fmaf(rd[k4].z, wd[4 * k4 + 2], a); a = fmaf(rd[k4].w, wd[4 * k4 + 3], a);
-                    b = fmaf(rw[k4].x, ww[4 * k4], b); b = fmaf(rw[k4].y, ww[4 * k4 + 1], b);
-                    b = fmaf(rw[k4].z, ww[4 * k4 + 2], b); b = fmaf(rw[k4].w, ww[4 * k4 + 3], b);
+                    const float4 rd = rb[k4], rw = rb[SCANN_RBF / 4 + k4];
+                    a = fmaf(rd.x, wd[4 * k4], a); a = fmaf(rd.y, wd[4 * k4 + 1], a);
+                    a = fmaf(rd.z, wd[4 * k4 + 2], a); a = fmaf(rd.w, wd[4 * k4 + 3], a);
+                    b = fmaf(rw.x, ww[4 * k4], b); b = fmaf(rw.y, ww[4 * k4 + 1], b);
+                    b = fmaf(rw.z, ww[4 * k4 + 2], b); b = fmaf(rw.w, ww[4 * k4 + 3], b);
                 }
                 const float sa = sigmoid_fast(a), sb = sigmoid_fast(b);
                 const float da = dv[q] * (b * sb) * (sa * (1.0f + a * (1.0f - sa)));
                 const float db = dv[q] * (a * sa) * (sb * (1.0f + b * (1.0f - sb)));
                 gbd += da;
                 gbw += db;
+                // the Gaussians are read again (shared-memory broadcasts) rather than kept: 40 registers less,
+                // two CTAs per SM
 #pragma unroll
                 for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
-                    gd[4 * k4] = fmaf(rd[k4].x, da, gd[4 * k4]); gd[4 * k4 + 1] = fmaf(rd[k4].y, da, gd[4 * k4 + 1]);
-                    gd[4 * k4 + 2] = fmaf(rd[k4].z, da, gd[4 * k4 + 2]); gd[4 * k4 + 3] = fmaf(rd[k4].w, da, gd[4 * k4 + 3]);
-                    gw[4 * k4] = fmaf(rw[k4].x, db, gw[4 * k4]); gw[4 * k4 + 1] = fmaf(rw[k4].y, db, gw[4 * k4 + 1]);
-                    gw[4 * k4 + 2] = fmaf(rw[k4].z, db, gw[4 * k4 + 2]); gw[4 * k4 + 3] = fmaf(rw[k4].w, db, gw[4 * k4 + 3]);
+                    const float4 rd = rb[k4], rw = rb[SCANN_RBF / 4 + k4];
+                    gd[4 * k4] = fmaf(rd.x, da, gd[4 * k4]); gd[4 * k4 + 1] = fmaf(rd.y, da, gd[4 * k4 + 1]);
+                    gd[4 * k4 + 2] = fmaf(rd.z, da, gd[4 * k4 + 2]); gd[4 * k4 + 3] = fmaf(rd.w, da, gd[4 * k4 + 3]);
+                    gw[4 * k4] = fmaf(rw.x, db, gw[4 * k4]); gw[4 * k4 + 1] = fmaf(rw.y, db, gw[4 * k4 + 1]);
+                    gw[4 * k4 + 2] = fmaf(rw.z, db, gw[4 * k4 + 2]); gw[4 * k4 + 3] = fmaf(rw.w, db, gw[4 * k4 + 3]);
                 }
             }
         }

@@ -114,7 +114,10 @@ class Engine:
         self._prep_event = None
         # local-attention kernels with four warp groups per CTA where the plan's tiles hold <= 48 rows (bit mask:
         # 1 geometry forward, 2 attention forward, 4 attention backward, 8 geometry backward)
-        self.la_groups4 = int(os.environ.get("SCANN_LA4", "0"))
+        # CTAs per SM of the SIMT geometry-initialisation kernels (latency-bound FMA chains: more resident warps)
+        self.gi_fwd_mult = int(os.environ.get("SCANN_GI_FWD", "3"))
+        self.gi_bwd_mult = int(os.environ.get("SCANN_GI_BWD", "2"))
+        self.la_groups4 = int(os.environ.get("SCANN_LA4", "17"))      # geometry forward, staggered start
         lib.scann_set_la_groups4(self.la_groups4)
         # pipelined input feed (facade fit): a step's host->device copy runs on its own stream into a staging
         # blob while the previous step computes; the main stream only does a device-to-device hand-over
@@ -563,7 +566,7 @@ class Engine:
         self.launches += 1
         self._pdl(True)
         if sp.g_update and "geom_init" not in self._skip:
-            check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+            check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid * self.gi_fwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                               _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                               self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
                                               self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
@@ -897,7 +900,7 @@ class Engine:
         R = b.R
         dx = ws["dx"]
         if sp.g_update and "geom_init" not in self._skip:
-          check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+          check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid * self.gi_bwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                            _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                            self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
                                            self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),

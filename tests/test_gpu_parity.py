@@ -137,12 +137,15 @@ def test_gradients_match_golden(name):
     assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
 
 
-@pytest.mark.parametrize("stride,balance", [(128, "0"), (64, "0"), (64, "1"), (128, "1")])
-def test_both_tile_layouts_match_golden(monkeypatch, stride, balance):
+@pytest.mark.parametrize("stride,balance,la4", [(128, "0", "17"), (64, "0", "17"), (64, "1", "17"), (128, "1", "17"),
+                                                (64, "1", "0"), (64, "1", "1")])
+def test_both_tile_layouts_match_golden(monkeypatch, stride, balance, la4):
     """The pair plan has two layouts (tile slots of 128 rows = one tile stream per CTA, 64 rows = two warp
-    groups per CTA) and an optional wave-balanced fill; every combination must give the same answer."""
+    groups per CTA, or four where a kernel has a four-group form and the tiles hold <= 48 rows: SCANN_LA4) and an
+    optional wave-balanced fill; every combination must give the same answer."""
     monkeypatch.setenv("SCANN_TILE_STRIDE", str(stride))
     monkeypatch.setenv("SCANN_BALANCE_TILES", balance)
+    monkeypatch.setenv("SCANN_LA4", la4)
     name = "qm9_b4"
     cfg, spec, lay, arena, inputs, target = build_case(name)
     z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
