@@ -57,6 +57,9 @@ int scann_set_la_groups4(int mask);
  * neighbor_mask [B,M,N] uint8, neighbors [B,M,N] int32, dist/weight [B,M,N] fp32.
  * Outputs: cnt[R], rowptr[R], tile_a0/tile_a1[tile_cap] (atom range of each tile), ntiles[1],
  * pair_c/pair_j/pair_slot/pair_d/pair_w [tile_cap*tile_stride].  scratch: >= 4*ceil(R/128) int32 (2* without valid_rows).
+ * With >= 6*ceil(R/128) + 6 int32, 8-byte aligned and ZEROED ONCE when allocated (never touched by the caller
+ * afterwards), the plan is built by one launch (one CTA per 128 atom rows, decoupled look-back through the words
+ * kept in scratch) instead of four; the result is identical.
  * tile_rows (<= tile_stride): greedy fill limit per tile, chosen by the caller to balance SM waves.
  * valid_rows, valid_j [tile_cap*tile_stride] / nvalid [1] (nullable): compact list of the valid pair rows in tile
  * order and the neighbour atom row of each, for

@@ -40,9 +40,10 @@ extern "C" int scann_set_pdl(int on) {
 // when the pair plan's tiles hold at most 48 rows; per calling thread, returns the previous mask.
 static thread_local int g_la4 = 0;
 int scann_la_tc4_mask() { return g_la4; }
+bool scann_plan_unfused() { return (g_la4 & 32) != 0; }
 extern "C" int scann_set_la_groups4(int mask) {
     int prev = g_la4;
-    g_la4 = mask & 31;      // bit 4 (development): stagger the start of the groups
+    g_la4 = mask & 63;      // bit 4: stagger the start of the groups; bit 5 (development): unfused pair plan
     return prev;
 }
 

@@ -35,6 +35,8 @@ bool scann_pdl_enabled();
 // which local-attention kernels run as four warp groups per CTA when the plan allows it (scann_set_la_groups4,
 // abi.cu, per thread): bit 0 geometry forward, 1 attention forward, 2 attention backward, 3 geometry backward
 int scann_la_tc4_mask();
+// development switch (bit 5 of scann_set_la_groups4): build the pair plan with the four separate kernels
+bool scann_plan_unfused();
 template <typename... KArgs, typename... Args>
 static inline void scann_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
     cudaLaunchConfig_t cfg = {};

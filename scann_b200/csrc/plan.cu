@@ -152,6 +152,148 @@ __global__ void plan_fill_kernel(const uint8_t* __restrict__ nmask, const int32_
     }
 }
 
+// The four kernels above in ONE launch of one CTA per plan group (PLAN_GSZ atom rows, one thread per row).  As
+// separate launches the plan costs ~45 us of a 1.2 ms QM9 train step and of a 0.4 ms inference step (four dependent
+// launches, two of them single-CTA serial loops); here a CTA counts its rows, thread 0 packs them greedily out of
+// shared memory, the CTA publishes (tiles, pairs) of its group and picks up the sums over the lower groups
+// (decoupled look-back: a CTA only ever waits for CTAs with a smaller index, which the hardware schedules first),
+// then fills its own pairs.  Same algorithm, same plan (tests/test_gpu_parity.py::
+// test_plan_gathers_and_masks_bit_exact runs both forms).
+//
+// sync[0] = epoch, sync[1] = ticket, sync[2 + g] = published word of group g, 64 bit:
+// (epoch + 1) << 32 | pairs << 12 | tiles.  Words of earlier launches carry an older epoch, so nothing has to be
+// cleared between launches (the buffer is zeroed once, when it is allocated); the last CTA to finish advances
+// the epoch.
+__global__ void __launch_bounds__(PLAN_GSZ) plan_chain_kernel(
+    const uint8_t* __restrict__ nmask, const int32_t* __restrict__ nbr, const float* __restrict__ dist,
+    const float* __restrict__ weight, int R, int M, int N, int ngroups, int tile_cap, int tile_rows, int tile_stride,
+    int32_t* __restrict__ cnt, int32_t* __restrict__ rowptr, int32_t* __restrict__ tile_a0, int32_t* __restrict__ tile_a1,
+    int32_t* __restrict__ ntiles, int32_t* __restrict__ pair_c, int32_t* __restrict__ pair_j,
+    int32_t* __restrict__ pair_slot, float* __restrict__ pair_d, float* __restrict__ pair_w,
+    int32_t* __restrict__ valid_rows, int32_t* __restrict__ valid_j, int32_t* __restrict__ nvalid,
+    unsigned long long* __restrict__ sync, int32_t* __restrict__ status) {
+    __shared__ int32_t s_cnt[PLAN_GSZ];
+    __shared__ int32_t s_rp[PLAN_GSZ];            // (pairs of the group before the atom) << 16 | group-local row
+    __shared__ int32_t s_red[2][PLAN_GSZ / 32];
+    __shared__ int32_t s_own[2], s_base[2];
+    const int tid = threadIdx.x, g = blockIdx.x, r = g * PLAN_GSZ + tid;
+    const unsigned epoch = (unsigned)*reinterpret_cast<volatile unsigned long long*>(sync) + 1u;
+    // ---- valid neighbours of this thread's atom row
+    int c = 0;
+    if (r < R) {
+        const uint8_t* m = nmask + (size_t)r * N;
+        const int32_t* j = nbr + (size_t)r * N;
+        int bad = 0;
+        for (int n = 0; n < N; ++n) {
+            if (m[n]) {
+                ++c;
+                const int v = j[n];
+                bad |= (v < 0) | (v >= M);
+            }
+        }
+        if (c > SCANN_TILE) { atomicOr(status, SCANN_ERR_TOO_MANY_NBRS); c = 0; }
+        if (bad) { atomicOr(status, SCANN_ERR_BAD_NEIGHBOR); c = 0; }
+        cnt[r] = c;
+    }
+    s_cnt[tid] = c;
+    __syncthreads();
+    // ---- greedy first-fit in row order (thread 0), publish the group's totals
+    if (tid == 0) {
+        int tile = 0, fill = 0, any = 0, pairs = 0;
+#pragma unroll 8
+        for (int a = 0; a < PLAN_GSZ; ++a) {
+            const int ca = s_cnt[a];
+            if (ca != 0) {
+                if (fill + ca > tile_rows && fill > 0) { ++tile; fill = 0; }
+                s_rp[a] = (pairs << 16) | (tile * tile_stride + fill);
+                fill += ca;
+                pairs += ca;
+                any = 1;
+            }
+        }
+        const int tiles = any ? tile + 1 : 0;
+        s_own[0] = tiles;
+        s_own[1] = pairs;
+        const unsigned long long word = ((unsigned long long)epoch << 32) | ((unsigned long long)pairs << 12) | (unsigned)tiles;
+        asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(sync + 2 + g), "l"(word) : "memory");
+    }
+    // ---- look back: sums over the groups below this one (thread i waits for group i)
+    int bt = 0, bp = 0;
+    for (int i = tid; i < g; i += PLAN_GSZ) {
+        unsigned long long w;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(sync + 2 + i) : "memory");
+        } while ((unsigned)(w >> 32) != epoch);
+        bt += (int)(w & 0xfffu);
+        bp += (int)((w >> 12) & 0xfffffu);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bt += __shfl_xor_sync(0xffffffffu, bt, o);
+        bp += __shfl_xor_sync(0xffffffffu, bp, o);
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = bt; s_red[1][tid >> 5] = bp; }
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0, p = 0;
+        for (int w = 0; w < PLAN_GSZ / 32; ++w) { t += s_red[0][w]; p += s_red[1][w]; }
+        s_base[0] = t;
+        s_base[1] = p;
+    }
+    __syncthreads();
+    const int gbase = s_base[0], gcbase = s_base[1];
+    const bool overflow = gbase + s_own[0] > tile_cap;
+    if (g == ngroups - 1 && tid == 0) {          // the last group knows the totals
+        int run = gbase + s_own[0], crun = gcbase + s_own[1];
+        if (run > tile_cap) { run = 0; crun = 0; }
+        *ntiles = run;
+        if (valid_rows) *nvalid = crun;
+    }
+    if (overflow && tid == 0) atomicOr(status, SCANN_ERR_TILE_OVERFLOW);
+    // ---- the pairs of this thread's atom into its tile rows (and the compact list, which follows the tile order)
+    if (r < R) {
+        if (c == 0 || overflow) {
+            rowptr[r] = 0;
+        } else {
+            const int packed = s_rp[tid];
+            const int rp = gbase * tile_stride + (packed & 0xffff);
+            const int vbase = gcbase + (packed >> 16);
+            rowptr[r] = rp;
+            const int tile = rp / tile_stride;
+            if (rp % tile_stride == 0) tile_a0[tile] = r;
+            atomicMax(&tile_a1[tile], r + 1);
+            const int b = r / M;
+            const uint8_t* m = nmask + (size_t)r * N;
+            int k = 0;
+            for (int n = 0; n < N; ++n) {
+                if (m[n]) {
+                    const size_t s = (size_t)r * N + n;
+                    const int p = rp + k;
+                    const int j = b * M + nbr[s];
+                    if (valid_rows) { valid_rows[vbase + k] = p; valid_j[vbase + k] = j; }
+                    ++k;
+                    pair_c[p] = r;
+                    pair_j[p] = j;
+                    pair_slot[p] = (int32_t)s;
+                    pair_d[p] = dist[s];
+                    pair_w[p] = weight[s];
+                }
+            }
+        }
+    }
+    // ---- the last CTA to get here advances the epoch (every published word of this launch has been consumed:
+    // a CTA passes its look-back before it takes a ticket)
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned long long t = atomicAdd(sync + 1, 1ull);
+        if (t == (unsigned long long)(ngroups - 1)) {
+            sync[1] = 0ull;
+            __threadfence();
+            *reinterpret_cast<volatile unsigned long long*>(sync) = (unsigned long long)epoch;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Ragged (CSR) batch -> padded device buffers: DataIterator.__getitem__ (scann/utils/datagenerator.py:69-135) on
 // the device.  One thread per padded atom row (b, m).  Neighbour value 1000 is the reference's padding marker
@@ -238,6 +380,18 @@ extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* nei
     // per-pair arrays need no initialisation.  tile_a1 is built with atomicMax.
     cudaMemsetAsync(pair_c, 0xFF, rows * sizeof(int32_t), st);
     cudaMemsetAsync(tile_a1, 0, (size_t)tile_cap * sizeof(int32_t), st);
+    // one launch (decoupled look-back over the plan groups) when the caller's scratch has room for the 64-bit
+    // words behind the 4 * ngroups ints of the four-kernel form (and the buffer is 8-byte aligned)
+    const int sync_off = (4 * ngroups + 1) & ~1;
+    if (!scann_plan_unfused() && scratch_len >= sync_off + 2 * (ngroups + 2) && ((uintptr_t)scratch & 7) == 0 &&
+        ngroups < 4096) {
+        plan_chain_kernel<<<ngroups, PLAN_GSZ, 0, st>>>(neighbor_mask, neighbors, dist, weight, R, M, N, ngroups, tile_cap,
+                                                       tile_rows, tile_stride, cnt, rowptr, tile_a0, tile_a1, ntiles, pair_c,
+                                                       pair_j, pair_slot, pair_d, pair_w, valid_rows, valid_j,
+                                                       valid_rows ? nvalid : nullptr,
+                                                       reinterpret_cast<unsigned long long*>(scratch + sync_off), status);
+        return scann_check_launch("scann_plan_build");
+    }
     plan_count_kernel<<<(R + 255) / 256, 256, 0, st>>>(neighbor_mask, neighbors, R, M, N, cnt, status);
     plan_group_kernel<<<(ngroups + 31) / 32, 128, 0, st>>>(cnt, R, ngroups, tile_rows, tile_stride, rowptr, gtiles, gcount);
     plan_scan_kernel<<<1, 1024, 0, st>>>(gtiles, ngroups, tile_cap, gbase, ntiles, status, gcount, gcbase,

@@ -395,7 +395,9 @@ class Engine:
         b.valid_rows = torch.empty(rows, **i32)
         b.valid_j = torch.empty(rows, **i32)
         b.nvalid = torch.zeros(1, **i32)
-        b.scratch = torch.empty(4 * ngroups + 8, **i32)
+        # 4 ints per plan group (four-kernel form) + the 64-bit look-back words of the one-launch form, which rely
+        # on the buffer being zero when it is first used (scann_plan_build)
+        b.scratch = torch.zeros(6 * ngroups + 16, **i32)
         b.graphs = {}
         return b
 
@@ -458,7 +460,8 @@ class Engine:
                                    _p(b.pair_c), _p(b.pair_j), _p(b.pair_slot), _p(b.pair_d), _p(b.pair_w),
                                    _p(b.valid_rows), _p(b.valid_j), _p(b.nvalid), _p(b.scratch), b.scratch.numel(), _p(self.status),
                                    self._stream()), "plan_build")
-        self.launches += 4
+        # one launch (look-back over the plan groups), or count / group / scan / fill with SCANN_LA4 bit 5
+        self.launches += 4 if (self.la_groups4 & 32) else 1
 
     # ------------------------------------------------------------------ workspaces
     def _workspace(self, b: Batch, training: bool) -> dict:

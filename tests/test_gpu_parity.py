@@ -77,9 +77,13 @@ def test_native_library_is_loaded_on_gpu():
     assert _abi.lib.scann_device_cc() >= 100
 
 
-@pytest.mark.parametrize("shape,B", [("qm9", 16), ("mp2018", 6), ("fullerene", 3)])
-def test_plan_gathers_and_masks_bit_exact(shape, B):
-    spec, lay, arena = small(shape if shape != "fullerene" else "fullerene")
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("shape,B", [("qm9", 16), ("mp2018", 6), ("fullerene", 3), ("qm9", 128), ("ptgp", 64)])
+def test_plan_gathers_and_masks_bit_exact(monkeypatch, shape, B, fused):
+    """Both forms of scann_plan_build (one fused single-CTA kernel / four kernels) against the host arrays."""
+    if not fused:
+        monkeypatch.setenv("SCANN_LA4", str(17 | 32))
+    spec, lay, arena = small(shape if shape != "ptgp" else "qm9")      # the plan does not depend on the model
     inputs, _ = make_batch(shape, 1, B=B)
     eng = engine_for(spec, arena)
     b = eng.load_batch(inputs)
