@@ -74,21 +74,36 @@ __global__ void __launch_bounds__(128) embed_bwd_gather_kernel(const int32_t* __
     float all = 0.f, g0 = 0.f, g1 = 0.f;
     float run = 0.f;
     int zrun = -1;
-    for (int r = r0; r < r1; ++r) {
-        float d = dx0[(size_t)r * SCANN_D + n] * drop_mult(drop, 0u, (uint32_t)r * SCANN_D + n) *
-                  swish_grad_f(t0[(size_t)r * SCANN_D + n]);
-        int z = atomic[r];
-        z = (z < 0 || z >= n_atoms) ? 0 : z;
-        if (z != zrun) {
-            if (zrun >= 0) atomicAdd(G + (size_t)zrun * SCANN_D + n, run);
-            zrun = z;
-            run = 0.f;
+    // rows in batches of 8: the loads of a batch are independent and issued together (the run-length logic with
+    // its atomics otherwise keeps the compiler from overlapping them: 32 dependent round trips per thread)
+    for (int rb = r0; rb < r1; rb += 8) {
+        float dv[8], tv[8];
+        int zv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = min(rb + q, r1 - 1);
+            dv[q] = dx0[(size_t)r * SCANN_D + n];
+            tv[q] = t0[(size_t)r * SCANN_D + n];
+            zv[q] = atomic[r];
         }
-        run += d;
-        all += d;
-        if (ring) {
-            g0 = fmaf(ring[(size_t)r * 2], d, g0);
-            g1 = fmaf(ring[(size_t)r * 2 + 1], d, g1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int r = rb + q;
+            if (r >= r1) break;
+            const float d = dv[q] * drop_mult(drop, 0u, (uint32_t)r * SCANN_D + n) * swish_grad_f(tv[q]);
+            int z = zv[q];
+            z = (z < 0 || z >= n_atoms) ? 0 : z;
+            if (z != zrun) {
+                if (zrun >= 0) atomicAdd(G + (size_t)zrun * SCANN_D + n, run);
+                zrun = z;
+                run = 0.f;
+            }
+            run += d;
+            all += d;
+            if (ring) {
+                g0 = fmaf(ring[(size_t)r * 2], d, g0);
+                g1 = fmaf(ring[(size_t)r * 2 + 1], d, g1);
+            }
         }
     }
     if (zrun >= 0) atomicAdd(G + (size_t)zrun * SCANN_D + n, run);
@@ -736,7 +751,7 @@ extern "C" int scann_embed_backward(const int32_t* atomic, const float* ring, in
                                     float* dbr, float* dWe, float* dbe, const void* drop_ctl, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     cudaMemsetAsync(G_ws, 0, (size_t)(n_atoms + 3) * SCANN_D * sizeof(float), st);
-    int rows_per_cta = 32;
+    int rows_per_cta = 16;
     embed_bwd_gather_kernel<<<(R + rows_per_cta - 1) / rows_per_cta, 128, 0, st>>>(atomic, ring, R, n_atoms, t0, dx0,
                                                                                   G_ws, rows_per_cta,
                                                                                   (const ScannDropCtl*)drop_ctl);

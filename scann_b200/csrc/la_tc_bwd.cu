@@ -246,18 +246,11 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
             tc_fence_after();
             b_issue_3xtf32(t_whi, t_wlo, smem_u32(sHi), smem_u32(sLo), t_dm, t_dc, bar, a.mma_rows);     // d_a^T = Wk dk^T
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
-        tc_fence_after();
-        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
-        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane, a.mma_rows);
-        tc_fence_before();
-        group_sync(grp, GT);
-        // ---- phase D: d_nbr = d_a * g' -> dx[j] ; dg' (+)= d_a * x[j]
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {
-            float4 gp[4], xj[4], dg[4];
-            int jj[4];
+        // ---- phase D: d_nbr = d_a * g' -> dx[j] ; dg' (+)= d_a * x[j].  The loads of its first four rows are issued
+        // before the wait for the MMAs, the second four behind the first four's arithmetic
+        float4 gp[4], xj[4], dg[4];
+        int jj[4];
+        auto load_d = [&](int hb) {
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii, r = wg + WG * i;
@@ -270,20 +263,31 @@ __global__ void __launch_bounds__(LTC_THREADS, 1) la_attn_bwd_tc_kernel(const La
                     if (a.dg_accum) dg[ii] = ld4(a.dg + (rowbase + r) * SCANN_D + lane * 4);
                 }
             }
+        };
+        auto apply_d = [&](int hb) {
 #pragma unroll
             for (int ii = 0; ii < 4; ++ii) {
                 const int i = hb * 4 + ii, r = wg + WG * i;
                 if (pc[i] < 0) continue;
-                float4 da = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
-                if (pc[i] >= 0) {
-                    red_add4(a.dx_scatter + (size_t)jj[ii] * SCANN_D + lane * 4, da.x * gp[ii].x, da.y * gp[ii].y,
-                             da.z * gp[ii].z, da.w * gp[ii].w);
-                    dg[ii] = make_float4(fmaf(da.x, xj[ii].x, dg[ii].x), fmaf(da.y, xj[ii].y, dg[ii].y),
-                                         fmaf(da.z, xj[ii].z, dg[ii].z), fmaf(da.w, xj[ii].w, dg[ii].w));
-                }
-                st4(a.dg + (rowbase + r) * SCANN_D + lane * 4, dg[ii]);
+                const float4 da = *reinterpret_cast<const float4*>(sS + tc_off4(r, lane));
+                red_add4(a.dx_scatter + (size_t)jj[ii] * SCANN_D + lane * 4, da.x * gp[ii].x, da.y * gp[ii].y,
+                         da.z * gp[ii].z, da.w * gp[ii].w);
+                st4(a.dg + (rowbase + r) * SCANN_D + lane * 4,
+                    make_float4(fmaf(da.x, xj[ii].x, dg[ii].x), fmaf(da.y, xj[ii].y, dg[ii].y),
+                                fmaf(da.z, xj[ii].z, dg[ii].z), fmaf(da.w, xj[ii].w, dg[ii].w)));
             }
-        }
+        };
+        load_d(0);
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        tc_fence_after();
+        if (t + t_step >= nt) pdl_trigger();             // last tile of this group, only its epilogue is left
+        b_tmem_to_rows(t_dm, t_dc, sS, wg, lane, a.mma_rows);
+        tc_fence_before();
+        group_sync(grp, GT);
+        apply_d(0);
+        load_d(1);
+        apply_d(1);
         group_sync(grp, GT);
     }
     pdl_trigger();

@@ -26,18 +26,36 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     const float rmse = sqrtf(sse[0] / h.batch);
     const float scale = 1.0f / (h.batch * rmse);
     float reg = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        float w = p[i];
-        reg = fmaf(l2mask[i] * w, w, reg);          // l2 penalty of the weights the loss was evaluated with
-        float gr = fmaf(g[i], scale, 2.0f * h.l2 * l2mask[i] * w);
-        if (grad_out) grad_out[i] = gr;
+    auto one = [&](float w, float gi, float lm, float& mi, float& vi, float& gr) -> float {
+        reg = fmaf(lm * w, w, reg);                  // l2 penalty of the weights the loss was evaluated with
+        gr = fmaf(gi, scale, 2.0f * h.l2 * lm * w);
+        if (!apply) return w;
+        mi = h.b1 * mi + (1.0f - h.b1) * gr;
+        vi = h.b2 * vi + (1.0f - h.b2) * gr * gr;
+        return w - h.alpha * mi / (sqrtf(vi) + h.eps);
+    };
+    // 16-byte accesses over the aligned body of the arena (seven streams of n floats), scalar tail
+    const bool al16 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)l2mask | (uintptr_t)grad_out) & 15) == 0;
+    const int n4 = al16 ? n >> 2 : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        const float4 w = reinterpret_cast<const float4*>(p)[i], gi = reinterpret_cast<const float4*>(g)[i],
+                     lm = reinterpret_cast<const float4*>(l2mask)[i];
+        float4 mi = make_float4(0.f, 0.f, 0.f, 0.f), vi = mi, gr, o;
+        if (apply) { mi = reinterpret_cast<const float4*>(m)[i]; vi = reinterpret_cast<const float4*>(v)[i]; }
+        o.x = one(w.x, gi.x, lm.x, mi.x, vi.x, gr.x); o.y = one(w.y, gi.y, lm.y, mi.y, vi.y, gr.y);
+        o.z = one(w.z, gi.z, lm.z, mi.z, vi.z, gr.z); o.w = one(w.w, gi.w, lm.w, mi.w, vi.w, gr.w);
+        if (grad_out) reinterpret_cast<float4*>(grad_out)[i] = gr;
         if (apply) {
-            float mi = h.b1 * m[i] + (1.0f - h.b1) * gr;
-            float vi = h.b2 * v[i] + (1.0f - h.b2) * gr * gr;
-            m[i] = mi;
-            v[i] = vi;
-            p[i] = w - h.alpha * mi / (sqrtf(vi) + h.eps);
+            reinterpret_cast<float4*>(m)[i] = mi;
+            reinterpret_cast<float4*>(v)[i] = vi;
+            reinterpret_cast<float4*>(p)[i] = o;
         }
+    }
+    for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float mi = apply ? m[i] : 0.f, vi = apply ? v[i] : 0.f, gr;
+        const float o = one(p[i], g[i], l2mask[i], mi, vi, gr);
+        if (grad_out) grad_out[i] = gr;
+        if (apply) { m[i] = mi; v[i] = vi; p[i] = o; }
     }
     reg = warp_sum(reg);
     if ((threadIdx.x & 31) == 0) atomicAdd(sse_rw + 2, reg);
@@ -55,7 +73,7 @@ __global__ void loss_value_kernel(const float* __restrict__ sse, float batch, fl
 extern "C" int scann_adam_step(float* params, const float* grads, float* m, float* v, const float* l2mask, int n,
                                float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream) {
     if (n <= 0) return 0;
-    int grid = (n + 255) / 256;
+    int grid = (n / 4 + 255) / 256 + 1;
     if (grid > 1184) grid = 1184;
     adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, grads, m, v, l2mask, n, sse,
                                                         (const AdamScalars*)scalars_dev, grad_out, apply);
