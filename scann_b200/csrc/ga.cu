@@ -30,20 +30,23 @@ __device__ __forceinline__ float block_max_128(float v, float* s_red) {
 __device__ float ga_scores(const float* __restrict__ qk, const uint8_t* __restrict__ mask, int M, int norm,
                            float* s_Q, float* s_s, float* s_ga, float* s_red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // loads are unconditional and selected afterwards (rows of padded atoms exist and are finite or not, the
+    // select drops them): a load guarded by the mask byte would make every iteration a dependent round trip
     float Q = 0.f;
-    for (int i = 0; i < M; ++i)
-        if (mask[i]) Q += qk[(size_t)i * 2 * SCANN_D + tid];
+#pragma unroll 8
+    for (int i = 0; i < M; ++i) {
+        const float q = qk[(size_t)i * 2 * SCANN_D + tid];
+        Q += mask[i] ? q : 0.f;
+    }
     s_Q[tid] = Q;
     __syncthreads();
     const float4 Q4 = ld4(s_Q + lane * 4);
+#pragma unroll 4
     for (int i = warp; i < M; i += GA_THREADS / 32) {
-        float v = 0.f;
-        if (mask[i]) {
-            float4 q = ld4(qk + (size_t)i * 2 * SCANN_D + lane * 4);
-            float4 k = ld4(qk + (size_t)i * 2 * SCANN_D + SCANN_D + lane * 4);
-            v = k.x * (Q4.x - q.x) + k.y * (Q4.y - q.y) + k.z * (Q4.z - q.z) + k.w * (Q4.w - q.w);
-        }
-        v = warp_sum(v);
+        const float4 q = ld4(qk + (size_t)i * 2 * SCANN_D + lane * 4);
+        const float4 k = ld4(qk + (size_t)i * 2 * SCANN_D + SCANN_D + lane * 4);
+        float v = k.x * (Q4.x - q.x) + k.y * (Q4.y - q.y) + k.z * (Q4.z - q.z) + k.w * (Q4.w - q.w);
+        v = warp_sum(mask[i] ? v : 0.f);
         if (lane == 0) s_s[i] = v;
     }
     __syncthreads();
@@ -97,12 +100,16 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_fwd_kernel(const float* __
     ga_scores(qkb, mb, M, norm, s_Q, s_s, s_ga, s_red);
     for (int i = tid; i < M; i += GA_THREADS) ga[(size_t)b * M + i] = s_ga[i];
     float c = 0.f;
-    for (int i = 0; i < M; ++i)
-        if (mb[i]) c = fmaf(s_ga[i], qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid], c);
+#pragma unroll 8
+    for (int i = 0; i < M; ++i) {
+        const float k = qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid];
+        c = fmaf(s_ga[i], mb[i] ? k : 0.f, c);
+    }
     s_ctx[tid] = c;
     if (ctx_out) ctx_out[(size_t)b * SCANN_D + tid] = c;
     __syncthreads();
     float t = bb[tid];
+#pragma unroll 16
     for (int d = 0; d < SCANN_D; ++d) t = fmaf(s_ctx[d], __ldg(Wb + (size_t)d * SCANN_D + tid), t);
     if (tb_out) tb_out[(size_t)b * SCANN_D + tid] = t;
     float yy = block_sum_128(swish_f(t) * wp[tid], s_red) + bp[0];
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_bwd_kernel(
     __syncthreads();
     {
         float dc = 0.f;
+#pragma unroll 16
         for (int n = 0; n < SCANN_D; ++n) dc = fmaf(s_dtb[n], __ldg(WbT + (size_t)n * SCANN_D + tid), dc);
         s_dctx[tid] = dc;
     }
@@ -152,13 +160,11 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_bwd_kernel(
     // d_ga_i = m_i <d_ctx, k_i>
     {
         const float4 dc4 = ld4(s_dctx + lane * 4);
+#pragma unroll 4
         for (int i = warp; i < M; i += GA_THREADS / 32) {
-            float v = 0.f;
-            if (mb[i]) {
-                float4 k = ld4(qkb + (size_t)i * 2 * SCANN_D + SCANN_D + lane * 4);
-                v = k.x * dc4.x + k.y * dc4.y + k.z * dc4.z + k.w * dc4.w;
-            }
-            v = warp_sum(v);
+            const float4 k = ld4(qkb + (size_t)i * 2 * SCANN_D + SCANN_D + lane * 4);
+            float v = k.x * dc4.x + k.y * dc4.y + k.z * dc4.z + k.w * dc4.w;
+            v = warp_sum(mb[i] ? v : 0.f);
             if (lane == 0) s_ds[i] = v;
         }
     }
@@ -181,12 +187,16 @@ __global__ void __launch_bounds__(GA_THREADS) ga_head_bwd_kernel(
     // d_Q[d] = sum_i d_s_i m_i k_i[d]
     const float Q = s_Q[tid], dctx = s_dctx[tid];
     float dQ = 0.f;
-    for (int i = 0; i < M; ++i)
-        if (mb[i]) dQ = fmaf(s_ds[i], qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid], dQ);
+#pragma unroll 8
     for (int i = 0; i < M; ++i) {
+        const float k = qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid];
+        dQ = fmaf(s_ds[i], mb[i] ? k : 0.f, dQ);            // s_ds is 0 for masked atoms, k may be anything
+    }
+#pragma unroll 4
+    for (int i = 0; i < M; ++i) {
+        const float q = qkb[(size_t)i * 2 * SCANN_D + tid], k = qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid];
         float dq = 0.f, dk = 0.f;
         if (mb[i]) {
-            float q = qkb[(size_t)i * 2 * SCANN_D + tid], k = qkb[(size_t)i * 2 * SCANN_D + SCANN_D + tid];
             dk = s_ga[i] * dctx + s_ds[i] * (Q - q);
             dq = dQ - s_ds[i] * k;
         }
