@@ -356,7 +356,10 @@ def run_ours(args):
                            "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     if n_wg:
         # every weight-gradient GEMM of the step in one launch: reads each saved per-pair tensor once
-        bytes_wg = L * (4 * 512.0 * P_valid + 512.0 * P_valid) + L * 8 * 512.0 * A_valid
+        # (per pair and layer: g', d_k, g, d_pre + the gathered x[j]; per atom: x, s_pre, t, dq and the four
+        # ResidualNorm operands -- models without geometry update have no g / d_pre / s_pre / t problems)
+        gu = bool(CFG["model"].get("g_update", True))
+        bytes_wg = L * ((5 if gu else 3) * 512.0 * P_valid + (8 if gu else 6) * 512.0 * A_valid)
         roof["wgrad_batch"] = {"achieved": bytes_wg / (ms_wg * 1e-3) / 1e9, "ms_per_launch": ms_wg,
                                "frac": bytes_wg / (ms_wg * 1e-3) / 1e9 / peaks["hbm_gbs"]}
     # bounded CPU sample (rank 0, N=1 only)

@@ -184,10 +184,13 @@ __global__ void __launch_bounds__(PLAN_GSZ) plan_chain_kernel(
         const uint8_t* m = nmask + (size_t)r * N;
         const int32_t* j = nbr + (size_t)r * N;
         int bad = 0;
+        // unconditional loads, selected afterwards: a load behind `if (m[n])` would make every slot a dependent
+        // round trip through L2
+#pragma unroll 4
         for (int n = 0; n < N; ++n) {
-            if (m[n]) {
+            const int mm = m[n], v = j[n];
+            if (mm) {
                 ++c;
-                const int v = j[n];
                 bad |= (v < 0) | (v >= M);
             }
         }
@@ -265,18 +268,21 @@ __global__ void __launch_bounds__(PLAN_GSZ) plan_chain_kernel(
             const int b = r / M;
             const uint8_t* m = nmask + (size_t)r * N;
             int k = 0;
+#pragma unroll 4
             for (int n = 0; n < N; ++n) {
-                if (m[n]) {
-                    const size_t s = (size_t)r * N + n;
+                const size_t s = (size_t)r * N + n;
+                const int mm = m[n], jn = nbr[s];
+                const float dn = dist[s], wn = weight[s];
+                if (mm) {
                     const int p = rp + k;
-                    const int j = b * M + nbr[s];
+                    const int j = b * M + jn;
                     if (valid_rows) { valid_rows[vbase + k] = p; valid_j[vbase + k] = j; }
                     ++k;
                     pair_c[p] = r;
                     pair_j[p] = j;
                     pair_slot[p] = (int32_t)s;
-                    pair_d[p] = dist[s];
-                    pair_w[p] = weight[s];
+                    pair_d[p] = dn;
+                    pair_w[p] = wn;
                 }
             }
         }

@@ -22,7 +22,7 @@ SCANN_GRAPHS=0 python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_plain.l
 SCANN_GRAPHS=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 290 -c 150 --csv \
   --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"
-SCANN_GRAPHS=0 ncu --set full --clock-control none --import-source on -k regex:'la_.*_tc_kernel|wgrad_batch|dense_chain' -s 40 -c 16 \
+SCANN_GRAPHS=0 ncu --set full --clock-control none --import-source on -k regex:'la_.*_tc|wgrad_batch|dense_chain|plan_chain|geom_init' -s 60 -c 36 \
   -o $O/${TAG}_la_tc python bench.py --steps 2 --warmup 3 --no-cpu > $O/${TAG}_ncu2.log 2>&1
 echo "ncu full rc=$?"
 ls -la $O | tail -20
