@@ -155,6 +155,10 @@ def cpu_train_step_fn():
     return step, cores
 
 
+def emit(line: str) -> None:          # replaced in main(): stdout is reserved for this one line
+    print(line)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -169,7 +173,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     v = n / dt
     sample = f"{args.steps} train steps of one 128-structure QM9-shaped batch after {args.warmup} warm-up"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -403,7 +407,7 @@ def run_ours(args):
         "infer": {"value": B * world * args.steps / (infer_ms * 1e-3), "unit": UNIT,
                   "note": "forward incl. ga_score, inputs resident in HBM"},
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     finish()
 
 
@@ -418,6 +422,21 @@ def main():
                     help="qm9 (default, BASELINE.json configs[1]) | mp2018 | fullerene: other shapes, for reference")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line.  Libraries write there too (NCCL prints "NCCL version ..." to stdout
+    # under NCCL_DEBUG=VERSION, whatever NCCL_DEBUG_FILE says), so file descriptor 1 points at stderr until the
+    # line is printed.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global emit
+
+    def emit(line: str) -> None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(line)
+        sys.stdout.flush()
+        os.dup2(2, 1)
+
     if args.impl == "reference":
         run_reference(args)
     else:
