@@ -287,9 +287,12 @@ def run_ours(args):
         pass
     clocks = sampler.stop() if rank == 0 else None
     # ---- instrumented pass: CUDA events around the local-attention kernels
+    # (eager launches, one event pair per call: a ~2 ms spin kernel in front of every step lets the host enqueue the
+    # whole step ahead of the GPU, so that an interval holds the kernels only and not the host's launch gaps)
     eng.prof = {}
     for _ in range(args.steps):
         flush.fill_(1.0)
+        torch.cuda._sleep(4_000_000)
         step_device()
     torch.cuda.synchronize()
     prof = eng.prof_summary()

@@ -293,6 +293,26 @@ int scann_adam_step(float* params, const float* grads, float* m, float* v, const
 int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch, float l2,
                      float* out3, void* stream);
 
+/* ---- gradient exchange over NVLink peer memory, fused into the optimiser -------------------------------------
+ * Data-parallel training (one process per GPU; the reference trains on one device, scann_model.py:232-241): instead of
+ * an NCCL all-reduce followed by scann_adam_step, every rank keeps its gradient arena in a block that the other ranks
+ * of the node map through CUDA IPC, and the optimiser kernel sums the peers' arenas itself (fixed rank order, so
+ * the parameters stay bit-identical on all ranks).  Block = [n + 4 floats, padded to 64] [64 x uint32 flag words];
+ * scann_p2p_alloc returns it zeroed.  ScannP2PBlock (device copy passed as block_dev):
+ *   const float* arena[8]; uint32_t* flags[8]; int world, rank;      (entry `rank` = the local block)
+ * Per step: scann_p2p_begin_step (waits until no peer still reads the local arena, zeroes sums[0..3]) -> zero the
+ * arena, forward, backward -> scann_adam_p2p_step (publishes / waits for "backward finished" flags, sums, updates,
+ * publishes "finished reading").  sums[0..2] = what scann_adam_step leaves in sse[0..2] (pass it to scann_loss_value).
+ * All waiting happens inside the kernels, so the sequence can be captured into a CUDA graph. */
+int scann_p2p_alloc(long long bytes, void** out_ptr);
+int scann_p2p_free(void* ptr);
+int scann_p2p_export(void* ptr, void* handle64);
+int scann_p2p_import(const void* handle64, void** out_ptr);
+int scann_p2p_close(void* ptr);
+int scann_p2p_begin_step(const void* block_dev, float* sums, void* stream);
+int scann_adam_p2p_step(float* params, float* m, float* v, const float* l2mask, int n, const void* block_dev,
+                        float* sums, const void* scalars_dev, float* grad_out, int apply, void* stream);
+
 /* ---- diagnostics --------------------------------------------------------------------------------
  * One 128x128x128 tile product on the tcgen05 tensor cores (self-test of descriptors / layouts).
  * layout 0: A@W, 1: A^T@W, 2: A@W^T, 3: A@W with A in tensor memory; nprod 1 (TF32) or 3 (3xTF32). */

@@ -54,6 +54,13 @@ PROTOTYPES = {
     "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_adam_step": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
     "scann_loss_value": (ci, [vp, vp, ci, vp, C.c_float, C.c_float, vp, vp]),
+    "scann_p2p_alloc": (ci, [C.c_longlong, C.POINTER(vp)]),
+    "scann_p2p_free": (ci, [vp]),
+    "scann_p2p_export": (ci, [vp, vp]),
+    "scann_p2p_import": (ci, [vp, C.POINTER(vp)]),
+    "scann_p2p_close": (ci, [vp]),
+    "scann_p2p_begin_step": (ci, [vp, vp, vp]),
+    "scann_adam_p2p_step": (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp]),
     "scann_tc_probe": (ci, [vp, vp, vp, ci, ci, vp]),
     "scann_tc_time": (ci, [vp, ci, ci, ci, vp]),
     "scann_debug_clocks": (ci, [vp]),

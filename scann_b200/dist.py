@@ -47,11 +47,70 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
+class P2PExchange:
+    """Gradient exchange fused into the optimiser kernel over NVLink peer memory (scann_b200/csrc/p2p.cu): every rank's
+    gradient arena sits in a block the other ranks of the node map through CUDA IPC; ``scann_adam_p2p_step`` sums the
+    peers' arenas while it updates.  Replaces ``allreduce(grads)`` + ``scann_adam_step`` of the NCCL path; the engine's
+    ``grads`` tensor is re-pointed at the shared block, so call this before the first train step."""
+
+    MAX_RANKS = 8
+
+    def __init__(self, engine, rank: int, world: int):
+        import ctypes as C
+        import numpy as np
+        from ._abi import check, lib
+        if world > self.MAX_RANKS:
+            raise ValueError(f"peer-memory exchange supports up to {self.MAX_RANKS} ranks of one node")
+        n = engine.layout.total
+        nfl = (n + 4 + 63) // 64 * 64
+        nbytes = nfl * 4 + 64 * 4
+        ptr = C.c_void_p()
+        check(lib.scann_p2p_alloc(nbytes, C.byref(ptr)), "p2p_alloc")
+        self.local = int(ptr.value)
+        handle = (C.c_ubyte * 64)()
+        check(lib.scann_p2p_export(self.local, C.cast(handle, C.c_void_p)), "p2p_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle))
+        self.bases = []
+        for r in range(world):
+            if r == rank:
+                self.bases.append(self.local)
+                continue
+            buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+            peer = C.c_void_p()
+            check(lib.scann_p2p_import(C.cast(buf, C.c_void_p), C.byref(peer)), f"p2p_import(rank {r})")
+            self.bases.append(int(peer.value))
+        # ScannP2PBlock: const float* arena[8]; uint32_t* flags[8]; int world, rank
+        blk = np.zeros(17, np.int64)
+        for r, base in enumerate(self.bases):
+            blk[r] = base
+            blk[8 + r] = base + nfl * 4
+        blk[16] = (rank << 32) | world          # little endian: {int world, int rank}
+        dev = engine.device
+        self.block = torch.from_numpy(blk).to(dev)
+        self.sums = torch.zeros(4, dtype=torch.float32, device=dev)
+
+        class _Raw:                              # zero-copy torch view of the shared block's arena
+            __cuda_array_interface__ = {"shape": (n + 4,), "typestr": "<f4", "data": (self.local, False), "version": 3}
+
+        self._raw = _Raw()
+        engine.grads = torch.as_tensor(self._raw, device=dev)
+        assert engine.grads.data_ptr() == self.local
+        engine.p2p = self
+        self.rank, self.world = rank, world
+        dist.barrier()                           # every rank has mapped every block before anyone starts a step
+
+
 def attach(model, world: int) -> None:
-    """Make ``model.train_on_batch`` data-parallel: local shard in, global-batch semantics out."""
+    """Make ``model.train_on_batch`` data-parallel: local shard in, global-batch semantics out.  The exchange is one
+    NCCL all-reduce of the gradient arena per step, or -- SCANN_P2P_REDUCE=1, ranks of one node -- the peer-memory
+    form fused into the optimiser kernel (``P2PExchange``)."""
     if world > 1:
         model.allreduce = allreduce_sum
         model.world_size = world
+        if os.environ.get("SCANN_P2P_REDUCE", "0") == "1" and torch.cuda.is_available():
+            P2PExchange(model.engine, env_world()[0], world)
+            model.allreduce = None
         # every rank draws its own Dropout masks (its shard holds different structures)
         rank = env_world()[0]
         model.engine.dropout_seed = (model.engine.dropout_seed + 7919 * rank) & 0x7FFFFFFF

@@ -79,6 +79,7 @@ class Engine:
         self.last_drop_seed = 0
         self._adam_ev = None
         self.step_count = 0
+        self.p2p = None        # dist.P2PExchange: gradient exchange over peer memory, fused into the optimiser kernel
         # RBF centres: np.linspace(0, gaussian_d, 20) / np.linspace(0, 2*pi, 20), float32 (scann_model.py:378,384)
         self.centers_d = torch.from_numpy(np.linspace(0, spec.gaussian_d, N_RBF, dtype="float32")).to(dev)
         self.centers_w = torch.from_numpy(np.linspace(0, np.pi * 2, N_RBF, dtype="float32")).to(dev)
@@ -1134,7 +1135,8 @@ class Engine:
     def loss_value(self, batch_global: int) -> torch.Tensor:
         """[loss (RMSE + l2 terms), RMSE, MAE] of the batch whose SSE sits in the gradient arena."""
         n = self.layout.total
-        check(lib.scann_loss_value(_p(self.params), _p(self.l2mask), n, _p(self.grads, n), float(batch_global),
+        sse = _p(self.p2p.sums) if self.p2p is not None else _p(self.grads, n)
+        check(lib.scann_loss_value(_p(self.params), _p(self.l2mask), n, sse, float(batch_global),
                                    L2_COEF, _p(self.loss_out), self._stream()), "loss_value")
         self.launches += 1
         return self.loss_out
@@ -1171,8 +1173,10 @@ class Engine:
         else:
             g = b.graphs.get(key)
             if g is None:
-                # one eager pass allocates workspaces / warms up, then capture on a side stream
-                self._train_body(b, allreduce, apply=False, want_grads=False, replan=replan)
+                # one eager pass allocates workspaces / warms up, then capture on a side stream.  With the peer-memory
+                # exchange the pass stays local (it applies nothing): ranks that meet a new batch shape at different
+                # steps would otherwise disagree on the number of exchanges
+                self._train_body(b, allreduce, apply=False, want_grads=False, replan=replan, exchange=False)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 n0 = self.launches
@@ -1186,9 +1190,14 @@ class Engine:
         if apply:
             self.step_count += 1
 
-    def _train_body(self, b: Batch, allreduce, apply: bool, want_grads: bool, replan: bool) -> None:
+    def _train_body(self, b: Batch, allreduce, apply: bool, want_grads: bool, replan: bool, exchange: bool = True) -> None:
+        p2p = self.p2p if exchange else None
         if replan:
             self._plan(b)
+        if self.p2p is not None:
+            # no peer still reads the arena that is zeroed next (scann_b200/csrc/p2p.cu); also in the local warm pass
+            check(lib.scann_p2p_begin_step(_p(self.p2p.block), _p(self.p2p.sums), self._stream()), "p2p_begin_step")
+            self.launches += 1
         self.grads.zero_()
         ws = self._workspace(b, True)
         if self.use_side_stream:
@@ -1204,9 +1213,16 @@ class Engine:
                 self._prep_event.record(self.side_stream)
         self.forward(b, training=True)
         self.backward(b, b.target)
+        n = self.layout.total
+        if p2p is not None:
+            check(lib.scann_adam_p2p_step(_p(self.params), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
+                                          _p(self.p2p.block), _p(self.p2p.sums), _p(self.adam_scalars),
+                                          _p(self.grad_out) if want_grads else 0, int(apply), self._stream()),
+                  "adam_p2p_step")
+            self.launches += 1
+            return
         if allreduce is not None:
             allreduce(self.grads)
-        n = self.layout.total
         check(lib.scann_adam_step(_p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
                                   _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
                                   int(apply), self._stream()), "adam_step")
