@@ -7,8 +7,8 @@
 // Each kernel keeps ONE 128x128 weight block stationary in tensor memory as the M x K operand
 // (W^T: lane = output feature, column = input feature; hi and lo tf32 parts, 256 columns) and streams
 // 128-pair tiles through shared memory as the N x K operand (canonical K-major image, tc_common.cuh).
-// D^T = W^T @ X^T lands in tensor memory (lane = feature, column = pair row); main (hi*hi) and
-// correction (lo*hi + hi*lo) terms use separate accumulators (256 columns).  The accumulator is moved to
+// D^T = W^T @ X^T lands in tensor memory (lane = feature, column = pair row) in ONE accumulator: the two
+// correction products (lo*hi, hi*lo) are issued before the hi*hi product (see issue_3xtf32).  The accumulator is moved to
 // shared memory transposed and the row-wise epilogue runs warp-per-row with coalesced gathers that
 // were prefetched into registers while the tensor core was busy.
 //
