@@ -200,6 +200,19 @@ int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, const int32_t* 
                         const float* bk, const float* gamma_g, const float* beta_g, const float* gamma,
                         const float* beta, float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out,
                         float* k_out, const void* attn_drop, int drop_site, void* stream);
+/* The same forward as two warp-specialised, TMA-fed pipelines (la_pipe.cu) for pair plans with tile_stride 32
+ * (at most 32 valid neighbours per atom): a producer warp streams the tiles of g through a six-stage shared-memory
+ * ring with cp.async.bulk.tensor (and gathers the neighbour rows x[j] with cp.async), one warp issues the
+ * tcgen05.mma of each tile, three consumer groups run the row-wise epilogues and store the results with TMA.
+ * rows = tile_cap * 32 (row count of every per-pair tensor; per-pair tensors must be 128-byte aligned).
+ * which: bit 0 = geometry kernel, bit 1 = attention kernel.  status: the engine's int32[8] status buffer (word 0:
+ * flag bits, SCANN_ERR_PIPE_TIMEOUT = 16 when a bounded mbarrier wait gave up; words 1..4: where). */
+int scann_la_forward_pipe(int grid, long long rows, int which, const int32_t* ntiles, const int32_t* pair_c,
+                          const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
+                          const float* W2, const float* Wk, const float* bk, const float* gamma_g,
+                          const float* beta_g, const float* gamma, const float* beta, float* g_out, float* ctx_pre,
+                          float* out, float* attn, float* pre_out, float* k_out, const void* attn_drop,
+                          int drop_site, int32_t* status, void* stream);
 /* attn_drop (ScannDropCtl*, device, nullable) / drop_site: training-mode Dropout(0.05) on the attention
  * probabilities of use_drop models (attention.py:115-116,191-192); mask index = pair row * 8 + head. */
 /* LocalAttention.call with g_update=False (attention.py:155): geometry' = swish(rbf(d) @ Wf + bf) * w is

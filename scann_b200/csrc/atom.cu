@@ -788,7 +788,7 @@ extern "C" int scann_geom_init_forward(const int32_t* ntiles, int grid, int tile
                                        const float* pair_w, const float* centers_d, const float* centers_w,
                                        const float* Wd, const float* bd, const float* Ww, const float* bw, float* g0,
                                        void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
     scann_launch(geom_init_fwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, g0);
     return scann_check_launch("scann_geom_init_forward");
@@ -799,7 +799,7 @@ extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, int til
                                         const float* Wd, const float* bd, const float* Ww, const float* bw,
                                         const float* dg0, float* dWd, float* dbd, float* dWw, float* dbw,
                                         void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("geom_init: tile_stride must be 64 or 128"); return 1; }
     scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
     return scann_check_launch("scann_geom_init_backward");
@@ -811,7 +811,7 @@ extern "C" int scann_noupdate_geom_backward(const int32_t* ntiles, int grid, int
                                             const float* pair_d, const float* pair_w, const float* centers_d,
                                             const float* Wf, const float* bf, const float* dg, float* dWf, float* dbf,
                                             void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("noupdate_geom_backward: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("noupdate_geom_backward: tile_stride must be 64 or 128"); return 1; }
     scann_launch(noupdate_geom_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w,
                  centers_d, Wf, bf, dg, dWf, dbf);
     return scann_check_launch("scann_noupdate_geom_backward");

@@ -676,6 +676,10 @@ static int la_fwd_configure() {
         e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(la_geom_fwd_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA4_GEOM_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_geom_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(la_attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_SMEM);
     if (e != cudaSuccess) { scann_set_error("la_forward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
     configured = true;
     return 0;
@@ -692,7 +696,7 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, cons
                                    const float* gamma_g, const float* beta_g, const float* gamma, const float* beta,
                                    float* g_out, float* ctx_pre, float* out, float* attn, float* pre_out, float* k_out,
                                    const void* attn_drop, int drop_site, void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_tc: tile_stride must be 32, 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_tc: mma_rows must be a multiple of 16 in 16..tile_stride"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
@@ -701,7 +705,11 @@ extern "C" int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, cons
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_out, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, k_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mma_rows,
                   (const ScannDropCtl*)attn_drop, drop_site};
-    if (tile_stride == 64) {
+    if (tile_stride == 32) {
+        // 32-row tile slots (the layout of the pipelined kernels, la_pipe.cu): four independent 4-warp groups
+        scann_launch(la_geom_fwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_SMEM, stream, ga);
+        scann_launch(la_attn_fwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    } else if (tile_stride == 64) {
         // four warp groups per CTA when the plan's tiles hold at most 48 rows (see the tc4 section above)
         const int m4 = mma_rows <= L4_ROWS ? scann_la_tc4_mask() : 0;
         if (m4 & 1) scann_launch(la_geom_fwd_tc4_kernel, dim3(grid), dim3(LTC_THREADS), LA4_GEOM_SMEM, stream, ga);
@@ -726,14 +734,15 @@ extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_r
                                             const float* bk, const float* gamma, const float* beta, float* ctx_pre,
                                             float* out, float* attn, float* g_save, float* k_out, const void* attn_drop,
                                             int drop_site, void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("la_forward_noupdate_tc: tile_stride must be 32, 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_forward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_fwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnArgs aa{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, nullptr, Wk, bk, gamma, beta,
                   ctx_pre, out, attn, k_out, pair_d, pair_w, centers, Wf, bf, g_save, mma_rows,
                   (const ScannDropCtl*)attn_drop, drop_site};
-    if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    if (tile_stride == 32) scann_launch(la_attn_fwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
+    else if (tile_stride == 64) scann_launch(la_attn_fwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     else scann_launch(la_attn_fwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_SMEM, stream, aa);
     return scann_check_launch("scann_la_forward_noupdate_tc");
 }

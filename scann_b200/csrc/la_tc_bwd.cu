@@ -665,6 +665,8 @@ static int la_bwd_configure() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_attn_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_BWD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_BWD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_attn_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_ATTN_BWD_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(la_geom_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_GEOM_BWD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_WGRAD_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(la_wgrad_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LA_WGRAD_SMEM);
     if (e != cudaSuccess) { scann_set_error("la_backward_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return 1; }
@@ -681,7 +683,7 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, con
                                     float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop,
                                     int drop_site, void* stream) {
     (void)wpart;
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_tc: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_tc: tile_stride must be 32, 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
@@ -689,7 +691,10 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, con
                      dg_has_up, dq, dx_scatter, dbk, mma_rows, (const ScannDropCtl*)attn_drop, drop_site};
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g, mma_rows};
-    if (tile_stride == 64) {
+    if (tile_stride == 32) {
+        scann_launch(la_attn_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        scann_launch(la_geom_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+    } else if (tile_stride == 64) {
         scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
         scann_launch(la_geom_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
     } else {
@@ -709,13 +714,14 @@ extern "C" int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_
                                              const float* proj, const float* g_new, float* kbuf, const float* WkT,
                                              const float* d_ctx, float* dg, float* dq, float* dx_scatter, float* dbk,
                                              const void* attn_drop, int drop_site, void* stream) {
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_noupdate_tc: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("la_backward_noupdate_tc: tile_stride must be 32, 64 or 128"); return 1; }
     if (mma_rows < 16 || mma_rows > tile_stride || mma_rows % 16) { scann_set_error("la_backward_noupdate_tc: bad mma_rows"); return 1; }
     if (la_bwd_configure()) return 1;
     if (grid <= 0) return 0;
     LaAttnBwdArgs ab{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x, proj, g_new, kbuf, WkT, d_ctx, dg,
                      0, dq, dx_scatter, dbk, mma_rows, (const ScannDropCtl*)attn_drop, drop_site};
-    if (tile_stride == 64) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+    if (tile_stride == 32) scann_launch(la_attn_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+    else if (tile_stride == 64) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     else scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
     return scann_check_launch("scann_la_backward_noupdate_tc");
 }

@@ -370,7 +370,7 @@ extern "C" int scann_plan_build(const uint8_t* neighbor_mask, const int32_t* nei
     cudaStream_t st = (cudaStream_t)stream_;
     long long Rll = (long long)B * M;
     if (Rll <= 0 || N <= 0 || Rll * N > 0x7fffffffLL) { scann_set_error("plan: bad shape B=%d M=%d N=%d", B, M, N); return 1; }
-    if (tile_stride != 64 && tile_stride != SCANN_TILE) { scann_set_error("plan: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != SCANN_TILE) { scann_set_error("plan: tile_stride must be 32, 64 or 128"); return 1; }
     if (tile_rows < 1 || tile_rows > tile_stride) { scann_set_error("plan: tile_rows must be in 1..tile_stride"); return 1; }
     int R = (int)Rll;
     int ngroups = (R + PLAN_GSZ - 1) / PLAN_GSZ;

@@ -300,7 +300,7 @@ extern "C" int scann_wgrad_batch_tc(int grid, const void* problems_dev, int npro
                                     const int32_t* pair_c, const int32_t* pair_j, const int32_t* valid_rows,
                                     const int32_t* valid_j, const int32_t* nvalid, void* stream) {
     if (nprob < 1 || nprob > WG_MAX_PROBLEMS) { scann_set_error("wgrad_batch_tc: nprob must be in 1..%d", WG_MAX_PROBLEMS); return 1; }
-    if (tile_stride != 64 && tile_stride != 128) { scann_set_error("wgrad_batch_tc: tile_stride must be 64 or 128"); return 1; }
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("wgrad_batch_tc: tile_stride must be 64 or 128"); return 1; }
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_batch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);

@@ -26,7 +26,8 @@ D = 128
 L2_COEF = 1e-4
 
 ERR_BITS = {1: "plan tile capacity exceeded", 2: "an atom has more than 128 valid neighbours",
-            4: "atomic number outside the embedding table", 8: "neighbour index outside [0, M)"}
+            4: "atomic number outside the embedding table", 8: "neighbour index outside [0, M)",
+            16: "a bounded mbarrier wait of a pipelined local-attention kernel gave up"}
 
 
 def _p(t: Optional[torch.Tensor], off_elems: int = 0) -> int:
@@ -66,7 +67,8 @@ class Engine:
         self.adam_v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.l2mask = torch.from_numpy(self.layout.l2_mask()).to(dev)
         self.grad_out = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # word 0: flag bits (ERR_BITS); words 1..4: {wait site, CTA, tile, stage} of a pipelined kernel that gave up
+        self.status = torch.zeros(8, dtype=torch.int32, device=dev)
         self.loss_out = torch.zeros(4, dtype=torch.float32, device=dev)
         # [0..7] optimiser scalars, [8..11] dropout control block (ScannDropCtl: seed, threshold, scale bits, enabled)
         self.adam_scalars = torch.zeros(16, dtype=torch.float32, device=dev)
@@ -110,7 +112,15 @@ class Engine:
         self.balance_tiles = os.environ.get("SCANN_BALANCE_TILES", "1") == "1"
         # rows per tile slot of the pair plan: 64 = two warp groups per CTA in the tensor-core local-attention
         # kernels (needs <= 64 neighbours per atom), 128 = one tile stream per CTA (also the SIMT engine)
-        self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "64"))
+        # 32 = the pipelined kernels (<= 32 neighbours per atom).  Default (0): 32 where the pipelined kernels apply,
+        # else 64, else 128.
+        self.tile_stride_pref = int(os.environ.get("SCANN_TILE_STRIDE", "0"))
+        # warp-specialised TMA pipelines for the local-attention kernels (la_pipe.cu, la_pipe_bwd.cu) on plans with
+        # 32-row tile slots: bit 0 geometry forward, 1 attention forward, 2 attention backward, 3 geometry backward.
+        # 0 keeps the round-1 kernels (four 4-warp groups per CTA on the same 32-row plan when SCANN_TILE_STRIDE=32).
+        self.la_pipe_built = 3
+        self.la_pipe = (int(os.environ.get("SCANN_LA_PIPE", str(self.la_pipe_built))) & self.la_pipe_built
+                        if (self.tc_la_fwd and self.tc_la_bwd) else 0)
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
         # local-attention kernels with four warp groups per CTA where the plan's tiles hold <= 48 rows (bit mask:
@@ -182,10 +192,13 @@ class Engine:
         return _p(self.grads, self.layout[name].offset + off)
 
     def check_status(self) -> None:
-        s = int(self.status.item())
+        words = self.status.cpu().tolist()
+        s = words[0]
         if s:
             self.status.zero_()
             msgs = [m for b, m in ERR_BITS.items() if s & b]
+            if s & 16:
+                msgs.append("wait site %d, CTA %d, tile %d, stage %d" % tuple(words[1:5]))
             raise _abi.ScannAbiError("device status: " + "; ".join(msgs))
 
     def set_params(self, arena: np.ndarray) -> None:
@@ -276,14 +289,20 @@ class Engine:
         ngroups = (R + PLAN_GSZ - 1) // PLAN_GSZ
         # rows per tile: fill whole waves of SMs (the kernels' cost per tile scales with its rows, and a
         # tile count just above a multiple of the SM count costs a whole extra round)
-        stride = 64 if (self.tile_stride_pref == 64 and self.tc_la_fwd and self.tc_la_bwd and N <= 32) else TILE
+        tc = self.tc_la_fwd and self.tc_la_bwd
+        pref = self.tile_stride_pref
+        stride = 64 if (pref in (0, 64) and tc and N <= 32) else TILE
+        if N <= 32 and tc and (pref == 32 or (pref == 0 and self.la_pipe and self.spec.g_update)):
+            stride = 32
         tile_rows = stride
         if P_host is not None and self.balance_tiles and N <= 64:
             slots = self.sm_count * (TILE // stride)
             waves = max(1, -(-P // (stride * slots)))      # more, smaller tiles only add per-tile latency (measured)
             tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
         # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
-        cap = (P // (tile_rows + 1 - N) + ngroups + 1 if N <= 64 else 2 * (P // TILE) + ngroups + 2)
+        # (and two consecutive tiles of a group together hold more than tile_rows rows)
+        cap = (min(P // (tile_rows + 1 - N), 2 * P // tile_rows + 1) + ngroups + 1 if N <= 64
+               else 2 * (P // TILE) + ngroups + 2)
         tile_cap = max(64, (cap + 63) // 64 * 64)
         key = (B, M, N, tile_cap, tile_rows, stride)
         b = self._batches.get(key)
@@ -629,8 +648,8 @@ class Engine:
                 pass
             elif self.tc_la_fwd:
                 save = training and self.tc_la_bwd
-                check(lib.scann_la_forward_tc(self.la_grid, b.stride, b.mma_rows, *la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
-                                              *self._adrop(training, l), st), "la_forward_tc")
+                self._la_forward_tc(b, la_args, _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0,
+                                    self._adrop(training, l), st)
                 self.launches += 1
             else:
                 check(lib.scann_la_forward(self.la_grid, *la_args, st), "la_forward")
@@ -658,6 +677,21 @@ class Engine:
         self._pdl(False)
         self.launches += 1
         return ws["y"], ws["ga"]
+
+    def _la_forward_tc(self, b: Batch, la_args, pre_out: int, k_out: int, adrop, st: int) -> None:
+        """LocalAttention forward (g_update=True) of one layer: the pipelined kernels on 32-row plans (``la_pipe`` bits
+        0 / 1), else the round-1 tensor-core kernels.  A half that is switched off is run by the round-1 kernels
+        (development: both kernels of the old form run first, the selected pipelined half then rewrites its outputs)."""
+        which = self.la_pipe & 3 if b.stride == 32 else 0
+        if which != 3:
+            check(lib.scann_la_forward_tc(self.la_grid, b.stride, b.mma_rows, *la_args, pre_out, k_out, *adrop, st),
+                  "la_forward_tc")
+        if which:
+            (ntiles, _a0, _a1, _cnt, _rowptr, pair_c, pair_j, x_in, proj, g_in, W2, Wk, bk, gg, bg, gam, bet, g_out,
+             ctxpre, out, attn) = la_args
+            check(lib.scann_la_forward_pipe(self.la_grid, b.rows, which, ntiles, pair_c, pair_j, x_in, proj, g_in, W2, Wk, bk,
+                                            gg, bg, gam, bet, g_out, ctxpre, out, attn, pre_out, k_out, *adrop,
+                                            _p(self.status), st), "la_forward_pipe")
 
     def _forward_chained(self, b: Batch, ws: dict, training: bool, attn_out: Optional[list]):
         """Layers of the forward pass with the per-atom Dense layers fused (scann_dense_chain):
@@ -710,13 +744,13 @@ class Engine:
                 g_in = gs[l] if training else gs[l % 2]
                 g_out = gs[l + 1] if training else gs[(l + 1) % 2]
                 save = training and self.tc_la_bwd
-                check(lib.scann_la_forward_tc(
-                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                self._la_forward_tc(b, (
+                    _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
                     _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), _p(g_in), self.w(fg, D * D),
                     self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"), self.w(f"{la}/layer_norm_g/gamma"),
                     self.w(f"{la}/layer_norm_g/beta"), self.w(f"{la}/layer_norm/gamma"),
-                    self.w(f"{la}/layer_norm/beta"), _p(g_out), _p(ctxpre), _p(out), _p(attn),
-                    _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, *self._adrop(training, l), st), "la_forward_tc")
+                    self.w(f"{la}/layer_norm/beta"), _p(g_out), _p(ctxpre), _p(out), _p(attn)),
+                    _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, self._adrop(training, l), st)
                 self.launches += 2
             else:
                 check(lib.scann_la_forward_noupdate_tc(
@@ -1221,7 +1255,9 @@ class Engine:
                   "adam_p2p_step")
             self.launches += 1
             return
-        if allreduce is not None:
+        if allreduce is not None and exchange:
+            # (not in the local warm-up pass of a new shape class, whose result is discarded: ranks that meet new
+            # shapes at different steps must still issue the same number of collectives)
             allreduce(self.grads)
         check(lib.scann_adam_step(_p(self.params), _p(self.grads), _p(self.adam_m), _p(self.adam_v), _p(self.l2mask), n,
                                   _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
