@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const _
                 bulk_load(c.idx + s * 64 + 32, a.pair_j + (size_t)t * PT, 128u, &c.full[s]);
             }
         }
+        __syncwarp();
     } else if (warp == PF_CW + 1) {
         // ================= MMA issue =================
         int i = 0;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const _
             const uint32_t ph = (uint32_t)(i / PF_NS) & 1u;
             pipe_wait(&c.ready[s], ph, c.dead, a.status, 2, t, s);
             tc_fence_after();
+            __syncwarp();                                       // the lanes leave the wait loop at different times
             if (tc_elect_one()) {
                 const uint32_t A = smem_u32(c.stages + (size_t)s * PF_STAGE);
                 pipe_issue_3xtf32(t_wraw, t_wlo, A, A + PT_IMG, t_acc0 + s * PT, &c.accf[s]);
@@ -299,6 +301,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
                 jn = pcv >= 0 ? a.pair_j[(size_t)tn * PT + lane] : 0;
             }
             pipe_wait(&c.empty[s], ph ^ 1u, c.dead, a.status, 11, t, s);
+            __syncwarp();
             uint8_t* A = c.stages + (size_t)s * PF_STAGE;
             if (lane == 0) {
                 mbar_expect_tx(&c.full[s], PT_IMG + 256u);
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
             const uint32_t ph = (uint32_t)(i / PF_NS) & 1u;
             pipe_wait(&c.ready[s], ph, c.dead, a.status, 12, t, s);
             tc_fence_after();
+            __syncwarp();                                       // the lanes leave the wait loop at different times
             if (tc_elect_one()) {
                 const uint32_t A = smem_u32(c.stages + (size_t)s * PF_STAGE);
                 pipe_issue_3xtf32(t_wraw, t_wlo, A, A + PT_IMG, t_acc0 + s * PT, &c.accf[s]);
