@@ -254,6 +254,23 @@ int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t*
                          float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
                          float* dg, int dg_has_up, float* dg_out, float* dq, float* s_pre, float* t_scatter,
                          float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop, int drop_site, void* stream);
+/* One half of scann_la_backward_tc: which bit 0 = attention kernel, bit 1 = geometry kernel. */
+int scann_la_backward_tc_part(int which, int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0, const int32_t* tile_a1,
+                         const int32_t* cnt, const int32_t* rowptr, const int32_t* pair_c, const int32_t* pair_j,
+                         const float* x, const float* proj, const float* g_in, const float* g_new, float* kbuf,
+                         float* prebuf, const float* W2T, const float* WkT, const float* gamma_g, const float* d_ctx,
+                         float* dg, int dg_has_up, float* dg_out, float* dq, float* s_pre, float* t_scatter,
+                         float* dx_scatter, float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop, int drop_site, void* stream);
+/* The same backward as two warp-specialised, TMA-fed pipelines (la_pipe_bwd.cu) for pair plans with tile_stride 32
+ * (see scann_la_forward_pipe): the tiles of k / g' / pre / g / dg' arrive by TMA, x[j] by cp.async, d_k / d_pre / dg
+ * leave by TMA stores (dg by a TMA reduce-add when dg_has_up).  rows = tile_cap * 32; which: bit 0 attention kernel,
+ * bit 1 geometry kernel. */
+int scann_la_backward_pipe(int grid, long long rows, int which, const int32_t* ntiles, const int32_t* pair_c,
+                           const int32_t* pair_j, const float* x, const float* proj, const float* g_in,
+                           const float* g_new, float* kbuf, float* prebuf, const float* W2T, const float* WkT,
+                           const float* gamma_g, const float* d_ctx, float* dg, int dg_has_up, float* dg_out, float* dq,
+                           float* s_pre, float* t_scatter, float* dx_scatter, float* dgamma_g, float* dbeta_g,
+                           float* dbk, const void* attn_drop, int drop_site, int32_t* status, void* stream);
 /* Pair weight gradients of one layer (3xTF32, MN-major operands) into wpart[grid][2][128][128]:
  * slot 0 = (x[j]*g')^T d_k (key/kernel), slot 1 = g^T d_pre (filter_geo rows 128..255).  Needs the d_k /
  * d_pre that scann_la_backward_tc left in kbuf / prebuf; off the critical path (side stream). */

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "scann_noupdate_geom_backward": (ci, [vp, ci, ci] + [vp] * 9 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci, ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp, ci, vp]),
+    "scann_la_backward_tc_part": (ci, [ci, ci, ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp, ci, vp]),
+    "scann_la_backward_pipe": (ci, [ci, C.c_longlong, ci] + [vp] * 14 + [ci] + [vp] * 8 + [vp, ci, vp, vp]),
     "scann_la_wgrad_tc": (ci, [ci, ci] + [vp] * 9 + [vp]),
     "scann_wgrad_batch_tc": (ci, [ci, vp, ci, vp, ci, vp, vp, vp, vp, vp, vp]),
     "scann_la_wpart_reduce": (ci, [vp, vp, ci, ci, vp, vp, vp]),

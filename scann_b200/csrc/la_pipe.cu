@@ -13,9 +13,9 @@
 //                     producer also gathers the neighbour features x[j] row by row with 16-byte cp.async straight
 //                     into the tile image.  It runs PF_NS - PF_NG tiles ahead of the consumers, so no compute warp
 //                     ever waits for HBM.
-//   MMA warp        : one elected lane issues the 48 tcgen05.mma of a tile as soon as its operand images are
+//   MMA warps       : one per consumer group; an elected lane issues the 48 tcgen05.mma of a tile once its images are
 //                     ready, into the stage's own accumulator columns, and commits to the stage's mbarrier.
-//   consumer groups : PF_NG groups of four warps; group g owns tiles g, g + PF_NG, ...: split pass (lo = x -
+//   consumer groups : PF_NG groups of eight warps; group g owns tiles g, g + PF_NG, ...: split pass (lo = x -
 //                     trunc(x); the TMA-landed fp32 tile itself is the "hi" operand because the tensor core
 //                     truncates), accumulator read-back, row-wise epilogue IN PLACE in the stage's images, and a
 //                     TMA store of the finished tile (g', and pre / k when training saves them).
@@ -26,24 +26,27 @@
 // images, so six tiles are in flight per SM.  Every mbarrier wait is bounded (pipe_common.cuh).
 #include <string.h>
 
-#include "pipe_common.cuh"
+#include "pipe_frame.cuh"
 
-#define PF_NS 6                                // ring stages
-#define PF_NG 3                                // consumer groups
-#define PF_CW (4 * PF_NG)                      // consumer warps
-#define PF_THREADS ((PF_CW + 2) * 32)          // + producer warp + MMA warp
-#define PF_STAGE (2u * PT_IMG)
-// dynamic shared memory: stages | idx[NS][64] | Es[NS][PT*8] | barriers | flags   (+ 1024 for alignment)
-#define PF_OFF_IDX (PF_NS * PF_STAGE)
-#define PF_OFF_ES (PF_OFF_IDX + PF_NS * 64u * 4u)
-#define PF_OFF_BAR (PF_OFF_ES + PF_NS * PT * 8u * 4u)
-#define PF_OFF_FLAGS (PF_OFF_BAR + 4u * PF_NS * 8u)
-#define PF_SMEM (PF_OFF_FLAGS + 16u + 1024u)
+#define PF_NS 6                                // ring stages: two tile images each
+typedef PipeFrame<PF_NS, 2> FwdFrame;
+#define PF_STAGE (FwdFrame::STAGE)
+#define PF_SMEM (FwdFrame::SMEM)
 
-__device__ __forceinline__ float4 pf4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 lds4(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void sts4(uint8_t* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
-__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+// phase timestamps of CTA 0, consumer group 0 (development builds: -DSCANN_PIPE_CLK): [kernel][tile ordinal][phase]
+#ifdef SCANN_PIPE_CLK
+__device__ long long g_pipe_clk[2][4][12];
+#define PCLK(k, ph) do { if (blockIdx.x == 0 && tid == 0 && (i / PF_NG) < 4) g_pipe_clk[k][i / PF_NG][ph] = clock64(); } while (0)
+#define PCLK0(k, ph) do { if (blockIdx.x == 0 && tid == 0) g_pipe_clk[k][0][ph] = clock64(); } while (0)
+extern "C" int scann_pipe_clocks(long long* host_out96) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out96, g_pipe_clk, sizeof(long long) * 96);
+    if (e != cudaSuccess) { scann_set_error("pipe_clocks: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+#else
+#define PCLK(k, ph) do { } while (0)
+#define PCLK0(k, ph) do { } while (0)
+#endif
 
 struct PipeGeomArgs {
     CUtensorMap tm_gin, tm_gout, tm_pre;
@@ -55,54 +58,15 @@ struct PipeGeomArgs {
     int32_t* status;
 };
 
-struct PipeCtx {
-    uint8_t* stages; int32_t* idx; float* es; uint64_t *full, *empty, *ready, *accf; uint32_t* tmem_slot; volatile int* dead;
-};
-__device__ __forceinline__ PipeCtx pipe_carve(uint8_t* smem_raw) {
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    PipeCtx c;
-    c.stages = smem;
-    c.idx = reinterpret_cast<int32_t*>(smem + PF_OFF_IDX);
-    c.es = reinterpret_cast<float*>(smem + PF_OFF_ES);
-    c.full = reinterpret_cast<uint64_t*>(smem + PF_OFF_BAR);
-    c.empty = c.full + PF_NS; c.ready = c.empty + PF_NS; c.accf = c.ready + PF_NS;
-    c.tmem_slot = reinterpret_cast<uint32_t*>(smem + PF_OFF_FLAGS);
-    c.dead = reinterpret_cast<volatile int*>(smem + PF_OFF_FLAGS + 4);
-    return c;
-}
-
 // =============================================================================================
 // Geometry update
 // =============================================================================================
 __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const __grid_constant__ PipeGeomArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    const PipeCtx c = pipe_carve(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == PF_CW + 1) tmem_alloc(c.tmem_slot, 512);
-    if (tid == 0) {
-        for (int s = 0; s < PF_NS; ++s) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); mbar_init(&c.ready[s], 1); mbar_init(&c.accf[s], 1); }
-        *c.dead = 0;
-        mbar_fence_init();
-    }
-    if (warp == PF_CW && lane == 0) {
-        tma_prefetch_desc(&a.tm_gin); tma_prefetch_desc(&a.tm_gout);
-        if (a.has_pre) tma_prefetch_desc(&a.tm_pre);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *c.tmem_slot;
-    const uint32_t t_wraw = tmem, t_wlo = tmem + 128, t_acc0 = tmem + 256;
-    if (warp < PF_CW) pipe_weight_to_tmem(a.W2, t_wraw, t_wlo, warp, lane, PF_CW);   // parameters only: before the PDL wait
-    pdl_wait();
-    const int nt = *a.ntiles;
-    tc_fence_before();
-    __syncthreads();                                     // the whole weight is in tensor memory
-    tc_fence_after();
-
+    PF_PROLOGUE(FwdFrame, PF_NS, a.W2, 1)
     if (warp == PF_CW) {
         // ================= producer =================
         if (lane == 0) {
+            tma_prefetch_desc(&a.tm_gin);
             int i = 0;
             for (int t = blockIdx.x; t < nt; t += gridDim.x, ++i) {
                 const int s = i % PF_NS;
@@ -117,28 +81,17 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const _
             }
         }
         __syncwarp();
-    } else if (warp == PF_CW + 1) {
-        // ================= MMA issue =================
-        int i = 0;
-        for (int t = blockIdx.x; t < nt; t += gridDim.x, ++i) {
-            const int s = i % PF_NS;
-            const uint32_t ph = (uint32_t)(i / PF_NS) & 1u;
-            pipe_wait(&c.ready[s], ph, c.dead, a.status, 2, t, s);
-            tc_fence_after();
-            __syncwarp();                                       // the lanes leave the wait loop at different times
-            if (tc_elect_one()) {
-                const uint32_t A = smem_u32(c.stages + (size_t)s * PF_STAGE);
-                pipe_issue_3xtf32(t_wraw, t_wlo, A, A + PT_IMG, t_acc0 + s * PT, &c.accf[s]);
-            }
-            __syncwarp();
-        }
+    } else if (warp > PF_CW) {
+        if (lane == 0) { tma_prefetch_desc(&a.tm_gout); if (a.has_pre) tma_prefetch_desc(&a.tm_pre); }
+        PF_STORE_LOOP(PF_NS, PF_STAGE, 2,
+            for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_gout, A + kb * PT_CB, kb * 32, t * PT);
+            if (a.has_pre) { for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_pre, Bm + kb * PT_CB, kb * 32, t * PT); })
     } else {
         // ================= consumers =================
-        const int grp = warp >> 2, wg = warp & 3, gtid = tid - grp * 128;
+        const int grp = warp / PF_GW, wgl = warp % PF_GW, q = warp & 3, half = (warp >> 2) & 1, gtid = tid - grp * PF_GT;
         const int l8 = lane & 7, rsub = lane >> 3;
-        float4 gm[4], bt[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) { gm[it] = ldg4(a.gamma_g + (l8 + 8 * it) * 4); bt[it] = ldg4(a.beta_g + (l8 + 8 * it) * 4); }
+        const int r = wgl * 4 + rsub;                        // this lane's row of every tile
+        const uint32_t t_acc = t_acc0 + grp * 3 * PT;        // a group has one tile between MMA issue and read-back
         int i = grp;
         for (int t = blockIdx.x + grp * gridDim.x; t < nt; t += PF_NG * gridDim.x, i += PF_NG) {
             const int s = i % PF_NS;
@@ -146,51 +99,66 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const _
             uint8_t* A = c.stages + (size_t)s * PF_STAGE;       // g (fp32, as landed) -> g'
             uint8_t* Bm = A + PT_IMG;                           // lo image -> transposed accumulator -> pre
             const int32_t* sidx = c.idx + s * 64;
+            PCLK(0, 0);
             pipe_wait(&c.full[s], ph, c.dead, a.status, 3, t, s);
-            // ---- split pass: the landed tile is the hi operand; lo = g - trunc(g)
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-                const uint32_t off = pt_off4(wg + 4 * it, lane);
-                const float4 v = lds4(A + off);
-                sts4(Bm + off, make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)));
-            }
-            fence_async_smem();
-            group_sync(grp, 128);
-            if (gtid == 0) mbar_arrive(&c.ready[s]);
-            // ---- while the tensor core works: gathered per-atom projections of this warp's rows
-            int pc[2];
-            float4 p13[2][4];
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                const int r = sp * 16 + wg * 4 + rsub;
-                pc[sp] = sidx[r];
-                const int j = pc[sp] >= 0 ? sidx[32 + r] : 0;
-                const int cc = pc[sp] >= 0 ? pc[sp] : 0;
+            PCLK(0, 1);
+            // ---- gathered per-atom projections of this lane's row: issued first, consumed after the MMA
+            const int pc = sidx[r];
+            float4 pa[4], pb[4];
+            {
+                const int j = pc >= 0 ? sidx[32 + r] : 0;
+                const int cc = pc >= 0 ? pc : 0;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const int c0 = (l8 + 8 * it) * 4;
-                    p13[sp][it] = pf4add(ld4(a.proj + (size_t)cc * 3 * SCANN_D + c0),
-                                         ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + c0));
+                    pa[it] = ld4(a.proj + (size_t)cc * 3 * SCANN_D + c0);
+                    pb[it] = ld4(a.proj + (size_t)j * 3 * SCANN_D + SCANN_D + c0);
                 }
             }
+            // ---- split pass: the landed tile is the hi operand; lo = g - trunc(g).  Loads first, then stores
+            {
+                float4 v[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) v[it] = lds4(A + pt_off4(wgl + PF_GW * it, lane));
+#pragma unroll
+                for (int it = 0; it < 4; ++it) sts4(Bm + pt_off4(wgl + PF_GW * it, lane), tf32_lo4(v[it]));
+            }
+            fence_async_smem();
+            PCLK(0, 9);
+            tc_fence_before();
+            pf_group_sync(grp);
+            if (wgl < 3) {                                      // warps 0..2 of the group: one product chain each
+                tc_fence_after();
+                if (tc_elect_one()) pf_issue_chain(wgl, t_wraw, t_wlo, smem_u32(A), smem_u32(Bm), t_acc, &c.accf[s]);
+                __syncwarp();
+            }
+            PCLK(0, 2);
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 4, t, s);
             tc_fence_after();
-            pipe_acc_to_image(t_acc0 + s * PT, Bm, nullptr, wg, lane);
-            tc_fence_before();
-            group_sync(grp, 128);
-            // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g' (in place)
+            PCLK(0, 3);
+            // the gathered rows are consumed here, not earlier: the loads stay in flight behind the split pass and the MMAs
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
-                const int r = sp * 16 + wg * 4 + rsub;
+            for (int it = 0; it < 4; ++it)
+                asm volatile("" : "+f"(pa[it].x), "+f"(pa[it].y), "+f"(pa[it].z), "+f"(pa[it].w), "+f"(pb[it].x), "+f"(pb[it].y),
+                             "+f"(pb[it].z), "+f"(pb[it].w));
+            float4 p13[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) p13[it] = pf4add(pa[it], pb[it]);
+            PCLK(0, 4);
+            pf_acc_to_image(t_acc, Bm, nullptr, q, half, lane);
+            tc_fence_before();
+            pf_group_sync(grp);
+            PCLK(0, 5);
+            // ---- row-wise epilogue: pre -> swish -> + g -> LayerNorm -> g' (in place)
+            if (!__all_sync(0xffffffffu, pc < 0)) {
                 float z[4][4], pre[4][4];
                 float s1 = 0.f;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const uint32_t off = pt_off4(r, l8 + 8 * it);
                     const float4 acc = lds4(Bm + off), g = lds4(A + off);
-                    pre[it][0] = acc.x + p13[sp][it].x; pre[it][1] = acc.y + p13[sp][it].y;
-                    pre[it][2] = acc.z + p13[sp][it].z; pre[it][3] = acc.w + p13[sp][it].w;
+                    pre[it][0] = acc.x + p13[it].x; pre[it][1] = acc.y + p13[it].y;
+                    pre[it][2] = acc.z + p13[it].z; pre[it][3] = acc.w + p13[it].w;
                     z[it][0] = swish_fast(pre[it][0]) + g.x; z[it][1] = swish_fast(pre[it][1]) + g.y;
                     z[it][2] = swish_fast(pre[it][2]) + g.z; z[it][3] = swish_fast(pre[it][3]) + g.w;
                     s1 += z[it][0] + z[it][1] + z[it][2] + z[it][3];
@@ -200,37 +168,31 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_fwd_pipe_kernel(const _
 #pragma unroll
                 for (int it = 0; it < 4; ++it)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { z[it][q] -= sh; m1 += z[it][q]; m2 = fmaf(z[it][q], z[it][q], m2); }
+                    for (int k = 0; k < 4; ++k) { z[it][k] -= sh; m1 += z[it][k]; m2 = fmaf(z[it][k], z[it][k], m2); }
                 oct_sum2(m1, m2);
                 m1 *= (1.0f / SCANN_D);
                 const float inv = rsqrtf(fmaxf(m2 * (1.0f / SCANN_D) - m1 * m1, 0.f) + SCANN_LN_EPS);
-                const bool ok = pc[sp] >= 0;
+                const bool ok = pc >= 0;
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const uint32_t off = pt_off4(r, l8 + 8 * it);
+                    const float4 gm = ldg4(a.gamma_g + (l8 + 8 * it) * 4), bt = ldg4(a.beta_g + (l8 + 8 * it) * 4);
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f), po = o;
                     if (ok) {
-                        o = make_float4((z[it][0] - m1) * inv * gm[it].x + bt[it].x, (z[it][1] - m1) * inv * gm[it].y + bt[it].y,
-                                        (z[it][2] - m1) * inv * gm[it].z + bt[it].z, (z[it][3] - m1) * inv * gm[it].w + bt[it].w);
+                        o = make_float4((z[it][0] - m1) * inv * gm.x + bt.x, (z[it][1] - m1) * inv * gm.y + bt.y,
+                                        (z[it][2] - m1) * inv * gm.z + bt.z, (z[it][3] - m1) * inv * gm.w + bt.w);
                         po = make_float4(pre[it][0], pre[it][1], pre[it][2], pre[it][3]);
                     }
                     sts4(A + off, o);
                     sts4(Bm + off, po);
                 }
             }
+            PCLK(0, 6);
             fence_async_smem();
-            group_sync(grp, 128);
-            if (gtid == 0) {
-#pragma unroll
-                for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_gout, A + kb * PT_CB, kb * 32, t * PT);
-                if (a.has_pre) {
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_pre, Bm + kb * PT_CB, kb * 32, t * PT);
-                }
-                tma_commit();
-                tma_wait_read0();
-                mbar_arrive(&c.empty[s]);
-            }
+            pf_group_sync(grp);
+            PCLK(0, 7);
+            if (gtid == 0) mbar_arrive(&c.ready[s]);            // tile finished in place: over to the store warp
+            PCLK(0, 8);
         }
     }
     pdl_trigger();
@@ -256,35 +218,12 @@ struct PipeAttnArgs {
     int32_t* status;
 };
 
+// full barrier of the attention kernel: the expect_tx arrive of lane 0 + the 32 cp.async arrives of the gathering lanes
 __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const __grid_constant__ PipeAttnArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    const PipeCtx c = pipe_carve(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (warp == PF_CW + 1) tmem_alloc(c.tmem_slot, 512);
-    if (tid == 0) {
-        // full: the expect_tx arrive of lane 0 + the 32 cp.async arrives of the gathering lanes
-        for (int s = 0; s < PF_NS; ++s) { mbar_init(&c.full[s], 33); mbar_init(&c.empty[s], 1); mbar_init(&c.ready[s], 1); mbar_init(&c.accf[s], 1); }
-        *c.dead = 0;
-        mbar_fence_init();
-    }
-    if (warp == PF_CW && lane == 0) {
-        tma_prefetch_desc(&a.tm_g);
-        if (a.has_k) tma_prefetch_desc(&a.tm_k);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *c.tmem_slot;
-    const uint32_t t_wraw = tmem, t_wlo = tmem + 128, t_acc0 = tmem + 256;
-    if (warp < PF_CW) pipe_weight_to_tmem(a.Wk, t_wraw, t_wlo, warp, lane, PF_CW);
-    pdl_wait();
-    const int nt = *a.ntiles;
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-
+    PF_PROLOGUE(FwdFrame, PF_NS, a.Wk, 33)
     if (warp == PF_CW) {
         // ================= producer: g' tile by TMA, x[j] rows by per-lane cp.async =================
+        if (lane == 0) tma_prefetch_desc(&a.tm_g);
         int i = 0;
         int jn = 0;
         if ((int)blockIdx.x < nt) {
@@ -312,32 +251,24 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
             }
             const uint32_t X = smem_u32(A + PT_IMG);
 #pragma unroll 8
-            for (int r = 0; r < PT; ++r) {
-                const int jr = __shfl_sync(0xffffffffu, j, r);
-                cp_async16(X + pt_off4(r, lane), a.x + (size_t)jr * SCANN_D + lane * 4);
+            for (int rr = 0; rr < PT; ++rr) {
+                const int jr = __shfl_sync(0xffffffffu, j, rr);
+                cp_async16(X + pt_off4(rr, lane), a.x + (size_t)jr * SCANN_D + lane * 4);
             }
             cp_async_arrive(&c.full[s]);
         }
-    } else if (warp == PF_CW + 1) {
-        // ================= MMA issue =================
-        int i = 0;
-        for (int t = blockIdx.x; t < nt; t += gridDim.x, ++i) {
-            const int s = i % PF_NS;
-            const uint32_t ph = (uint32_t)(i / PF_NS) & 1u;
-            pipe_wait(&c.ready[s], ph, c.dead, a.status, 12, t, s);
-            tc_fence_after();
-            __syncwarp();                                       // the lanes leave the wait loop at different times
-            if (tc_elect_one()) {
-                const uint32_t A = smem_u32(c.stages + (size_t)s * PF_STAGE);
-                pipe_issue_3xtf32(t_wraw, t_wlo, A, A + PT_IMG, t_acc0 + s * PT, &c.accf[s]);
-            }
-            __syncwarp();
+    } else if (warp > PF_CW) {
+        if (a.has_k) {
+            if (lane == 0) tma_prefetch_desc(&a.tm_k);
+            PF_STORE_LOOP(PF_NS, PF_STAGE, 12, for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_k, A + kb * PT_CB, kb * 32, t * PT);)
         }
     } else {
         // ================= consumers =================
-        const int grp = warp >> 2, wg = warp & 3, gtid = tid - grp * 128;
+        const int grp = warp / PF_GW, wgl = warp % PF_GW, q = warp & 3, half = (warp >> 2) & 1, gtid = tid - grp * PF_GT;
         const int l8 = lane & 7, rsub = lane >> 3;
+        const int r = wgl * 4 + rsub;
         const float4 gam = ldg4(a.gamma + lane * 4), bet = ldg4(a.beta + lane * 4);
+        const uint32_t t_acc = t_acc0 + grp * 3 * PT;
         int i = grp;
         for (int t = blockIdx.x + grp * gridDim.x; t < nt; t += PF_NG * gridDim.x, i += PF_NG) {
             const int s = i % PF_NS;
@@ -346,57 +277,58 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
             uint8_t* A = c.stages + (size_t)s * PF_STAGE;       // g' -> a = x[j] * g' (hi operand) -> keys
             uint8_t* Bm = A + PT_IMG;                           // x[j] -> lo image
             const int32_t* sidx = c.idx + s * 64;
-            float* Es = c.es + s * PT * 8;
+            float* Es = c.es + s * 2 * PT * 8;
             pipe_wait(&c.full[s], ph, c.dead, a.status, 13, t, s);
-            int pc[2];
-            float4 qv[2][4];
+            const int pc = sidx[r];
+            const bool ok = pc >= 0;
+            float4 qv[4];
 #pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                pc[sp] = sidx[sp * 16 + wg * 4 + rsub];
-#pragma unroll
-                for (int it = 0; it < 4; ++it) {
-                    qv[sp][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (pc[sp] >= 0) qv[sp][it] = ld4(a.proj + (size_t)pc[sp] * 3 * SCANN_D + 2 * SCANN_D + (l8 + 8 * it) * 4);
-                }
+            for (int it = 0; it < 4; ++it) {
+                qv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) qv[it] = ld4(a.proj + (size_t)pc * 3 * SCANN_D + 2 * SCANN_D + (l8 + 8 * it) * 4);
             }
             // ---- a = x[j] * g' in place: the fp32 product is the hi operand, lo = a - trunc(a) over x[j]
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;        // stale operand rows only feed their own columns
-                const int r = sp * 16 + wg * 4 + rsub;
-                const bool ok = pc[sp] >= 0;
+            // (rows of a warp whose four rows are all padding keep stale operands: they only feed their own columns)
+            if (!__all_sync(0xffffffffu, !ok)) {
+                float4 g[4], xv[4];
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const uint32_t off = pt_off4(r, l8 + 8 * it);
-                    const float4 g = lds4(A + off), xv = lds4(Bm + off);
+                    g[it] = lds4(A + off);
+                    xv[it] = lds4(Bm + off);
+                }
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const uint32_t off = pt_off4(r, l8 + 8 * it);
                     float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok) av = make_float4(g.x * xv.x, g.y * xv.y, g.z * xv.z, g.w * xv.w);
+                    if (ok) av = make_float4(g[it].x * xv[it].x, g[it].y * xv[it].y, g[it].z * xv[it].z, g[it].w * xv[it].w);
                     sts4(A + off, av);
-                    sts4(Bm + off, make_float4(tf32_lo(av.x), tf32_lo(av.y), tf32_lo(av.z), tf32_lo(av.w)));
+                    sts4(Bm + off, tf32_lo4(av));
                 }
             }
             fence_async_smem();
-            group_sync(grp, 128);
-            if (gtid == 0) mbar_arrive(&c.ready[s]);
+            tc_fence_before();
+            pf_group_sync(grp);
+            if (wgl < 3) {
+                tc_fence_after();
+                if (tc_elect_one()) pf_issue_chain(wgl, t_wraw, t_wlo, smem_u32(A), smem_u32(Bm), t_acc, &c.accf[s]);
+                __syncwarp();
+            }
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 14, t, s);
             tc_fence_after();
-            pipe_acc_to_image(t_acc0 + s * PT, A, a.bk, wg, lane);          // keys k = a @ Wk + bk
+            pf_acc_to_image(t_acc, A, a.bk, q, half, lane);                  // keys k = a @ Wk + bk
             tc_fence_before();
-            group_sync(grp, 128);
+            pf_group_sync(grp);
             // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = 4 adjacent lanes of the row)
-#pragma unroll
-            for (int sp = 0; sp < 2; ++sp) {
-                if (__all_sync(0xffffffffu, pc[sp] < 0)) continue;
-                const int r = sp * 16 + wg * 4 + rsub;
+            if (!__all_sync(0xffffffffu, !ok)) {
 #pragma unroll
                 for (int it = 0; it < 4; ++it) {
                     const float4 kv = lds4(A + pt_off4(r, l8 + 8 * it));
-                    const float4 q = qv[sp][it];
-                    const float e = quad_sum(kv.x * q.x + kv.y * q.y + kv.z * q.z + kv.w * q.w) * 0.25f;
+                    const float e = quad_sum(kv.x * qv[it].x + kv.y * qv[it].y + kv.z * qv[it].z + kv.w * qv[it].w) * 0.25f;
                     if ((l8 & 3) == 0) Es[r * 8 + 2 * it + (l8 >> 2)] = e;
                 }
             }
-            group_sync(grp, 128);
+            pf_group_sync(grp);
             // ---- per atom (one warp each): softmax over its rows, context, residual q, LayerNorm.  The atoms of the
             // tile are read off the centre indices: valid rows are a prefix, an atom's rows are contiguous
             {
@@ -406,31 +338,31 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
                 const uint32_t hmask = __ballot_sync(0xffffffffu, myc >= 0 && (lane == 0 || myc != prevc));
                 const int nvalid = __popc(vmask), natoms = __popc(hmask);
                 uint32_t m = hmask;
-                for (int k = 0; k < wg; ++k) m &= m - 1;
-                for (int k = wg; k < natoms; k += 4) {
+                for (int k = 0; k < wgl; ++k) m &= m - 1;
+                for (int k = wgl; k < natoms; k += PF_GW) {
                     const int r0 = __ffs(m) - 1;
                     uint32_t mn = m;
                     mn &= mn - 1;
                     const int n = (mn ? __ffs(mn) - 1 : nvalid) - r0;
                     const int atom = sidx[r0];
                     const int h = lane >> 2;
-                    const float4 q = ld4(a.proj + (size_t)atom * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+                    const float4 qa = ld4(a.proj + (size_t)atom * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
                     float mx = -INFINITY;
-                    for (int r = 0; r < n; ++r) mx = fmaxf(mx, Es[(r0 + r) * 8 + h]);
+                    for (int rr = 0; rr < n; ++rr) mx = fmaxf(mx, Es[(r0 + rr) * 8 + h]);
                     float sm = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                    for (int r = 0; r < n; ++r) {
-                        float p = __expf(Es[(r0 + r) * 8 + h] - mx);
-                        const float4 kv = lds4(A + pt_off4(r0 + r, lane));
+                    for (int rr = 0; rr < n; ++rr) {
+                        float p = __expf(Es[(r0 + rr) * 8 + h] - mx);
+                        const float4 kv = lds4(A + pt_off4(r0 + rr, lane));
                         sm += p;                                        // the softmax is normalised before the dropout
-                        p *= drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
+                        p *= drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + rr) * 8u + h);
                         c0 = fmaf(p, kv.x, c0); c1 = fmaf(p, kv.y, c1); c2 = fmaf(p, kv.z, c2); c3 = fmaf(p, kv.w, c3);
                     }
                     const float is = 1.0f / sm;
                     if (a.attn && (lane & 3) == 0)
-                        for (int r = 0; r < n; ++r)
-                            a.attn[(rowbase + r0 + r) * 8 + h] = __expf(Es[(r0 + r) * 8 + h] - mx) * is *
-                                                               drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
-                    c0 = c0 * is + q.x; c1 = c1 * is + q.y; c2 = c2 * is + q.z; c3 = c3 * is + q.w;
+                        for (int rr = 0; rr < n; ++rr)
+                            a.attn[(rowbase + r0 + rr) * 8 + h] = __expf(Es[(r0 + rr) * 8 + h] - mx) * is *
+                                                                drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + rr) * 8u + h);
+                    c0 = c0 * is + qa.x; c1 = c1 * is + qa.y; c2 = c2 * is + qa.z; c3 = c3 * is + qa.w;
                     if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
                     const float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
                     c0 -= mean; c1 -= mean; c2 -= mean; c3 -= mean;
@@ -438,20 +370,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
                     st4(a.out + (size_t)atom * SCANN_D + lane * 4,
                         make_float4(c0 * inv * gam.x + bet.x, c1 * inv * gam.y + bet.y, c2 * inv * gam.z + bet.z,
                                     c3 * inv * gam.w + bet.w));
-                    for (int k2 = 0; k2 < 4 && m; ++k2) m &= m - 1;     // this warp's next atom
+                    for (int k2 = 0; k2 < PF_GW && m; ++k2) m &= m - 1;     // this warp's next atom
                 }
             }
-            fence_async_smem();
-            group_sync(grp, 128);
-            if (gtid == 0) {
-                if (a.has_k) {
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) tma_store_2d(&a.tm_k, A + kb * PT_CB, kb * 32, t * PT);
-                    tma_commit();
-                    tma_wait_read0();
-                }
-                mbar_arrive(&c.empty[s]);
-            }
+            if (a.has_k) fence_async_smem();
+            pf_group_sync(grp);
+            // training: the keys leave through the store warp; inference: the stage goes straight back to the producer
+            if (gtid == 0) mbar_arrive(a.has_k ? &c.ready[s] : &c.empty[s]);
         }
     }
     pdl_trigger();

@@ -674,7 +674,9 @@ static int la_bwd_configure() {
     return 0;
 }
 
-extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
+// which: bit 0 attention kernel, bit 1 geometry kernel (scann_la_backward_tc = both; the halves are separate entry
+// points so that either can be replaced by its pipelined form, la_pipe_bwd.cu).
+extern "C" int scann_la_backward_tc_part(int which, int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
                                     const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
                                     const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
                                     const float* g_in, const float* g_new, float* kbuf, float* prebuf, const float* W2T,
@@ -692,16 +694,29 @@ extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, con
     LaGeomBwdArgs gb{ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, g_in, prebuf, dg, W2T, gamma_g, dg_out,
                      s_pre, t_scatter, dgamma_g, dbeta_g, mma_rows};
     if (tile_stride == 32) {
-        scann_launch(la_attn_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
-        scann_launch(la_geom_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+        if (which & 1) scann_launch(la_attn_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        if (which & 2) scann_launch(la_geom_bwd_tc_kernel<4>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
     } else if (tile_stride == 64) {
-        scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
-        scann_launch(la_geom_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+        if (which & 1) scann_launch(la_attn_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        if (which & 2) scann_launch(la_geom_bwd_tc_kernel<2>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
     } else {
-        scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
-        scann_launch(la_geom_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
+        if (which & 1) scann_launch(la_attn_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_ATTN_BWD_SMEM, stream, ab);
+        if (which & 2) scann_launch(la_geom_bwd_tc_kernel<1>, dim3(grid), dim3(LTC_THREADS), LA_GEOM_BWD_SMEM, stream, gb);
     }
     return scann_check_launch("scann_la_backward_tc");
+}
+
+extern "C" int scann_la_backward_tc(int grid, int tile_stride, int mma_rows, const int32_t* ntiles, const int32_t* tile_a0,
+                                    const int32_t* tile_a1, const int32_t* cnt, const int32_t* rowptr,
+                                    const int32_t* pair_c, const int32_t* pair_j, const float* x, const float* proj,
+                                    const float* g_in, const float* g_new, float* kbuf, float* prebuf, const float* W2T,
+                                    const float* WkT, const float* gamma_g, const float* d_ctx, float* dg, int dg_has_up,
+                                    float* dg_out, float* dq, float* s_pre, float* t_scatter, float* dx_scatter,
+                                    float* wpart, float* dgamma_g, float* dbeta_g, float* dbk, const void* attn_drop,
+                                    int drop_site, void* stream) {
+    return scann_la_backward_tc_part(3, grid, tile_stride, mma_rows, ntiles, tile_a0, tile_a1, cnt, rowptr, pair_c, pair_j, x,
+                                     proj, g_in, g_new, kbuf, prebuf, W2T, WkT, gamma_g, d_ctx, dg, dg_has_up, dg_out, dq,
+                                     s_pre, t_scatter, dx_scatter, wpart, dgamma_g, dbeta_g, dbk, attn_drop, drop_site, stream);
 }
 
 // Backward of LocalAttention.call with g_update = False (attention.py:155-216): the attention kernel only

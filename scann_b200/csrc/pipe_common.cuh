@@ -97,7 +97,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-__device__ __noinline__ void pipe_give_up(volatile int* dead, int32_t* status, int code, int tile, int stage) {
+static __device__ __noinline__ void pipe_give_up(volatile int* dead, int32_t* status, int code, int tile, int stage) {
     *dead = 1;
     if (status) atomicOr(status, SCANN_ERR_PIPE_TIMEOUT);
     if (status && atomicCAS(status + 1, 0, code) == 0) { status[2] = (int)blockIdx.x; status[3] = tile; status[4] = stage; }

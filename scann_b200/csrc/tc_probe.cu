@@ -7,6 +7,8 @@
 //   nprod 1: single TF32 product of the raw fp32 operands; nprod 3: hi/lo split, 3 products into one
 //   accumulator; nprod 4: the same 3 products, the two cross terms in a second accumulator that is
 //   added on the CUDA cores (measures what the tensor core's accumulation costs in accuracy).
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -158,6 +160,29 @@ __global__ void __launch_bounds__(128, 1) tc_time_kernel(float* out, int mode, i
         const uint32_t idesc = tc_idesc_tf32(128, ncols, false, false);
         const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + TC_TILE_BYTES);
         long long t0 = clock64();
+        if (mode & 16) {          // fast issue, round-robin over nacc = mode >> 8 independent accumulators of ncols columns
+            const int nacc = mode >> 8;
+            const uint64_t bd0 = tc_desc(sb, cg, rg);
+            const uint64_t step = (uint64_t)((2u * cg) >> 4);
+            auto run = [&](auto NA) {
+                constexpr int NACC = decltype(NA)::value;
+                for (int i = 0; i < nmma; i += 16 * NACC) {
+#pragma unroll
+                    for (int ks = 0; ks < 16; ++ks)
+#pragma unroll
+                        for (int q = 0; q < NACC; ++q)
+                            tc_mma_ts(tmem + 256 + q * ncols, tmem + ks * 8, bd0 + ks * step, idesc, (i | ks) != 0);
+                }
+            };
+            switch (nacc) {
+                case 1: run(std::integral_constant<int, 1>{}); break;
+                case 2: run(std::integral_constant<int, 2>{}); break;
+                case 3: run(std::integral_constant<int, 3>{}); break;
+                case 4: run(std::integral_constant<int, 4>{}); break;
+                case 6: run(std::integral_constant<int, 6>{}); break;
+                default: run(std::integral_constant<int, 8>{}); break;
+            }
+        } else
         if (mode & 4) {           // fast issue: descriptors advanced by immediates, 16 MMAs per unrolled group
             const uint64_t bd0 = tc_desc(sb, cg, rg), ad0 = tc_desc(sa, cg, rg);
             const uint64_t step = (uint64_t)((2u * cg) >> 4);

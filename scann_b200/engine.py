@@ -118,7 +118,7 @@ class Engine:
         # warp-specialised TMA pipelines for the local-attention kernels (la_pipe.cu, la_pipe_bwd.cu) on plans with
         # 32-row tile slots: bit 0 geometry forward, 1 attention forward, 2 attention backward, 3 geometry backward.
         # 0 keeps the round-1 kernels (four 4-warp groups per CTA on the same 32-row plan when SCANN_TILE_STRIDE=32).
-        self.la_pipe_built = 3
+        self.la_pipe_built = 15
         self.la_pipe = (int(os.environ.get("SCANN_LA_PIPE", str(self.la_pipe_built))) & self.la_pipe_built
                         if (self.tc_la_fwd and self.tc_la_bwd) else 0)
         self.side_stream = torch.cuda.Stream(device=self.device)
@@ -295,7 +295,8 @@ class Engine:
         if N <= 32 and tc and (pref == 32 or (pref == 0 and self.la_pipe and self.spec.g_update)):
             stride = 32
         tile_rows = stride
-        if P_host is not None and self.balance_tiles and N <= 64:
+        # (the pipelined kernels on 32-row slots keep six tiles in flight per SM: full tiles, no wave balancing)
+        if P_host is not None and self.balance_tiles and N <= 64 and stride != 32:
             slots = self.sm_count * (TILE // stride)
             waves = max(1, -(-P // (stride * slots)))      # more, smaller tiles only add per-tile latency (measured)
             tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
@@ -1044,15 +1045,21 @@ class Engine:
                     self.gw(f"{la}/filter_geo/bias"), st), "noupdate_geom_backward")
                 self.launches += 2
             elif "la_bwd" not in self._skip:
-                check(lib.scann_la_backward_tc(self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1),
-                                               _p(b.cnt), _p(b.rowptr), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]),
-                                               _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]),
-                                               _p(ws["kk"][l]), _p(ws["pre"][l]), self.wT(fg, D * D),
-                                               self.wT(f"{la}/key/kernel"), self.w(f"{la}/layer_norm_g/gamma"),
-                                               _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None), _p(dg_out),
-                                               _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc), 0,
-                                               self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"),
-                                               self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_tc")
+                plan_args = (_p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr), _p(b.pair_c), _p(b.pair_j))
+                data = (_p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["g"][l]), _p(ws["g"][l + 1]), _p(ws["kk"][l]),
+                        _p(ws["pre"][l]), self.wT(fg, D * D), self.wT(f"{la}/key/kernel"),
+                        self.w(f"{la}/layer_norm_g/gamma"), _p(ws["d_ctx"]), _p(dg_buf), int(dg_up is not None),
+                        _p(dg_out), _p(dq), _p(s_pre), _p(t_sc), _p(dx_sc))
+                grads = (self.gw(f"{la}/layer_norm_g/gamma"), self.gw(f"{la}/layer_norm_g/beta"), self.gw(f"{la}/key/bias"))
+                pipe = (self.la_pipe >> 2) & 3 if b.stride == 32 else 0
+                for part in (1, 2):                   # attention kernel, then geometry kernel: pipelined or round-1 form
+                    if pipe & part:
+                        check(lib.scann_la_backward_pipe(self.la_grid, b.rows, part, plan_args[0], plan_args[5], plan_args[6],
+                                                         *data, *grads, *self._adrop(True, l), _p(self.status), st),
+                              "la_backward_pipe")
+                    else:
+                        check(lib.scann_la_backward_tc_part(part, self.la_grid, b.stride, b.mma_rows, *plan_args, *data, 0,
+                                                            *grads, *self._adrop(True, l), st), "la_backward_tc")
                 self.launches += 2
             self._ev("la_backward", False)
             # next link of the critical path: gradient w.r.t. the layer input x_l, then the tail of layer l-1
