@@ -12,6 +12,8 @@ from __future__ import annotations
 
 import math
 import os
+
+import numpy as np
 from typing import Callable, Dict, Optional
 
 
@@ -160,6 +162,8 @@ class SGDRC(Callback):
             if self.tcur > self.ti:                       # cycle finished: longer cycle, new peak
                 self.ti, self.tcur = int(self.tmult * self.ti), 1
                 self.lr_warmup_current = self.lr_warmup_next
-            phase = 0.5 * (1.0 + math.cos(math.pi * self.tcur / self.ti))
-            self.lr = float(self.lr_min + (self.lr_warmup_current - self.lr_min) * phase)
+            # the reference's expression, operation for operation (custom_layers.py:176-178): the schedule is pinned
+            # bit for bit against the reference's own class (tests/test_reference_pins.py)
+            self.lr = float(self.lr_min + (self.lr_warmup_current - self.lr_min) *
+                            (1 + np.cos(self.tcur / self.ti * np.pi)) / 2.0)
         return self.lr

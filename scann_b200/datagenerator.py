@@ -112,6 +112,35 @@ def pack_padded(csr: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     return out
 
 
+def prepare_input_from_neighbors(atomic_numbers, neighbors, angle: bool = True) -> Dict[str, np.ndarray]:
+    """The padding half of ``prepare_input_pmt`` (scann/utils/general.py:218-246) for a caller who already has the
+    neighbour lists of ONE structure -- the README inference flow (README.md:102-120) without pymatgen:
+    ``neighbors[a]`` = list of tuples ``n`` as ``compute_voronoi_neighbor`` returns them (``n[1]`` neighbour atom
+    index, ``n[2]`` solid angle, ``n[3]`` normalised solid angle, ``n[-1]`` distance).  ``angle=True`` selects the raw
+    solid angle (what the g_update models are trained on, general.py:224).  Returns the model's input dict with a
+    leading batch axis of 1; padded slots carry index 0 / weight 0 / distance 0 and ``neighbor_mask`` False, exactly
+    as ``pad_sequence(..., value=1000)`` + ``!= 1000`` produce them (tests/test_reference_pins.py)."""
+    na = len(neighbors)
+    if len(atomic_numbers) != na:
+        raise ValueError("one neighbour list per atom is required")
+    n_max = max((len(lc) for lc in neighbors), default=0)
+    nbr = np.full((1, na, n_max), 1000, np.int32)
+    w = np.zeros((1, na, n_max), np.float32)
+    d = np.zeros((1, na, n_max), np.float32)
+    wi = 2 if angle else 3
+    for a, lc in enumerate(neighbors):
+        k = len(lc)
+        if k:
+            nbr[0, a, :k] = [n[1] for n in lc]
+            w[0, a, :k] = [n[wi] for n in lc]
+            d[0, a, :k] = [n[-1] for n in lc]
+    mask = nbr != 1000
+    nbr[nbr == 1000] = 0
+    atomics = np.array([atomic_numbers], "int32")
+    return {"atomic": atomics, "atom_mask": np.expand_dims(atomics != 0, -1), "neighbors": nbr, "neighbor_mask": mask,
+            "neighbor_weight": w, "neighbor_distance": d}
+
+
 def padded_to_csr(inputs: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     """Inverse of ``pack_padded`` for batches whose valid atoms / neighbour slots are prefixes (what
     DataIterator.__getitem__ produces): padded dict -> CSR batch for ``Engine.load_batch_csr``."""
