@@ -41,6 +41,91 @@ class History:
         self.history.setdefault(key, []).append(float(v))
 
 
+# --------------------------------------------------------------------------- model_config of the HDF5 files
+def keras_model_config(spec: ModelSpec) -> str:
+    """The ``model_config`` attribute of a full-model HDF5 file (scann_model.py:165-177 saves the whole model): the
+    layers of ``create_model`` (scann_model.py:329-453) in graph order with the names Keras gives them and the
+    ``get_config`` dictionaries of the reference's own layers (attention.py:42-50,218-231,320-331;
+    custom_layers.py:67-75).  It carries everything ``spec_from_model_config`` needs to rebuild the model without a
+    yaml; it does NOT carry Keras' ``inbound_nodes`` wiring, so ``keras.models.load_model`` cannot rebuild the graph
+    from a file written here (``load_weights`` on a model built by the reference's ``create_model`` can read it)."""
+    import json
+    L = []
+
+    def add(cls, name, **cfg):
+        L.append({"class_name": cls, "name": name, "config": dict(cfg, name=name)})
+
+    E = spec.embedding_dim
+    if spec.feature == "cgcnn":
+        add("Dense", "embed_atom", units=E, activation="linear")
+    else:
+        add("Embedding", "embed_atom", input_dim=spec.n_atoms, output_dim=E)
+    if spec.use_ring:
+        add("Dense", "extra_embed", units=10, activation="linear")
+    add("Dense", "dense_embed", units=spec.local_dim, activation="swish")
+    add("Dropout", "dropout", rate=0.1)
+    add("GaussianExpansion", "gaussian_expansion", centers=np.linspace(0, spec.gaussian_d, 20).tolist(), width=0.5)
+    if spec.g_update:
+        add("Dense", "neighbor_d", units=spec.local_dim, activation="swish")
+        add("GaussianExpansion", "gaussian_expansion_1", centers=np.linspace(0, np.pi * 2, 20).tolist(), width=0.5)
+        add("Dense", "neighbor_w", units=spec.local_dim, activation="swish")
+    for l in range(spec.n_attention):
+        sfx = "" if l == 0 else f"_{l}"
+        add("LocalAttention", "local_attention" + sfx, dim=spec.local_dim, num_head=spec.num_head, v_proj=False, scale=0.5,
+            kq_proj=True, dropout=bool(spec.use_drop), g_update=bool(spec.g_update))
+        if spec.use_attn_norm:
+            add("ResidualNorm", "residual_norm" + sfx, dim=spec.local_dim, dropout=0.1)
+    add("Dense", "after_Lc", units=spec.local_dim, activation="swish")
+    add("GlobalAttention", "global_attention", dim=spec.global_dim, v_proj=False, kq_proj=True, norm=bool(spec.use_ga_norm))
+    add("Dense", "bf_property", units=spec.dense_out, activation="swish")
+    add("Dense", "predict_property", units=1, activation="mrelu" if spec.mrelu_head else "linear")
+    return json.dumps({"class_name": "Functional", "config": {"name": "model", "layers": L}, "backend": "tensorflow",
+                       "keras_version": "2.10.0"})
+
+
+def spec_from_model_config(model_config) -> ModelSpec:
+    """ModelSpec from the ``model_config`` JSON of a full-model HDF5 file -- written here or by Keras 2.10 for the
+    reference's graph (same layer classes, names and ``get_config`` keys): what ``load_model(path)`` gets from the file
+    instead of a yaml (scann_model.py:85-96)."""
+    import json
+    if isinstance(model_config, bytes):
+        model_config = model_config.decode()
+    cfg = json.loads(model_config) if isinstance(model_config, str) else model_config
+    layers = cfg["config"]["layers"]
+    by_name = {l.get("name", l["config"].get("name")): l for l in layers}
+    la = [l for l in layers if l["class_name"] == "LocalAttention"]
+    ga = [l for l in layers if l["class_name"] == "GlobalAttention"]
+    if not la or not ga or "embed_atom" not in by_name:
+        raise ValueError("model_config does not describe a SCANN graph (no LocalAttention / GlobalAttention / embed_atom)")
+    emb = by_name["embed_atom"]
+    cgcnn = emb["class_name"] == "Dense"
+    gexp = [l for l in layers if l["class_name"] == "GaussianExpansion"]
+    last = by_name.get("predict_property", {"config": {}})["config"].get("activation", "linear")
+    act = last if isinstance(last, str) else str(last.get("config", last))
+    c0 = la[0]["config"]
+    return ModelSpec(
+        n_atoms=int(emb["config"].get("input_dim", 0)) if not cgcnn else 0,
+        embedding_dim=int(emb["config"]["units" if cgcnn else "output_dim"]),
+        n_attention=len(la), local_dim=int(c0["dim"]), num_head=int(c0["num_head"]),
+        global_dim=int(ga[0]["config"]["dim"]), dense_out=int(by_name["bf_property"]["config"]["units"]),
+        use_attn_norm=any(l["class_name"] == "ResidualNorm" for l in layers), use_ga_norm=bool(ga[0]["config"]["norm"]),
+        use_ring="extra_embed" in by_name, g_update=bool(c0["g_update"]),
+        gaussian_d=float(max(gexp[0]["config"]["centers"])) if gexp else 4.0,
+        feature="cgcnn" if cgcnn else "atomic", use_drop=bool(c0.get("dropout", False)),
+        target="e_b" if "mrelu" in act else "homo")
+
+
+def spec_from_h5(path: str) -> ModelSpec:
+    from . import h5lite
+    f = h5lite.File(path)
+    if "model_config" not in f.attrs:
+        raise ValueError(f"{path}: no model_config attribute (a weights-only file); pass the yaml config instead")
+    mc = f.attrs["model_config"]
+    if isinstance(mc, np.ndarray):
+        mc = mc.reshape(-1)[0] if mc.size == 1 else mc.tobytes()
+    return spec_from_model_config(mc)
+
+
 # --------------------------------------------------------------------------- keras-like model
 class ScannKerasModel:
     """What ``SCANN.model`` exposes.  ``infer=True`` is the re-wrapped model of
@@ -231,7 +316,7 @@ class ScannKerasModel:
         """``model.save("...h5")``: full-model layout (weights under /model_weights)."""
         if path.endswith((".h5", ".hdf5", ".keras")):
             from . import h5lite
-            h5lite.save_keras_weights(path, self._keras_layers(), full_model=True)
+            h5lite.save_keras_weights(path, self._keras_layers(), full_model=True, model_config=keras_model_config(self.spec))
         else:
             self.save_weights(path)
 
@@ -254,9 +339,15 @@ class ScannKerasModel:
         for e in self.layout:
             per_layer.setdefault(e.name.split("/")[0], []).append(e)
         out, seen = {}, set()
-        for lname, ws in h5lite.load_keras_weights(path):
-            if not ws:
-                continue
+        file_layers = [(n, ws) for n, ws in h5lite.load_keras_weights(path) if ws]
+        if any(n not in per_layer for n, _ in file_layers):
+            # Keras' automatic names carry a per-session counter (a model built second in a session is saved with
+            # local_attention_7 ...): fall back to what keras load_weights itself does for topological loading --
+            # the weight-bearing layers IN ORDER, shapes checked below
+            if len(file_layers) != len(per_layer):
+                raise ValueError(f"{path}: {len(file_layers)} layers with weights, the model expects {len(per_layer)}")
+            file_layers = [(mine, ws) for (_, ws), mine in zip(file_layers, per_layer)]
+        for lname, ws in file_layers:
             if lname not in per_layer:
                 raise ValueError(f"{path}: layer {lname!r} with weights is not part of this model configuration")
             ents = per_layer[lname]
@@ -315,14 +406,18 @@ class SCANN:
             self.model.load_weights(pretrained)
 
     @classmethod
-    def load_model_infer(cls, path: str, config: dict):
-        m = create_model(config, infer=True)
+    def load_model_infer(cls, path: str, config: Optional[dict] = None):
+        """``SCANN.load_model_infer(path)`` (scann_model.py:85-91): the graph comes from the file's ``model_config``
+        (``config`` = a yaml dict is optional, for weights-only files)."""
+        m = (create_model(config, infer=True) if config is not None
+             else ScannKerasModel(spec_from_h5(path), infer=True))
         m.load_weights(path)
         return m
 
     @classmethod
-    def load_model(cls, path: str, config: dict):
-        m = create_model(config)
+    def load_model(cls, path: str, config: Optional[dict] = None):
+        """``SCANN.load_model(path)`` (scann_model.py:93-96)."""
+        m = create_model(config) if config is not None else ScannKerasModel(spec_from_h5(path))
         m.load_weights(path)
         return m
 
@@ -361,14 +456,20 @@ class SCANN:
         with open(os.path.join(self._run_dir(), "config.yaml"), "w") as f:
             yaml.safe_dump(self.config, f, default_flow_style=False)
         self.train_iterators(self.trainIter, getattr(self, "validIter", None), epochs, self.create_callbacks())
+        # the reference deletes the trained model here (scann_model.py:243-245), so that evaluate() runs on the best
+        # val_mae checkpoint, not on the last epoch's weights; the engine object is kept, its weights are reloaded
+        self._evaluate_from_checkpoint = True
 
     def evaluate(self):
         """``SCANN.evaluate`` (scann_model.py:247-313): best checkpoint -> test predictions -> R2 / MAE report."""
         hy = self.config["hyper"]
-        if self.model is None:
+        best = "{}/models/model_{}.h5".format(self._run_dir(), hy["target"])
+        if self.model is None or (getattr(self, "_evaluate_from_checkpoint", False) and os.path.exists(best)):
             print("Load best validation weight for predicting testset", "\n")
-            self.model = create_model(self.config)
-            self.model.load_weights("{}/models/model_{}.h5".format(self._run_dir(), hy["target"]))
+            if self.model is None:
+                self.model = create_model(self.config)
+            self.model.load_weights(best)
+            self._evaluate_from_checkpoint = False
         data = self.dataIter if hasattr(self, "dataIter") else self.testIter
         y, y_predict = [], []
         for i in range(len(data)):

@@ -87,3 +87,36 @@ def test_cosine_decay_matches_keras_formula():
     assert sch(100) == pytest.approx(0.5e-4)
     assert sch(1000) == pytest.approx(0.5e-4)
     assert sch(50) == pytest.approx(1e-4 * (0.5 * 0.5 + 0.5))
+
+
+def test_model_config_round_trip_for_every_shipped_config():
+    """model.save writes a model_config from which load_model(path) rebuilds the graph without a yaml
+    (scann_model.py:85-96); the JSON uses the reference's layer classes, names and get_config keys."""
+    import json
+    from scann_b200.config import model_spec
+    from scann_b200.configs import get_config
+    from scann_b200.model import keras_model_config, spec_from_model_config
+    for name in ("qm9", "mp2018", "fullerene", "ptgp"):
+        for feature in ("atomic", "cgcnn"):
+            cfg = get_config(name, feature=feature, target="e_b" if name == "mp2018" else "homo")
+            if name == "ptgp":
+                cfg["model"].update(g_update=False, gaussian_d=4.0)
+            spec = model_spec(cfg)
+            js = keras_model_config(spec)
+            back = spec_from_model_config(js)
+            if feature == "cgcnn":
+                spec = spec.__class__(**{**spec.__dict__, "n_atoms": 0})      # the Dense embedding has no vocabulary
+            assert back == spec, (name, feature, back, spec)
+            layers = json.loads(js)["config"]["layers"]
+            names = [l["name"] for l in layers]
+            assert names.count("global_attention") == 1 and "after_Lc" in names
+            assert sum(l["class_name"] == "LocalAttention" for l in layers) == spec.n_attention
+            la = next(l for l in layers if l["class_name"] == "LocalAttention")["config"]
+            assert set(la) >= {"dim", "num_head", "v_proj", "scale", "kq_proj", "dropout", "g_update"}   # attention.py:218-231
+
+
+def test_reference_layer_package_exports():
+    import scann.layers as L
+    for n in ("GlobalAttention", "LocalAttention", "ResidualNorm", "GaussianExpansion", "SGDRC", "root_mean_squared_error",
+              "r2_square", "gather_shape", "mrelu"):
+        assert n in L.__all__ and n in L._CUSTOM_OBJECTS
