@@ -343,19 +343,23 @@ int scann_p2p_begin_step(const void* block_dev, float* sums, void* stream);
 int scann_adam_p2p_step(float* params, float* m, float* v, const float* l2mask, int n, const void* block_dev,
                         float* sums, const void* scalars_dev, float* grad_out, int apply, void* stream);
 
-/* ---- diagnostics --------------------------------------------------------------------------------
- * One 128x128x128 tile product on the tcgen05 tensor cores (self-test of descriptors / layouts).
- * layout 0: A@W, 1: A^T@W, 2: A@W^T, 3: A@W with A in tensor memory; nprod 1 (TF32) or 3 (3xTF32). */
+/* ---- development probes ------------------------------------------------------------------------
+ * Exported only by development builds (nvcc -DSCANN_DEV_PROBES; the production library carries neither these entry
+ * points nor the timestamp stores inside its kernels).
+ * scann_tc_probe: one 128x128x128 tile product on the tcgen05 tensor cores (self-test of descriptors / layouts).
+ * layout 0: A@W, 1: A^T@W, 2: A@W^T, 3: A@W with A in tensor memory; nprod 1 (TF32) or 3 (3xTF32).
+ * scann_tc_time: out[0] = cycles per tcgen05.mma (128 x ncols x 8, tf32) in a chain of nmma accumulating MMAs; mode
+ * bit 0: A from tensor memory, bit 1: core-matrix stride 128 B, bit 4: round-robin over (mode >> 8) accumulators.
+ * scann_debug_clocks*: phase timestamps (clock64) of CTA 0 of the last la_geom_fwd_tc / dense_tc / dense_chain launch;
+ * scann_pipe_clocks: of consumer group 0 of the last la_geom_fwd_pipe launch (96 int64, HOST). */
+#ifdef SCANN_DEV_PROBES
 int scann_tc_probe(const float* A, const float* W, float* D, int layout, int nprod, void* stream);
-/* out[0] = cycles per tcgen05.mma (128 x ncols x 8, tf32) in a chain of nmma accumulating MMAs.
- * mode bit 0: A from tensor memory; mode bit 1: core-matrix stride 128 B instead of 144 B. */
 int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream);
-/* Phase timestamps (clock64) of CTA 0 of the last la_geom_fwd_tc launch; host_out32: 32 int64 (HOST). */
 int scann_debug_clocks(long long* host_out32);
-/* Same for CTA (0,0) of the last dense_tc launch; host_out16: 16 int64 (HOST). */
 int scann_debug_clocks_dense(long long* host_out16);
-/* Same for CTA 0 of the last dense_chain launch (3 prologue stamps, then 4 per step); host_out64: 64 int64 (HOST). */
 int scann_debug_clocks_chain(long long* host_out64);
+int scann_pipe_clocks(long long* host_out96);
+#endif
 
 #ifdef __cplusplus
 }

@@ -64,11 +64,16 @@ PROTOTYPES = {
     "scann_p2p_close": (ci, [vp]),
     "scann_p2p_begin_step": (ci, [vp, vp, vp]),
     "scann_adam_p2p_step": (ci, [vp, vp, vp, vp, ci, vp, vp, vp, vp, ci, vp]),
+}
+
+# development probes: exported only by builds with -DSCANN_DEV_PROBES (bound when present)
+DEV_PROTOTYPES = {
     "scann_tc_probe": (ci, [vp, vp, vp, ci, ci, vp]),
     "scann_tc_time": (ci, [vp, ci, ci, ci, vp]),
     "scann_debug_clocks": (ci, [vp]),
     "scann_debug_clocks_dense": (ci, [vp]),
     "scann_debug_clocks_chain": (ci, [vp]),
+    "scann_pipe_clocks": (ci, [vp]),
 }
 
 
@@ -120,6 +125,11 @@ def _load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    for name, (res, args) in DEV_PROTOTYPES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
     return lib
 
 

@@ -24,9 +24,14 @@
 #define CH_MAX_STEPS 6
 extern "C" int scann_device_sm_count(void);
 
-// phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks_chain: development aid
+// phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks_chain: development builds only
+// (SCANN_NVCC_DEFS=-DSCANN_DEV_PROBES); the production kernels carry no timestamp stores
+#ifdef SCANN_DEV_PROBES
 __device__ long long g_dbg_clk_chain[64];
 #define CCLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (i) < 64) g_dbg_clk_chain[i] = clock64(); } while (0)
+#else
+#define CCLK(i) do { } while (0)
+#endif
 
 // Mirrors ScannChainStep in include/scann_b200.h (same field order).
 struct ChainStep {
@@ -460,11 +465,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+#ifdef SCANN_DEV_PROBES
 extern "C" int scann_debug_clocks_chain(long long* host_out64) {
     cudaError_t e = cudaMemcpyFromSymbol(host_out64, g_dbg_clk_chain, sizeof(long long) * 64);
     if (e != cudaSuccess) { scann_set_error("debug_clocks_chain: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
+#endif
 
 // Host-side mirror of the public struct (include/scann_b200.h): identical layout to ChainStep.
 extern "C" int scann_dense_chain(const void* steps_host, int nsteps, int R, void* stream) {

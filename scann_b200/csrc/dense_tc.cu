@@ -19,8 +19,12 @@
 extern "C" int scann_device_sm_count(void);
 
 // phase timestamps of CTA (0,0) (clock64), read back with scann_debug_clocks_dense: development aid
+#ifdef SCANN_DEV_PROBES
 __device__ long long g_dbg_clk_dense[16];
 #define DCLK(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_dbg_clk_dense[i] = clock64(); } while (0)
+#else
+#define DCLK(i) do { } while (0)
+#endif
 
 struct DenseTcArgs {
     const float* A[3];
@@ -234,11 +238,13 @@ __global__ void __launch_bounds__(DTC_THREADS, 1) dense_tc_kernel(const DenseTcA
     DCLK(5);
 }
 
+#ifdef SCANN_DEV_PROBES
 extern "C" int scann_debug_clocks_dense(long long* host_out16) {
     cudaError_t e = cudaMemcpyFromSymbol(host_out16, g_dbg_clk_dense, sizeof(long long) * 16);
     if (e != cudaSuccess) { scann_set_error("debug_clocks_dense: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
+#endif
 
 extern "C" int scann_dense_forward_tc(const float* const* A, int lda, const float* const* W, const float* const* bias,
                                       int kblk, int nblk, int R, float* C, int ldc, int mode, const float* resid,

@@ -33,8 +33,8 @@ typedef PipeFrame<PF_NS, 2> FwdFrame;
 #define PF_STAGE (FwdFrame::STAGE)
 #define PF_SMEM (FwdFrame::SMEM)
 
-// phase timestamps of CTA 0, consumer group 0 (development builds: -DSCANN_PIPE_CLK): [kernel][tile ordinal][phase]
-#ifdef SCANN_PIPE_CLK
+// phase timestamps of CTA 0, consumer group 0 (development builds: -DSCANN_DEV_PROBES): [kernel][tile ordinal][phase]
+#ifdef SCANN_DEV_PROBES
 __device__ long long g_pipe_clk[2][4][12];
 #define PCLK(k, ph) do { if (blockIdx.x == 0 && tid == 0 && (i / PF_NG) < 4) g_pipe_clk[k][i / PF_NG][ph] = clock64(); } while (0)
 #define PCLK0(k, ph) do { if (blockIdx.x == 0 && tid == 0) g_pipe_clk[k][0][ph] = clock64(); } while (0)

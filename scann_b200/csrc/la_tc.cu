@@ -32,8 +32,12 @@
 #define LTC_RPW 8                          // rows per warp in the row-wise epilogue (= TR / warps per group)
 
 // phase timestamps of CTA 0 (clock64), read back with scann_debug_clocks: development aid
+#ifdef SCANN_DEV_PROBES
 __device__ long long g_dbg_clk[32];
 #define DBG_CLK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_dbg_clk[i] = clock64(); } while (0)
+#else
+#define DBG_CLK(i) do { } while (0)
+#endif
 
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
@@ -747,8 +751,10 @@ extern "C" int scann_la_forward_noupdate_tc(int grid, int tile_stride, int mma_r
     return scann_check_launch("scann_la_forward_noupdate_tc");
 }
 
+#ifdef SCANN_DEV_PROBES
 extern "C" int scann_debug_clocks(long long* host_out32) {
     cudaError_t e = cudaMemcpyFromSymbol(host_out32, g_dbg_clk, sizeof(long long) * 32);
     if (e != cudaSuccess) { scann_set_error("debug_clocks: %s", cudaGetErrorString(e)); return 1; }
     return 0;
 }
+#endif

@@ -7,6 +7,7 @@
 //   nprod 1: single TF32 product of the raw fp32 operands; nprod 3: hi/lo split, 3 products into one
 //   accumulator; nprod 4: the same 3 products, the two cross terms in a second accumulator that is
 //   added on the CUDA cores (measures what the tensor core's accumulation costs in accuracy).
+#ifdef SCANN_DEV_PROBES      // development builds only: SCANN_NVCC_DEFS=-DSCANN_DEV_PROBES python -m scann_b200.build --force
 #include <type_traits>
 
 #include "common.cuh"
@@ -216,3 +217,4 @@ extern "C" int scann_tc_time(float* out, int mode, int nmma, int ncols, void* st
     tc_time_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(out, mode, nmma, ncols);
     return scann_check_launch("scann_tc_time");
 }
+#endif  // SCANN_DEV_PROBES

@@ -92,9 +92,12 @@ class Engine:
                 for blk in range(e.shape[0] // D):
                     offs.append(e.offset + blk * D * D)
         self.tblocks = torch.tensor(offs, dtype=torch.int32, device=dev)
+        import collections
         self._ws: Dict[Tuple, dict] = {}
         self._pinned: Dict[Tuple, list] = {}
-        self._batches: Dict[Tuple, Batch] = {}
+        self._batches: "collections.OrderedDict[Tuple, Batch]" = collections.OrderedDict()
+        # persistent device buffers + captured graphs are kept for this many batch shape classes (LRU)
+        self.max_shape_classes = int(os.environ.get("SCANN_MAX_SHAPE_CLASSES", "8"))
         self.use_graphs = os.environ.get("SCANN_GRAPHS", "1") == "1"
         self.la_grid = self.sm_count
         self.launches = 0
@@ -300,14 +303,29 @@ class Engine:
             slots = self.sm_count * (TILE // stride)
             waves = max(1, -(-P // (stride * slots)))      # more, smaller tiles only add per-tile latency (measured)
             tile_rows = min(stride, max(N, -(-P // (waves * slots)) + (N + 1) // 2))
+            tile_rows = min(stride, (tile_rows + 7) // 8 * 8)          # quantised: few shape classes per data set
         # tile capacity: every non-final tile of a greedy group holds more than tile_rows-N rows
         # (and two consecutive tiles of a group together hold more than tile_rows rows)
         cap = (min(P // (tile_rows + 1 - N), 2 * P // tile_rows + 1) + ngroups + 1 if N <= 64
                else 2 * (P // TILE) + ngroups + 2)
-        tile_cap = max(64, (cap + 63) // 64 * 64)
+        # shape classes are quantised (capacities on a geometric grid, ratio 1.25) so that a shuffled data set whose
+        # batches differ a little in their pair counts maps onto a handful of persistent buffers / captured graphs
+        tile_cap = 64
+        while tile_cap < cap:
+            tile_cap = (tile_cap * 5 // 4 + 63) // 64 * 64
         key = (B, M, N, tile_cap, tile_rows, stride)
         b = self._batches.get(key)
+        if b is not None:
+            self._batches.move_to_end(key)
         if b is None:
+            while len(self._batches) >= self.max_shape_classes:      # least recently used class: buffers, graphs
+                old_key, old = self._batches.popitem(last=False)
+                old.graphs.clear()
+                for k in [k for k in self._pinned if k[1] == old_key]:
+                    del self._pinned[k]
+                live = {(x.R, x.B, x.rows) for x in self._batches.values()}
+                for k in [k for k in self._ws if k[:3] not in live and k[:3] != (B * M, B, tile_cap * stride)]:
+                    del self._ws[k]
             b = self._batches[key] = self._new_batch(B, M, N, tile_cap, ngroups, stride)
             b.tile_rows = tile_rows
             # rows of a tile slot that can hold pairs, rounded up to the MMA granularity: the N extent of the

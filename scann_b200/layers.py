@@ -125,7 +125,7 @@ class _Plan:
         self.pair_d = torch.empty(rows, dtype=torch.float32, device=dev)
         self.pair_w = torch.empty(rows, dtype=torch.float32, device=dev)
         self.status = torch.zeros(1, **i32)
-        scratch = torch.empty(2 * ngroups + 8, **i32)
+        scratch = torch.zeros(2 * ngroups + 8, **i32)      # the one-launch plan form relies on a zeroed buffer
         zeros = torch.zeros(P, dtype=torch.float32, device=dev)
         check(lib.scann_plan_build(_p(mask_u8), _p(neighbors), _p(zeros), _p(zeros), B, M, N, cap, TILE, TILE, _p(self.cnt),
                                    _p(self.rowptr), _p(self.tile_a0), _p(self.tile_a1), _p(self.ntiles),

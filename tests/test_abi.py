@@ -9,9 +9,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "scann_b200.h")
 
 
-def header_symbols():
+def _production_header():
+    """The header without comments and without the development-probe block (#ifdef SCANN_DEV_PROBES)."""
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.sub(r"#ifdef SCANN_DEV_PROBES.*?#endif", "", src, flags=re.S)
+
+
+def header_symbols():
+    src = _production_header()
     return sorted(set(re.findall(r"\b(scann_[a-z0-9_]+)\s*\(", src)))
 
 
@@ -33,12 +39,15 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert s in _abi.PROTOTYPES, f"{s} has no ctypes prototype"
     for s in _abi.PROTOTYPES:
         assert s in syms, f"{s} bound in _abi.py but not declared in the header"
+    # the production library carries no development probes (timestamp stores, tcgen05 self-tests)
+    if "SCANN_DEV_PROBES" not in os.environ.get("SCANN_NVCC_DEFS", ""):
+        for s in _abi.DEV_PROTOTYPES:
+            assert not hasattr(raw, s), f"{s} is a development probe and must not be in the production library"
 
 
 def test_prototype_arity_matches_header():
     from scann_b200 import _abi
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = _production_header()
     for name, (_, args) in _abi.PROTOTYPES.items():
         m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
         assert m, name
