@@ -309,11 +309,53 @@ def run_ours(args):
     torch.cuda.synchronize()
     infer_ms = i0.elapsed_time(i1)
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, infer_ms, (e2e_csr_s or 0.0) * 1e3, e2e_tob_s * 1e3], dtype=torch.float64,
-                     device=dev)
+    # ---- MP2018-shaped sub-record (BASELINE.json configs[4]: the data-parallel scaling sweep is quoted on
+    # MP2018-shaped batches): the same two timed regions on model_mp2018.yaml, 64 structures per GPU
+    mp_dev_ms = mp_e2e_ms = 0.0
+    mp_info = None
+    if args.workload == "qm9" and not args.no_mp2018:
+        mcfg, mshape, mB, _ = workload_config("mp2018")
+        mmodel = create_model(mcfg, seed=1)
+        sdist.attach(mmodel, world)
+        meng = mmodel.engine
+        meng.train_dropout = True
+        minputs, mtarget = make_batch(mshape, seed=rank, B=mB)
+        mA, mP = count_valid(minputs)
+        mdev = {k: torch.from_numpy(np.ascontiguousarray(v.view(np.uint8) if v.dtype == np.bool_ else v)).to(dev)
+                for k, v in minputs.items()}
+        mtgt = torch.from_numpy(mtarget).to(dev)
+
+        def mstep():
+            bb = meng.load_batch(mdev, plan=False, pairs_hint=mP)
+            meng.train_step(bb, mtgt, mcfg["hyper"]["lr"], allreduce=mmodel.allreduce, batch_global=mB * world, replan=True)
+
+        for _ in range(max(args.warmup, 3)):
+            mstep()
+        barrier()
+        mevs = []
+        for _ in range(args.steps):
+            flush.fill_(1.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mstep()
+            e1.record()
+            mevs.append((e0, e1))
+        barrier()
+        mp_dev_ms = sum(a.elapsed_time(b) for a, b in mevs)
+        mmodel.fit(Repeat((minputs, mtarget), 3), epochs=1, verbose=0)
+        barrier()
+        t0 = time.perf_counter()
+        mmodel.fit(Repeat((minputs, mtarget), args.steps), epochs=1, verbose=0)
+        barrier()
+        mp_e2e_ms = (time.perf_counter() - t0) * 1e3
+        meng.check_status()
+        mp_info = {"B": mB, "A": mA, "P": mP, "layers": mcfg["model"]["n_attention"], "h2d": mmodel.last_e2e_bytes[0]}
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3, infer_ms, (e2e_csr_s or 0.0) * 1e3, e2e_tob_s * 1e3, mp_dev_ms, mp_e2e_ms],
+                     dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, infer_ms, e2e_csr_ms, e2e_tob_ms = (float(x) for x in t.cpu())
+    dev_ms, e2e_ms, infer_ms, e2e_csr_ms, e2e_tob_ms, mp_dev_ms, mp_e2e_ms = (float(x) for x in t.cpu())
 
     def finish():
         # Captured CUDA graphs hold NCCL work; tearing the communicator down under them can hang at
@@ -337,7 +379,11 @@ def run_ours(args):
     n_fwd, ms_fwd = prof.get("la_forward", (0, float("nan")))
     n_wg, ms_wg = prof.get("wgrad_batch", (0, float("nan")))
     ach = bytes_bwd / (ms_bwd * 1e-3) / 1e9
-    kern = ("la_attn_bwd_tc_kernel + la_geom_bwd_tc_kernel (one scann_la_backward_tc call = one layer of "
+    pipe_bwd = eng.tc_la_bwd and (eng.la_pipe & 12) == 12 and int(inputs["neighbors"].shape[2]) <= 32 and \
+        bool(CFG["model"].get("g_update", True))
+    kern = ("la_attn_bwd_pipe_kernel + la_geom_bwd_pipe_kernel (one layer of local-attention backward: warp-specialised "
+            "TMA pipelines, la_pipe_bwd.cu)" if pipe_bwd else
+            "la_attn_bwd_tc_kernel + la_geom_bwd_tc_kernel (one scann_la_backward_tc call = one layer of "
             "local-attention backward)" if eng.tc_la_bwd else "la_bwd_simt_kernel")
     # DRAM traffic of the same kernels from the committed `ncu --set full` capture (dram__bytes_read.sum +
     # dram__bytes_write.sum per launch), when the workload matches the capture
@@ -357,18 +403,39 @@ def run_ours(args):
             "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
             "share_of_step": n_bwd * ms_bwd / args.steps / (dev_ms / args.steps),
             "algorithmic_bytes_per_launch": bytes_bwd,
-            "tensor_view": {"tf32_tflops_issued": flops_bwd / (ms_bwd * 1e-3) / 1e12,
-                            "note": "3 tf32 products per fp32 product; nominal dense tf32 peak is half the bf16 peak"},
+            # measured kind::tf32 rate of one SM (profiles/r02_tf32_peak.md: 46.4 cycles per 128x128x8 tcgen05.mma from
+            # one issuing thread = 5 650 flop/clk/SM), times the SMs and the SM clock seen during this run
+            "tensor_view": (lambda tf, pk: {"tf32_tflops_issued": tf, "tf32_peak_measured_tflops": pk, "frac": tf / pk,
+                                            "note": "3 tf32 products per fp32 product; peak = 5650 flop/clk/SM (measured "
+                                                    "tcgen05 kind::tf32 issue rate) x SMs x SM clock"})(
+                flops_bwd / (ms_bwd * 1e-3) / 1e12,
+                5650.0 * eng.sm_count * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e12),
             "la_forward": {"achieved": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "ms_per_launch": ms_fwd,
                            "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     if n_wg:
         # every weight-gradient GEMM of the step in one launch: reads each saved per-pair tensor once
         # (per pair and layer: g', d_k, g, d_pre + the gathered x[j]; per atom: x, s_pre, t, dq and the four
         # ResidualNorm operands -- models without geometry update have no g / d_pre / s_pre / t problems)
+        # (the gathered neighbour rows x[j] of the key-kernel problem come out of the [A,128] atom array, which stays in
+        # L2: they are counted once per atom, not once per pair)
         gu = bool(CFG["model"].get("g_update", True))
-        bytes_wg = L * ((5 if gu else 3) * 512.0 * P_valid + (8 if gu else 6) * 512.0 * A_valid)
+        bytes_wg = L * ((4 if gu else 2) * 512.0 * P_valid + (9 if gu else 7) * 512.0 * A_valid)
         roof["wgrad_batch"] = {"achieved": bytes_wg / (ms_wg * 1e-3) / 1e9, "ms_per_launch": ms_wg,
                                "frac": bytes_wg / (ms_wg * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    # global attention + head (one CTA per structure): algorithmic bytes 516 A + 512 B forward (q|k rows in, ga out,
+    # pooled context), twice that backward; a few microseconds of launch-latency-bound work per step
+    n_gaf, ms_gaf = prof.get("ga_forward", (0, float("nan")))
+    n_gab, ms_gab = prof.get("ga_backward", (0, float("nan")))
+    if n_gaf:
+        bytes_ga = 2 * 516.0 * A_valid + 512.0 * B
+        roof["global_attention"] = {
+            "kernel": "ga_head_fwd_kernel / ga_head_bwd_kernel (GlobalAttention + property head, one CTA per structure)",
+            "forward": {"achieved": bytes_ga / (ms_gaf * 1e-3) / 1e9, "ms_per_launch": ms_gaf,
+                        "frac": bytes_ga / (ms_gaf * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_ga},
+            "backward": (None if not n_gab else
+                         {"achieved": 2 * bytes_ga / (ms_gab * 1e-3) / 1e9, "ms_per_launch": ms_gab,
+                          "frac": 2 * bytes_ga / (ms_gab * 1e-3) / 1e9 / peaks["hbm_gbs"]}),
+            "note": "1-2 MB per launch: bound by launch latency and the per-structure reduction chain, not by HBM"}
     # bounded CPU sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu and args.workload == "qm9":
@@ -409,6 +476,14 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "infer": {"value": B * world * args.steps / (infer_ms * 1e-3), "unit": UNIT,
                   "note": "forward incl. ga_score, inputs resident in HBM"},
+        "mp2018": (None if mp_info is None else {
+            "metric": f"structures/sec (mp2018 train step fwd+bwd+Adam, batch {mp_info['B']} per GPU)",
+            "value": mp_info["B"] * world * args.steps / (mp_dev_ms * 1e-3), "unit": UNIT,
+            "ms_per_step": mp_dev_ms / args.steps,
+            "e2e": {"value": mp_info["B"] * world * args.steps / (mp_e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(mp_info["h2d"]), "d2h_bytes_per_step": 16},
+            "config": {"workload": f"mp2018_train_step_b{mp_info['B']}", "layers": mp_info["layers"],
+                       "valid_atoms_per_gpu": mp_info["A"], "valid_pairs_per_gpu": mp_info["P"], "parallelism": f"dp{world}"}}),
     }
     emit(json.dumps(out))
     finish()
@@ -421,6 +496,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline sample")
+    ap.add_argument("--no-mp2018", action="store_true", help="skip the MP2018-shaped sub-record")
     ap.add_argument("--workload", default="qm9", choices=sorted(WORKLOADS),
                     help="qm9 (default, BASELINE.json configs[1]) | mp2018 | fullerene: other shapes, for reference")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

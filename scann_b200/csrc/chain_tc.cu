@@ -107,19 +107,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = blockIdx.x * TR;
     if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-    // The three products of 3xTF32 are issued by THREE warps at the same time (one elected lane each): a single thread
-    // sustains one tcgen05.mma per ~45-60 cycles whatever its N (profiles/r02b_tc_time2.log), so 48 MMAs from one
-    // thread cost ~3 000 cycles per GEMM step against ~1 000 for three chains of 16.  Each chain has its own
-    // accumulator (main | W_lo X_hi | W_hi X_lo; summed in the read-back, corrections first); with 128-row tiles only
-    // two accumulators fit next to the weight block, and the second warp issues both correction chains.
-    constexpr int NISS = TR <= 64 ? 3 : 2;
-    if (tid == 0) { mbar_init(&bar, NISS); mbar_fence_init(); }
+    // (Issuing the three products of 3xTF32 from three warps into three accumulators was tried in round 2: no change
+    // of the step time -- the chain's GEMM steps are not bound by MMA issue -- and 1.1e-5 instead of 8e-6 on the
+    // QM9 golden: kept as it was.)
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const uint32_t t_whi = tmem, t_wlo = tmem + 128, t_dm = tmem + 256, t_dc = tmem + 256 + TR;
-    const uint32_t t_dc2 = NISS == 3 ? tmem + 256 + 2 * TR : t_dc;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t idesc = tc_idesc_tf32(128, TR, false, false);
     const int l8 = lane & 7, rsub = lane >> 3;
@@ -178,25 +174,18 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
             tc_fence_before();
             __syncthreads();
             if (kb == 0) CCLK(3 + si * 4);
-            if (warp < NISS && tc_elect_one()) {
+            if (warp == 0 && tc_elect_one()) {
                 tc_fence_after();
                 const uint64_t dh = tc_desc_kmajor(smem_u32(sXhi), 0), dl = tc_desc_kmajor(smem_u32(sXlo), 0);
                 const bool first = kb == 0;
-                if (warp == 0) {
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)
-                        tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
-                }
-                if (warp == 1) {
+                for (int ks = 0; ks < 16; ++ks)
+                    tc_mma_ts(t_dm, t_whi + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)
-                        tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
-                }
-                if (warp == NISS - 1) {
+                for (int ks = 0; ks < 16; ++ks)
+                    tc_mma_ts(t_dc, t_wlo + ks * 8, dh + ks * TC_KSTEP_DESC, idesc, !(first && ks == 0));
 #pragma unroll
-                    for (int ks = 0; ks < 16; ++ks)
-                        tc_mma_ts(t_dc2, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, NISS == 2 || !(first && ks == 0));
-                }
+                for (int ks = 0; ks < 16; ++ks) tc_mma_ts(t_dc, t_whi + ks * 8, dl + ks * TC_KSTEP_DESC, idesc, true);
                 tc_commit(&bar);
             }
             if (WPREF && kb == st.kblk - 1) {
@@ -232,15 +221,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) dense_chain_kernel(const __grid
                 float m[16], c[16];
                 tmem_ld16(t_dm + lane_base + rr, m);
                 tmem_ld16(t_dc + lane_base + rr, c);
-                if (NISS == 3) {
-                    float c2[16];
-                    tmem_ld16(t_dc2 + lane_base + rr, c2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) c[q] += c2[q];
-                } else {
-                    tmem_ld_wait();
-                }
+                tmem_ld_wait();
 #pragma unroll
                 for (int q = 0; q < 16; ++q) *reinterpret_cast<float*>(sS + tc_off(rr + q, n)) = m[q] + c[q];
             }

@@ -42,6 +42,14 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Spin until *p has reached `target` (wrap-safe) -- BOUNDED: a peer that died or a protocol error must not hang the
+// GPU.  After ~2 s the wait gives up and marks sums[3] (the engine reports it); the step's result is then garbage.
+__device__ __forceinline__ void p2p_wait_flag(const uint32_t* p, uint32_t target, float* sums) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(p) - target) < 0) {
+        if (clock64() - t0 > 4000000000LL) { if (sums) sums[3] = 1.0f; return; }
+    }
+}
 
 struct AdamScalarsP {      // same block as AdamScalars in optim.cu
     float alpha, b1, b2, eps, l2, batch;
@@ -52,9 +60,8 @@ __global__ void __launch_bounds__(32) p2p_begin_step_kernel(const P2PBlock* __re
     const uint32_t* fl = b.flags[b.rank];
     const uint32_t e_prev = fl[P2P_EPOCH];
     const int s = threadIdx.x;
-    if (s < b.world && s != b.rank)
-        while ((int32_t)(ld_acquire_sys(fl + P2P_DONE + s) - e_prev) < 0) {}
-    if (s < 4) sums[s] = 0.f;
+    if (s < 3) sums[s] = 0.f;                   // sums[3]: sticky "a flag wait gave up" marker
+    if (s < b.world && s != b.rank) p2p_wait_flag(fl + P2P_DONE + s, e_prev, sums);
 }
 
 // sums[0] = global SSE, [1] = global sum |err|, [2] = l2 penalty sum (as sse[0..2] of adam_kernel / loss_value)
@@ -72,8 +79,7 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(float* __restrict__ p, fl
         __threadfence_system();                 // this rank's gradients (earlier kernels of the stream) before the flag
         st_release_sys(b.flags[threadIdx.x] + P2P_READY + b.rank, e);
     }
-    if ((int)threadIdx.x < b.world && (int)threadIdx.x != b.rank)
-        while ((int32_t)(ld_acquire_sys(fl + P2P_READY + threadIdx.x) - e) < 0) {}
+    if ((int)threadIdx.x < b.world && (int)threadIdx.x != b.rank) p2p_wait_flag(fl + P2P_READY + threadIdx.x, e, sums);
     __syncthreads();
     const AdamScalarsP h = *hs;
     float sse = 0.f, sabs = 0.f;

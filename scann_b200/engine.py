@@ -687,12 +687,14 @@ class Engine:
         self._dense([_p(ws["xa"])], D, [self.w("global_attention/query/kernel"), self.w("global_attention/key/kernel")],
                     [self.w("global_attention/query/bias"), self.w("global_attention/key/bias")], 1, 2, R,
                     _p(ws["qk"]), 2 * D)
+        self._ev("ga_forward", True)
         check(lib.scann_ga_head_forward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                         self.w("bf_property/kernel"), self.w("bf_property/bias"),
                                         self.w("predict_property/kernel"), self.w("predict_property/bias"),
                                         int(sp.mrelu_head), _p(ws["ga"]), _p(ws["y"]),
                                         _p(ws["ctxg"]) if training else 0, _p(ws["tb"]) if training else 0, st),
               "ga_head_forward")
+        self._ev("ga_forward", False)
         self._pdl(False)
         self.launches += 1
         return ws["y"], ws["ga"]
@@ -804,12 +806,14 @@ class Engine:
                 steps.append(chain_step(W=[self.w("global_attention/key/kernel")],
                                         bias=self.w("global_attention/key/bias"), C_=_p(ws["qk"], D), ldc=2 * D))
             self._chain(steps, R)
+        self._ev("ga_forward", True)
         check(lib.scann_ga_head_forward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                         self.w("bf_property/kernel"), self.w("bf_property/bias"),
                                         self.w("predict_property/kernel"), self.w("predict_property/bias"),
                                         int(sp.mrelu_head), _p(ws["ga"]), _p(ws["y"]),
                                         _p(ws["ctxg"]) if training else 0, _p(ws["tb"]) if training else 0, st),
               "ga_head_forward")
+        self._ev("ga_forward", False)
         self._pdl(False)
         self.launches += 1
         return ws["y"], ws["ga"]
@@ -851,11 +855,13 @@ class Engine:
         self._pdl(False)
         check(lib.scann_rmse_prepare(_p(ws["y"]), _p(target), b.B, _p(ws["dy"]), _p(self.grads, n), st), "rmse_prepare")
         self._pdl(True)
+        self._ev("ga_backward", True)
         check(lib.scann_ga_head_backward(_p(ws["qk"]), _p(b.atom_mask), b.B, b.M, int(sp.use_ga_norm),
                                          self.wT("bf_property/kernel"), self.w("predict_property/kernel"),
                                          _p(ws["tb"]), _p(ws["dy"]), _p(ws["d_qk"]), _p(ws["d_tb"]),
                                          self.gw("predict_property/kernel"), self.gw("predict_property/bias"), st),
               "ga_head_backward")
+        self._ev("ga_backward", False)
         self.launches += 2
         if self.use_chain and self.tc_la_bwd:
             return self._backward_chained(b, ws, fork, wgrad, side, main, sst)

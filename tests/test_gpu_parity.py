@@ -227,8 +227,14 @@ def test_full_configuration_parity_against_oracle(name):
     l2n = [e.name for e in lay if e.l2]
     loss, y_ref, ga_ref, grads = O.loss_and_grads(w, inputs, target, l2n, **kw)
     eng, b, y, ga = run_forward(spec, arena, inputs)
-    assert rel(y, y_ref.ravel()) <= TOL_OUT
-    assert rel(ga, ga_ref[..., 0]) <= (TOL_OUT if ring else ga_tolerance(spec, lay, arena, inputs))
+    # At full depth and batch the reference's OWN fp32 arithmetic (the fp32 oracle, same graph order) sits further than
+    # 1e-5 from fp64 on the worst of the B*M ga scores / B outputs (error grows with the layer count, and the bound is a
+    # max over 100x more elements than in the small cases): the bound is 1e-5 or 3x that measured fp32 noise floor.
+    y32, ga32 = O.predict(w, inputs, torch.float32, **kw)
+    tol_y = max(TOL_OUT, 3.0 * rel(y32, y_ref))
+    tol_ga = max(TOL_OUT, 3.0 * rel(ga32, ga_ref))
+    assert rel(y, y_ref.ravel()) <= tol_y, (rel(y, y_ref.ravel()), tol_y)
+    assert rel(ga, ga_ref[..., 0]) <= tol_ga, (rel(ga, ga_ref[..., 0]), tol_ga)
     eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
     torch.cuda.synchronize()
     eng.check_status()

@@ -1,0 +1,28 @@
+#!/bin/bash
+# multi-GPU visit (gpurun --gpus N): data-parallel correctness (NCCL and peer-memory exchange) + the bench at N ranks
+N=${1:-8}; TAG=${2:-r02m}
+O=gpurun_out
+mkdir -p $O
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29511 tools/dp_check.py > $O/${TAG}_dp_check_${N}gpu.log 2>&1; echo "dp_check rc=$?"; grep -E "world|DP_CHECK" $O/${TAG}_dp_check_${N}gpu.log
+timeout 900 $TR --master-port 29512 bench.py --gpus $N --no-cpu > $O/${TAG}_bench_${N}gpu_nccl.json 2> $O/${TAG}_bench_${N}gpu_nccl.err; echo "bench nccl rc=$?"
+python - <<PY
+import json
+for m in ("nccl",):
+    try:
+        d = json.load(open("$O/${TAG}_bench_${N}gpu_%s.json" % m))
+        print(m, "qm9 ms/step", round(d["ms_per_step"], 4), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "| mp2018 ms/step", round(d["mp2018"]["ms_per_step"], 4), "value", round(d["mp2018"]["value"]), "e2e", round(d["mp2018"]["e2e"]["value"]))
+    except Exception as e:
+        print(m, "failed", e)
+PY
+SCANN_P2P_REDUCE=1 timeout 900 $TR --master-port 29513 bench.py --gpus $N --no-cpu > $O/${TAG}_bench_${N}gpu_p2p.json 2> $O/${TAG}_bench_${N}gpu_p2p.err; echo "bench p2p rc=$?"
+python - <<PY
+import json
+for m in ("p2p",):
+    try:
+        d = json.load(open("$O/${TAG}_bench_${N}gpu_%s.json" % m))
+        print(m, "qm9 ms/step", round(d["ms_per_step"], 4), "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "| mp2018 ms/step", round(d["mp2018"]["ms_per_step"], 4), "value", round(d["mp2018"]["value"]), "e2e", round(d["mp2018"]["e2e"]["value"]))
+    except Exception as e:
+        print(m, "failed", e)
+PY
+tail -3 $O/${TAG}_bench_${N}gpu_p2p.err
