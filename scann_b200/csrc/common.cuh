@@ -3,6 +3,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// numerics experiment (SCANN_NVCC_DEFS=-DSCANN_ACCURATE_MATH): IEEE expf / division instead of ex2.approx / rcp.approx
+// in every epilogue -- used once to attribute the full-depth error budget, not a product mode
+#ifdef SCANN_ACCURATE_MATH
+#define __expf expf
+#define __fdividef(a, b) ((a) / (b))
+#endif
+
 #define SCANN_D 128          // local_dim = global_dim = dense_out (every shipped config)
 #define SCANN_H 8            // attention heads
 #define SCANN_HD 16          // head dim

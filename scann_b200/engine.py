@@ -195,6 +195,9 @@ class Engine:
         return _p(self.grads, self.layout[name].offset + off)
 
     def check_status(self) -> None:
+        if self.p2p is not None and float(self.p2p.sums[3].item()) != 0.0:
+            self.p2p.sums[3] = 0.0
+            raise _abi.ScannAbiError("peer-memory gradient exchange: a flag wait gave up (a peer rank is not taking part)")
         words = self.status.cpu().tolist()
         s = words[0]
         if s:
