@@ -202,7 +202,17 @@ def run_ours(args):
     # the Keras train step runs the graph with training=True: Dropout(0.1) after dense_embed and in every
     # ResidualNorm is part of the measured step (the facade does the same in train_on_batch / fit)
     eng.train_dropout = True
-    inputs, target = make_batch(shape_name, seed=rank, B=B, use_ring=bool(CFG["model"].get("use_ring")))
+    def rank_batch(shape, Bl, ring=False):
+        """This rank's batch.  One GPU: the seeded batch of Bl structures.  N GPUs: the seeded GLOBAL batch of N * Bl
+        structures, dealt to the ranks with equal structure counts and balanced pair counts (dist.balanced_shards:
+        a data-parallel step is as slow as its slowest rank) -- per-GPU work stays what it is on one GPU."""
+        if world == 1:
+            return make_batch(shape, seed=rank, B=Bl, use_ring=ring)
+        gin, gt = make_batch(shape, seed=0, B=Bl * world, use_ring=ring)
+        mine = sdist.balanced_shards(gin["neighbor_mask"].reshape(Bl * world, -1).sum(1), world)[rank]
+        return {k: np.ascontiguousarray(v[mine]) for k, v in gin.items()}, np.ascontiguousarray(gt[mine])
+
+    inputs, target = rank_batch(shape_name, B, bool(CFG["model"].get("use_ring")))
     A_valid, P_valid = count_valid(inputs)
     lr = CFG["hyper"]["lr"]
 
@@ -319,7 +329,7 @@ def run_ours(args):
         sdist.attach(mmodel, world)
         meng = mmodel.engine
         meng.train_dropout = True
-        minputs, mtarget = make_batch(mshape, seed=rank, B=mB)
+        minputs, mtarget = rank_batch(mshape, mB)
         mA, mP = count_valid(minputs)
         mdev = {k: torch.from_numpy(np.ascontiguousarray(v.view(np.uint8) if v.dtype == np.bool_ else v)).to(dev)
                 for k, v in minputs.items()}
@@ -455,6 +465,8 @@ def run_ours(args):
         "config": {"workload": f"{args.workload}_train_step_b{B}", "structures_per_gpu": B,
                    "M": int(inputs["neighbors"].shape[1]), "N": int(inputs["neighbors"].shape[2]), "layers": L,
                    "valid_atoms_per_gpu": A_valid, "valid_pairs_per_gpu": P_valid, "parallelism": f"dp{world}",
+                   "sharding": ("one seeded batch" if world == 1 else
+                                "seeded global batch dealt to the ranks: equal structure counts, balanced pair counts"),
                    "l2": "flushed between steps (256 MiB write outside the timed events)",
                    "engine": "tcgen05 3xTF32 (fp32-accurate)" if eng.tc_la_bwd else "fp32 SIMT",
                    "dropout": eng.dropout_rate if eng.train_dropout else 0.0,

@@ -47,6 +47,32 @@ def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
+def balanced_shards(cost, world: int):
+    """Assign len(cost) structures to ``world`` ranks, the same NUMBER of structures per rank (len(cost) must be a
+    multiple of world -- the RMSE of the global batch does not care which rank holds which structure) and nearly the
+    same total ``cost`` (valid atom-neighbour pairs: what the local-attention kernels' time is proportional to).
+    A data-parallel step ends with an exchange every rank waits for, so its time is the SLOWEST rank's: shards of
+    randomly drawn structures differ by 3 % (QM9) to 11 % (MP2018-shaped crystals) in their pair counts, and that
+    difference is lost on every step.  Longest-processing-time greedy: structures in decreasing cost order, each to
+    the lightest rank that still has room.  Returns a list of ``world`` sorted index arrays."""
+    import numpy as np
+    cost = np.asarray(cost, np.int64)
+    n = len(cost)
+    if n % world:
+        raise ValueError("the number of structures must be a multiple of the number of ranks")
+    per = n // world
+    load = np.zeros(world, np.int64)
+    count = np.zeros(world, np.int64)
+    owner = np.empty(n, np.int64)
+    for i in np.argsort(-cost, kind="stable"):
+        open_ranks = np.flatnonzero(count < per)
+        r = open_ranks[np.argmin(load[open_ranks])]
+        owner[i] = r
+        load[r] += cost[i]
+        count[r] += 1
+    return [np.flatnonzero(owner == r) for r in range(world)]
+
+
 class P2PExchange:
     """Gradient exchange fused into the optimiser kernel over NVLink peer memory (scann_b200/csrc/p2p.cu): every rank's
     gradient arena sits in a block the other ranks of the node map through CUDA IPC; ``scann_adam_p2p_step`` sums the
@@ -63,7 +89,7 @@ class P2PExchange:
             raise ValueError(f"peer-memory exchange supports up to {self.MAX_RANKS} ranks of one node")
         n = engine.layout.total
         nfl = (n + 4 + 63) // 64 * 64
-        nbytes = nfl * 4 + 64 * 4
+        nbytes = nfl * 4 + 64 * 4 + nfl * 4       # arena | 64 flag words | reduced arena (two-shot exchange, >= 4 ranks)
         ptr = C.c_void_p()
         check(lib.scann_p2p_alloc(nbytes, C.byref(ptr)), "p2p_alloc")
         self.local = int(ptr.value)

@@ -120,3 +120,20 @@ def test_reference_layer_package_exports():
     for n in ("GlobalAttention", "LocalAttention", "ResidualNorm", "GaussianExpansion", "SGDRC", "root_mean_squared_error",
               "r2_square", "gather_shape", "mrelu"):
         assert n in L.__all__ and n in L._CUSTOM_OBJECTS
+
+
+def test_balanced_shards_equal_counts_and_nearly_equal_pair_counts():
+    from scann_b200.dist import balanced_shards
+    from scann_b200.synth import make_batch
+    for shape, B in (("qm9", 128), ("mp2018", 64)):
+        inp, _ = make_batch(shape, seed=0, B=B * 8)
+        cost = inp["neighbor_mask"].reshape(B * 8, -1).sum(1)
+        shards = balanced_shards(cost, 8)
+        assert sorted(np.concatenate(shards).tolist()) == list(range(B * 8))        # a partition
+        assert all(len(s) == B for s in shards)
+        loads = np.array([cost[s].sum() for s in shards])
+        assert loads.max() - loads.min() <= 0.005 * loads.mean()                     # within 0.5 %
+        naive = np.array([cost[r * B:(r + 1) * B].sum() for r in range(8)])
+        assert naive.max() - naive.min() > 4 * (loads.max() - loads.min())
+    with pytest.raises(ValueError):
+        balanced_shards(np.ones(10), 4)
