@@ -128,13 +128,17 @@ class P2PExchange:
 
 
 def attach(model, world: int) -> None:
-    """Make ``model.train_on_batch`` data-parallel: local shard in, global-batch semantics out.  The exchange is one
-    NCCL all-reduce of the gradient arena per step, or -- SCANN_P2P_REDUCE=1, ranks of one node -- the peer-memory
-    form fused into the optimiser kernel (``P2PExchange``)."""
+    """Make ``model.train_on_batch`` data-parallel: local shard in, global-batch semantics out.  The exchange is the
+    peer-memory form fused into the optimiser kernel (``P2PExchange``; ranks of one node, the default there) or one
+    NCCL all-reduce of the gradient arena per step (SCANN_P2P_REDUCE=0, or ranks on several nodes)."""
     if world > 1:
         model.allreduce = allreduce_sum
         model.world_size = world
-        if os.environ.get("SCANN_P2P_REDUCE", "0") == "1" and torch.cuda.is_available():
+        # default on one node: the peer-memory exchange (validated against the single-GPU full-batch run on 2, 4 and 8
+        # GPUs, tools/dp_check.py); SCANN_P2P_REDUCE=0 selects the NCCL all-reduce, which is also the multi-node path
+        one_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world and world <= P2PExchange.MAX_RANKS
+        want = os.environ.get("SCANN_P2P_REDUCE", "1" if one_node else "0") == "1"
+        if want and torch.cuda.is_available():
             P2PExchange(model.engine, env_world()[0], world)
             model.allreduce = None
         # every rank draws its own Dropout masks (its shard holds different structures)

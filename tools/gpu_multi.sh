@@ -5,7 +5,7 @@ O=gpurun_out
 mkdir -p $O
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 $TR --master-port 29511 tools/dp_check.py > $O/${TAG}_dp_check_${N}gpu.log 2>&1; echo "dp_check rc=$?"; grep -E "world|DP_CHECK" $O/${TAG}_dp_check_${N}gpu.log
-timeout 900 $TR --master-port 29512 bench.py --gpus $N --no-cpu > $O/${TAG}_bench_${N}gpu_nccl.json 2> $O/${TAG}_bench_${N}gpu_nccl.err; echo "bench nccl rc=$?"
+SCANN_P2P_REDUCE=0 timeout 900 $TR --master-port 29512 bench.py --gpus $N --no-cpu > $O/${TAG}_bench_${N}gpu_nccl.json 2> $O/${TAG}_bench_${N}gpu_nccl.err; echo "bench nccl rc=$?"
 python - <<PY
 import json
 for m in ("nccl",):
