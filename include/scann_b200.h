@@ -8,14 +8,20 @@
  *
  * Conventions
  *  - every function returns 0 on success; non-zero -> scann_last_error() holds a message;
- *  - all pointers are DEVICE pointers unless stated; arguments are borrowed, outputs are
- *    caller-allocated, nothing is allocated or freed inside the library;
+ *  - all pointers are DEVICE pointers unless stated -- RAW pointers and sizes, not DLManagedTensor*: the DLPack
+ *    hand-over (torch / tf.experimental.dlpack) happens on the host side, which passes data_ptr() of the
+ *    imported tensor; arguments are borrowed, outputs are caller-allocated, nothing is allocated or freed inside
+ *    the library (one explicit exception: scann_p2p_alloc / scann_p2p_free, whose block must be exportable through
+ *    CUDA IPC);
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and re-entrant across
- *    streams; the only global state is the per-thread error string;
+ *    streams; the only global state is the per-thread error string and two per-thread launch switches
+ *    (scann_set_pdl, scann_set_la_groups4: scheduling choices, never numerics);
+ *  - there is no scann_allreduce_*: the data-parallel exchange is either torch.distributed (NCCL) on the host side
+ *    or the peer-memory form fused into the optimiser kernel (scann_p2p_*, scann_adam_p2p_step);
  *  - per-atom tensors are [R,128] fp32 row-major with R = B*M (row r = b*M + m);
  *    per-pair tensors use the tile-padded packed layout built by scann_plan_build:
- *    tile t owns rows [S t, S t + S) with S = tile_stride (128, or 64 when the local-attention kernels
- *    run two warp groups per CTA on 64-row tiles), rows with pair_c < 0 are padding;
+ *    tile t owns rows [S t, S t + S) with S = tile_stride (32 for the pipelined local-attention kernels,
+ *    64 / 128 for the round-1 kernels), rows with pair_c < 0 are padding;
  *  - weight blocks are [128,128] fp32 row-major (Keras Dense kernels, [in,out]);
  *  - `status` is a device int32 of SCANN_ERR_* bits set by kernels on malformed input.
  */
@@ -31,6 +37,7 @@ extern "C" {
 #define SCANN_ERR_TOO_MANY_NBRS 2
 #define SCANN_ERR_BAD_ATOMIC 4
 #define SCANN_ERR_BAD_NEIGHBOR 8
+#define SCANN_ERR_PIPE_TIMEOUT 16   /* a bounded mbarrier wait of a pipelined kernel gave up (status[1..4] say where) */
 
 /* ---- library ---------------------------------------------------------------------------- */
 const char* scann_last_error(void);
@@ -202,8 +209,9 @@ int scann_la_forward_tc(int grid, int tile_stride, int mma_rows, const int32_t* 
                         float* k_out, const void* attn_drop, int drop_site, void* stream);
 /* The same forward as two warp-specialised, TMA-fed pipelines (la_pipe.cu) for pair plans with tile_stride 32
  * (at most 32 valid neighbours per atom): a producer warp streams the tiles of g through a six-stage shared-memory
- * ring with cp.async.bulk.tensor (and gathers the neighbour rows x[j] with cp.async), one warp issues the
- * tcgen05.mma of each tile, three consumer groups run the row-wise epilogues and store the results with TMA.
+ * ring with cp.async.bulk.tensor (and gathers the neighbour rows x[j] with cp.async), two consumer groups of eight
+ * warps split each tile into its hi / lo operand images, issue its three tcgen05.mma product chains and run the
+ * row-wise epilogue in place, and a store warp writes the finished tiles back with TMA.
  * rows = tile_cap * 32 (row count of every per-pair tensor; per-pair tensors must be 128-byte aligned).
  * which: bit 0 = geometry kernel, bit 1 = attention kernel.  status: the engine's int32[8] status buffer (word 0:
  * flag bits, SCANN_ERR_PIPE_TIMEOUT = 16 when a bounded mbarrier wait gave up; words 1..4: where). */

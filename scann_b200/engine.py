@@ -298,7 +298,10 @@ class Engine:
         tc = self.tc_la_fwd and self.tc_la_bwd
         pref = self.tile_stride_pref
         stride = 64 if (pref in (0, 64) and tc and N <= 32) else TILE
-        if N <= 32 and tc and (pref == 32 or (pref == 0 and self.la_pipe and self.spec.g_update)):
+        # (32-row slots need the batched weight-gradient launch: the per-layer la_wgrad_tc kernels of the unbatched
+        # variant only know 64 / 128-row slots)
+        if N <= 32 and tc and self.use_chain and self.use_wgrad_batch and (
+                pref == 32 or (pref == 0 and self.la_pipe and self.spec.g_update)):
             stride = 32
         tile_rows = stride
         # (the pipelined kernels on 32-row slots keep six tiles in flight per SM: full tiles, no wave balancing)
