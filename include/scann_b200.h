@@ -189,6 +189,18 @@ typedef struct ScannChainStep {
 } ScannChainStep;
 int scann_dense_chain(const ScannChainStep* steps, int nsteps, int R, void* stream);
 
+/* Warp-specialised form of scann_dense_chain (chain2_tc.cu): same steps, same arithmetic, same reference lines
+ * (attention.py:25-40,141-161,206-214; scann_model.py:424-429), but W[kb] of every step points to the WEIGHT IMAGE of
+ * the 128x128 block instead of the block itself.  scann_weight_images writes the images of `nblocks` blocks of the
+ * parameter arena (offsets[b] = element offset of block b, row-major [in,out]) into `images`
+ * ([nblocks][2][32768] floats, 1024-byte aligned): orientation 0 is the operand of x @ W, orientation 1 of x @ W^T
+ * (what the backward pass multiplies with) -- four K-blocks of [tf32-truncated | remainder] chunk blocks in the
+ * 128-byte-swizzled K-major tcgen05 layout, streamed into shared memory with cp.async.bulk.  Call it after every change
+ * of the parameters.  R must not exceed scann_dense_chain2_max_rows() (64 rows per SM). */
+int scann_weight_images(const float* params, const int32_t* offsets, int nblocks, float* images, void* stream);
+int scann_dense_chain2(const ScannChainStep* steps, int nsteps, int R, void* stream);
+int scann_dense_chain2_max_rows(void);
+
 /* ---- local attention (the hot kernel) ---------------------------------------------------------
  * LocalAttention.call, g_update=True, v_proj=False, kq_proj=True (scann/layers/attention.py:118-216).
  * proj = [x@W1+bf | x@W3 | x@Wq+bq] ([R,384]); W2 = rows 128..255 of filter_geo/kernel.
@@ -366,6 +378,7 @@ int scann_tc_time(float* out, int mode, int nmma, int ncols, void* stream);
 int scann_debug_clocks(long long* host_out32);
 int scann_debug_clocks_dense(long long* host_out16);
 int scann_debug_clocks_chain(long long* host_out64);
+int scann_debug_clocks_chain2(long long* host_out192);
 int scann_pipe_clocks(long long* host_out96);
 #endif
 

@@ -35,6 +35,9 @@ PROTOTYPES = {
     "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_forward_tc": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_chain": (ci, [vp, ci, ci, vp]),
+    "scann_dense_chain2": (ci, [vp, ci, ci, vp]),
+    "scann_dense_chain2_max_rows": (ci, []),
+    "scann_weight_images": (ci, [vp, vp, ci, vp, vp]),
     "scann_dense_wgrad": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp]),
     "scann_layernorm_backward": (ci, [vp, vp, vp, ci, vp, vp, ci, vp, vp, vp]),
     "scann_la_nopair_forward": (ci, [vp, vp, ci, vp, vp, vp, vp, vp]),
@@ -73,6 +76,7 @@ DEV_PROTOTYPES = {
     "scann_debug_clocks": (ci, [vp]),
     "scann_debug_clocks_dense": (ci, [vp]),
     "scann_debug_clocks_chain": (ci, [vp]),
+    "scann_debug_clocks_chain2": (ci, [vp]),
     "scann_pipe_clocks": (ci, [vp]),
 }
 

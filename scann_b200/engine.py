@@ -145,6 +145,14 @@ class Engine:
         self._skip = set(filter(None, os.environ.get("SCANN_DEBUG_SKIP", "").split(",")))
         # per-atom Dense layers between two local-attention layers fused into one chained kernel
         self.use_chain = os.environ.get("SCANN_CHAIN", "1") == "1" and self.tc_dense and self.tc_la_fwd
+        # warp-specialised chained kernel (chain2_tc.cu): weight blocks as ready-made tcgen05 operand images, rebuilt
+        # after every optimiser step / set_params and streamed into shared memory with cp.async.bulk
+        self.use_chain2 = os.environ.get("SCANN_CHAIN2", "1") == "1" and self.use_chain
+        self.chain2_max_rows = lib.scann_dense_chain2_max_rows() if self.use_chain2 else 0
+        self._wimg_index = {int(o): i for i, o in enumerate(offs)}
+        self._wimg_buf = torch.empty(len(offs) * 2 * 32768 + 256, dtype=torch.float32, device=dev) if self.use_chain2 else None
+        self._wimg_base = ((self._wimg_buf.data_ptr() + 1023) // 1024 * 1024) if self.use_chain2 else 0
+        self._wimg_dirty = True
         # every weight-gradient GEMM of the step in one persistent launch at the end of the backward pass
         self.use_wgrad_batch = os.environ.get("SCANN_WGRAD_BATCH", "1") == "1" and self.use_chain and self.tc_la_bwd
 
@@ -209,6 +217,7 @@ class Engine:
 
     def set_params(self, arena: np.ndarray) -> None:
         self.params.copy_(torch.from_numpy(np.ascontiguousarray(arena, np.float32)))
+        self._wimg_dirty = True
 
     def get_params(self) -> np.ndarray:
         return self.params.cpu().numpy()
@@ -569,9 +578,36 @@ class Engine:
                                       self._stream()), "dense_forward")
         self.launches += 1
 
+    def _weight_images(self, stream: Optional[int] = None) -> None:
+        """Operand images of every 128x128 weight block (scann_weight_images) from the current parameters."""
+        if not self.use_chain2:
+            return
+        check(lib.scann_weight_images(_p(self.params), _p(self.tblocks), self.tblocks.numel(), self._wimg_base,
+                                      self._stream() if stream is None else stream), "weight_images")
+        self.launches += 1
+        self._wimg_dirty = False
+
+    def _wimg_ptr(self, p: int) -> int:
+        """Weight image of the block a ``w()`` pointer (orientation 0: x @ W) or a ``wT()`` pointer (orientation 1:
+        x @ W^T) addresses."""
+        nbytes = 4 * self.layout.total
+        for base, orient in ((self.params.data_ptr(), 0), (self.paramsT.data_ptr(), 1)):
+            if base <= p < base + nbytes:
+                return self._wimg_base + (self._wimg_index[(p - base) // 4] * 2 + orient) * 131072
+        raise KeyError("not a weight block of the parameter arena")
+
     def _chain(self, steps, R):
-        """One scann_dense_chain launch: ``steps`` is a list of ChainStep (see include/scann_b200.h)."""
+        """One scann_dense_chain launch: ``steps`` is a list of ChainStep (see include/scann_b200.h).  Up to 64 rows
+        per SM the warp-specialised form runs (scann_dense_chain2: weight pointers replaced by their operand images)."""
         if "chain" in self._skip:
+            return
+        if self.use_chain2 and R <= self.chain2_max_rows:
+            for s in steps:
+                for kb in range(s.kblk):
+                    s.W[kb] = self._wimg_ptr(s.W[kb])
+            arr = (ChainStep * len(steps))(*steps)
+            check(lib.scann_dense_chain2(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, self._stream()), "dense_chain2")
+            self.launches += 1
             return
         arr = (ChainStep * len(steps))(*steps)
         check(lib.scann_dense_chain(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, self._stream()), "dense_chain")
@@ -591,6 +627,9 @@ class Engine:
         L, R = sp.n_attention, b.R
         xs, gs = ws["x"], ws["g"]
         E = sp.embedding_dim
+        self._pdl(False)
+        if self._wimg_dirty:
+            self._weight_images()
         if training and not sp.g_update and not (self.use_chain and self.tc_la_bwd and self.use_wgrad_batch):
             raise NotImplementedError("training of g_update=False models needs the tensor-core engine "
                                       "(SCANN_ENGINE=tc, SCANN_CHAIN=1)")
@@ -1291,6 +1330,8 @@ class Engine:
                                           _p(self.grad_out) if want_grads else 0, int(apply), self._stream()),
                   "adam_p2p_step")
             self.launches += 1
+            if apply:
+                self._weight_images()
             return
         if allreduce is not None and exchange:
             # (not in the local warm-up pass of a new shape class, whose result is discarded: ranks that meet new
@@ -1300,6 +1341,8 @@ class Engine:
                                   _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
                                   int(apply), self._stream()), "adam_step")
         self.launches += 1
+        if apply:
+            self._weight_images()
 
     def predict_step(self, b: Batch, replan: bool = False):
         """Inference forward (plan + graph of kernels) -> (y[B], ga[B*M]) device tensors."""
