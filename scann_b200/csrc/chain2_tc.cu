@@ -134,8 +134,8 @@ struct C2Cfg {
     static constexpr uint32_t OFF_X = C2_NSLOT * C2_SLOT_BYTES;      // after the weight ring
     static constexpr uint32_t OFF_S = OFF_X + NXBUF * 2u * IMG;
     static constexpr uint32_t OFF_BAR = OFF_S + IMG;                 // w_full[4] w_empty[4] x_full[2] x_empty[2] acc_full[2] acc_empty[2]
-    static constexpr uint32_t OFF_MISC = OFF_BAR + 16u * 8u;         // tmem slot, dead flag
-    static constexpr uint32_t SMEM = OFF_MISC + 16u + 1024u;         // + alignment slack
+    static constexpr uint32_t OFF_MISC = OFF_BAR + 16u * 8u;         // tmem slot, dead flag, copy of the kernel arguments
+    static constexpr uint32_t SMEM = OFF_MISC + 16u + (uint32_t)sizeof(C2Args) + 1024u;   // + alignment slack
     static constexpr int RPW = TR / C2_EPI_WARPS;                    // rows per epilogue warp
     static constexpr int STEPS = RPW / 2;                            // 2-row passes per epilogue warp
     static constexpr int XIT = TR * 32 / C2_EPI_THREADS;             // 16-byte chunks per thread of one activation tile
@@ -158,6 +158,10 @@ __device__ __forceinline__ float4 c2_lo4(float4 v) {
     return make_float4(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u), v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u),
                        v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u), v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
 }
+// drop_mult (common.cuh) on a control block that already sits in registers
+__device__ __forceinline__ float c2_drop(const ScannDropCtl& c, uint32_t site, uint32_t idx) {
+    return drop_hash(c.seed, site, idx) >= c.threshold ? __uint_as_float(c.scale_bits) : 0.0f;
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -169,7 +173,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 }
 
 template <int TR>
-__global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __grid_constant__ C2Args a) {
+__global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __grid_constant__ C2Args ga) {
     typedef C2Cfg<TR> K;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -182,6 +186,15 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
     volatile int* dead = reinterpret_cast<volatile int*>(smem + K::OFF_MISC + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r0 = blockIdx.x * TR;
+    // The step / block tables are read from a shared-memory copy: a step's fields indexed by the runtime step number
+    // out of the constant bank cost a constant-cache miss (several hundred cycles) at every first touch, in the
+    // middle of the row-wise epilogues
+    const C2Args& a = *reinterpret_cast<const C2Args*>(smem + K::OFF_MISC + 16);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&ga);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem + K::OFF_MISC + 16);
+        for (int i = tid; i < (int)(sizeof(C2Args) / 4); i += C2_THREADS) dst[i] = src[i];
+    }
     if (warp == C2_EPI_WARPS) tmem_alloc(tmem_slot, K::TCOLS);
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 3); }
@@ -298,6 +311,11 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                 gam[it] = st.gamma ? ldg4(st.gamma + c0) : bias[it];
                 bet[it] = st.beta ? ldg4(st.beta + c0) : bias[it];
             }
+            // dropout control block (device memory) and the neighbour count of the first row: fetched now, used after the MMA
+            ScannDropCtl dctl = {0u, 0u, 0u, 0u};
+            if (st.drop) dctl = *st.drop;
+            int cnt0 = 1;
+            if (st.cnt && r0 + warp * K::RPW + rsub < a.R) cnt0 = st.cnt[r0 + warp * K::RPW + rsub];
             float4 rv0[2], pv0[2];
             {
                 const int r = r0 + warp * K::RPW + rsub;
@@ -376,10 +394,10 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                         if (st.resid && ok) rv = ld4(st.resid + (size_t)r * st.ldres + c0);
                     }
                     float d0 = 1.f, d1 = 1.f, d2 = 1.f, d3 = 1.f;
-                    if (st.drop && mode != 4) {
+                    if (dctl.enabled && mode != 4) {
                         const uint32_t idx = (uint32_t)r * SCANN_D + c0;
-                        d0 = drop_mult(st.drop, st.drop_site, idx); d1 = drop_mult(st.drop, st.drop_site, idx + 1);
-                        d2 = drop_mult(st.drop, st.drop_site, idx + 2); d3 = drop_mult(st.drop, st.drop_site, idx + 3);
+                        d0 = c2_drop(dctl, st.drop_site, idx); d1 = c2_drop(dctl, st.drop_site, idx + 1);
+                        d2 = c2_drop(dctl, st.drop_site, idx + 2); d3 = c2_drop(dctl, st.drop_site, idx + 3);
                     }
                     v[it][0] = (acc.x + bias[it].x) * d0 + rv.x; v[it][1] = (acc.y + bias[it].y) * d1 + rv.y;
                     v[it][2] = (acc.z + bias[it].z) * d2 + rv.z; v[it][3] = (acc.w + bias[it].w) * d3 + rv.w;
@@ -483,13 +501,13 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                     for (int it = 0; it < 2; ++it)
                         st4(st.C + (size_t)r * st.ldc + (l16 + 16 * it) * 4, make_float4(v[it][0], v[it][1], v[it][2], v[it][3]));
                 }
-                if (mode == 4 && st.drop) {
+                if (mode == 4 && dctl.enabled) {
                     // gradient through the dropout that follows the Dense of the next (transposed) step
 #pragma unroll
                     for (int it = 0; it < 2; ++it) {
                         const uint32_t idx = (uint32_t)r * SCANN_D + (l16 + 16 * it) * 4;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) v[it][k] *= drop_mult(st.drop, st.drop_site, idx + k);
+                        for (int k = 0; k < 4; ++k) v[it][k] *= c2_drop(dctl, st.drop_site, idx + k);
                     }
                 }
                 if (ok && st.C2) {
@@ -509,7 +527,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                 if (tid == 0) C2CLK(2, si * 6 + 3);
                 if (st.cnt) {
                     // atoms without a valid neighbour: context = q, out = LayerNorm(q)   (attention.py:206-214)
-                    const bool nop = ok && st.cnt[r] == 0;
+                    const bool nop = ok && (step == 0 ? cnt0 : st.cnt[r]) == 0;
                     if (__any_sync(0xffffffffu, nop)) {
                         float m1 = 0.f, m2 = 0.f;
 #pragma unroll

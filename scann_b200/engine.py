@@ -619,23 +619,12 @@ class Engine:
         self.launches += 1
 
     # ------------------------------------------------------------------ forward
-    def forward(self, b: Batch, training: bool = False, attn_out: Optional[list] = None):
-        """Runs the whole graph; returns (y[B], ga[B*M]) device tensors (views of the workspace)."""
-        sp, st = self.spec, self._stream()
-        self._flush_host(b)
-        ws = self._workspace(b, training)
-        L, R = sp.n_attention, b.R
-        xs, gs = ws["x"], ws["g"]
-        E = sp.embedding_dim
-        self._pdl(False)
-        if self._wimg_dirty:
-            self._weight_images()
-        if training and not sp.g_update and not (self.use_chain and self.tc_la_bwd and self.use_wgrad_batch):
-            raise NotImplementedError("training of g_update=False models needs the tensor-core engine "
-                                      "(SCANN_ENGINE=tc, SCANN_CHAIN=1)")
+    def _embed_forward(self, b: Batch, ws: dict, training: bool, st: int) -> None:
+        """Input embedding + dense_embed (+ ring features, Dropout 0.1) -> x_0  (scann_model.py:361-374)."""
+        sp = self.spec
+        R, E = b.R, sp.embedding_dim
         ring = sp.use_ring
         cg = sp.feature == "cgcnn"
-        self._pdl(False)
         if cg:
             if "emb_rows" not in ws:
                 ws["emb_rows"] = torch.empty(R, E, dtype=torch.float32, device=self.device)
@@ -647,19 +636,65 @@ class Engine:
                                       0 if cg else self.w("embed_atom/embeddings"), self.w("extra_embed/kernel") if ring else 0,
                                       self.w("extra_embed/bias") if ring else 0,
                                       self.w("dense_embed/kernel"), self.w("dense_embed/bias"),
-                                      _p(ws["t0"]) if training else 0, _p(xs[0]), _p(self.status),
+                                      _p(ws["t0"]) if training else 0, _p(ws["x"][0]), _p(self.status),
                                       _p(self.adam_scalars, 8) if training else 0, _p(ws["emb_rows"]) if cg else 0, st),
               "embed_forward")
         self.launches += 1
-        self._pdl(True)
+
+    def forward(self, b: Batch, training: bool = False, attn_out: Optional[list] = None, replan: bool = False,
+                side_work=None):
+        """Runs the whole graph; returns (y[B], ga[B*M]) device tensors (views of the workspace).
+
+        Two branches meet in front of the first per-atom projection: the pair plan (``replan``) and the geometry
+        initialisation need the neighbour lists only, the weight operand images and the embedding need the atoms
+        only.  With a side stream the second branch (and ``side_work()``: whatever else the caller wants enqueued
+        there, e.g. the preparation of the backward pass) runs beside the first."""
+        sp, st = self.spec, self._stream()
+        self._flush_host(b)
+        ws = self._workspace(b, training)
+        L, R = sp.n_attention, b.R
+        xs, gs = ws["x"], ws["g"]
+        if training and not sp.g_update and not (self.use_chain and self.tc_la_bwd and self.use_wgrad_batch):
+            raise NotImplementedError("training of g_update=False models needs the tensor-core engine "
+                                      "(SCANN_ENGINE=tc, SCANN_CHAIN=1)")
+        self._pdl(False)
+        main = torch.cuda.current_stream(self.device)
+        fork = self.use_side_stream and (replan or side_work is not None)
+        embed_ev = None
+        if fork:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side_stream.wait_event(ev)
+            with torch.cuda.stream(self.side_stream):
+                sst = self.side_stream.cuda_stream
+                if self._wimg_dirty or training:
+                    self._weight_images(sst)
+                self._embed_forward(b, ws, training, sst)
+                embed_ev = torch.cuda.Event()
+                embed_ev.record(self.side_stream)
+                if side_work is not None:
+                    side_work()
+            if replan:
+                self._plan(b)
+        else:
+            if replan:
+                self._plan(b)
+            if self._wimg_dirty or training:
+                self._weight_images()
+            self._embed_forward(b, ws, training, st)
+            if side_work is not None:
+                side_work()
         if sp.g_update and "geom_init" not in self._skip:
             check(lib.scann_geom_init_forward(_p(b.ntiles), self.la_grid * self.gi_fwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
                                               _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
                                               self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
                                               self.w("neighbor_w/bias"), _p(gs[0]), st), "geom_init_forward")
             self.launches += 1
+        if embed_ev is not None:
+            main.wait_event(embed_ev)         # x_0 and the weight images are ready
         if self.use_chain and (not training or self.tc_la_bwd):
-            return self._forward_chained(b, ws, training, attn_out)
+            return self._forward_chained(b, ws, training, attn_out)    # (first launch without PDL, then switched on)
+        self._pdl(not fork)
         for l in range(L):
             la = layer_name("local_attention", l)
             rn = layer_name("residual_norm", l)
@@ -793,6 +828,7 @@ class Engine:
             return steps
 
         self._chain(proj_steps(0, xs[0]), R)
+        self._pdl(True)
         for l in range(L):
             la = layer_name("local_attention", l)
             rn = layer_name("residual_norm", l)
@@ -1299,29 +1335,27 @@ class Engine:
             g.replay()
         if apply:
             self.step_count += 1
+            self._wimg_dirty = True      # the parameters moved: the next forward rebuilds the weight operand images
 
     def _train_body(self, b: Batch, allreduce, apply: bool, want_grads: bool, replan: bool, exchange: bool = True) -> None:
         p2p = self.p2p if exchange else None
-        if replan:
-            self._plan(b)
         if self.p2p is not None:
             # no peer still reads the arena that is zeroed next (scann_b200/csrc/p2p.cu); also in the local warm pass
             check(lib.scann_p2p_begin_step(_p(self.p2p.block), _p(self.p2p.sums), self._stream()), "p2p_begin_step")
             self.launches += 1
         self.grads.zero_()
         ws = self._workspace(b, True)
-        if self.use_side_stream:
-            # overlap with the forward: weight transposes and the zero-fill of the scatter targets
-            main = torch.cuda.current_stream(self.device)
-            ev = torch.cuda.Event()
-            ev.record(main)
-            self.side_stream.wait_event(ev)
-            with torch.cuda.stream(self.side_stream):
+
+        def prep():
+            # overlaps with the forward (side stream, behind the embedding): weight transposes and the zero-fill of
+            # the scatter targets of the backward pass
+            if self.use_side_stream:
                 self._backward_prep(ws, self.side_stream.cuda_stream)
                 ws["scat_all"].zero_()
                 self._prep_event = torch.cuda.Event()
                 self._prep_event.record(self.side_stream)
-        self.forward(b, training=True)
+
+        self.forward(b, training=True, replan=replan, side_work=prep)
         self.backward(b, b.target)
         n = self.layout.total
         if p2p is not None:
@@ -1330,8 +1364,6 @@ class Engine:
                                           _p(self.grad_out) if want_grads else 0, int(apply), self._stream()),
                   "adam_p2p_step")
             self.launches += 1
-            if apply:
-                self._weight_images()
             return
         if allreduce is not None and exchange:
             # (not in the local warm-up pass of a new shape class, whose result is discarded: ranks that meet new
@@ -1341,29 +1373,23 @@ class Engine:
                                   _p(self.grads, n), _p(self.adam_scalars), _p(self.grad_out) if want_grads else 0,
                                   int(apply), self._stream()), "adam_step")
         self.launches += 1
-        if apply:
-            self._weight_images()
 
     def predict_step(self, b: Batch, replan: bool = False):
         """Inference forward (plan + graph of kernels) -> (y[B], ga[B*M]) device tensors."""
         key = ("infer", replan)
         self._flush_host(b)
+        if self._wimg_dirty:
+            self._weight_images()        # outside the captured graph: only needed after the parameters changed
         if not self.use_graphs or self.prof is not None:
-            if replan:
-                self._plan(b)
-            return self.forward(b, training=False)
+            return self.forward(b, training=False, replan=replan)
         g = b.graphs.get(key)
         if g is None:
-            if replan:
-                self._plan(b)
-            self.forward(b, training=False)
+            self.forward(b, training=False, replan=replan)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             n0 = self.launches
             with torch.cuda.graph(g):
-                if replan:
-                    self._plan(b)
-                self.forward(b, training=False)
+                self.forward(b, training=False, replan=replan)
             g.n_launches = self.launches - n0
             b.graphs[key] = g
         else:
