@@ -76,6 +76,12 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(S0 + 2 * PT_IMG + kb * PT_CB, &a.tm_g, kb * 32, t * PT, &c.full[s]);
                 bulk_load(c.idx + s * 64, a.pair_c + (size_t)t * PT, 128u, &c.full[s]);
                 bulk_load(c.idx + s * 64 + 32, a.pair_j + (size_t)t * PT, 128u, &c.full[s]);
+                // the ring is only PB_NS tiles deep: pull the tile behind it into L2 now
+                const int tp = t + PB_NS * (int)gridDim.x;
+                if (tp < nt) {
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) { tma_prefetch_2d(&a.tm_k, kb * 32, tp * PT); tma_prefetch_2d(&a.tm_g, kb * 32, tp * PT); }
+                }
             }
             const uint32_t X = smem_u32(S0 + 3 * PT_IMG);
 #pragma unroll 8
@@ -98,6 +104,21 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
         const int hl = lane >> 2;                                // head of this lane's columns
         float4 dbk = make_float4(0.f, 0.f, 0.f, 0.f);
         int i = grp;
+        // The query and d_ctx rows of a tile's centre atoms come from global memory (L2): they are fetched one tile ahead
+        // -- the indices at the start of the previous tile, the rows behind its MMA issue, into the registers that tile
+        // no longer needs -- so that phase A does not start with an exposed L2 round trip
+        float4 qv[4], dc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int t0 = blockIdx.x + grp * gridDim.x;
+            const int pn = t0 < nt ? a.pair_c[(size_t)t0 * PT + wgl + PF_GW * k] : -1;
+            qv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dc[k] = qv[k];
+            if (pn >= 0) {
+                qv[k] = ld4(a.proj + (size_t)pn * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+                dc[k] = ld4(a.d_ctx + (size_t)pn * SCANN_D + lane * 4);
+            }
+        }
         for (int t = blockIdx.x + grp * gridDim.x; t < nt; t += PF_NG * gridDim.x, i += PF_NG) {
             const int s = i % PB_NS;
             const uint32_t ph = (uint32_t)(i / PB_NS) & 1u;
@@ -111,17 +132,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             float* Ds = Es + PT * 8;                            // [PT][8] dp -> de
             pipe_wait(&c.full[s], ph, c.dead, a.status, 23, t, s);
             int pc[4];
-            float4 qv[4], dc[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                pc[k] = sidx[wgl + PF_GW * k];
-                qv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                dc[k] = qv[k];
-                if (pc[k] >= 0) {
-                    qv[k] = ld4(a.proj + (size_t)pc[k] * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
-                    dc[k] = ld4(a.d_ctx + (size_t)pc[k] * SCANN_D + lane * 4);
-                }
-            }
+            for (int k = 0; k < 4; ++k) pc[k] = sidx[wgl + PF_GW * k];
             // ---- phase A: e = 0.25 <q_h,k_h>, dp = <dctx_h,k_h> per (row, head)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -217,6 +229,23 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             int jj[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) jj[k] = pc[k] >= 0 ? sidx[32 + wgl + PF_GW * k] : 0;
+            // the next tile's query / d_ctx rows (its centre indices straight from global memory): in flight behind the
+            // MMAs and phase D
+            {
+                const int tn = t + PF_NG * (int)gridDim.x;
+                int pn[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pn[k] = tn < nt ? a.pair_c[(size_t)tn * PT + wgl + PF_GW * k] : -1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    qv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dc[k] = qv[k];
+                    if (pn[k] >= 0) {
+                        qv[k] = ld4(a.proj + (size_t)pn[k] * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+                        dc[k] = ld4(a.d_ctx + (size_t)pn[k] * SCANN_D + lane * 4);
+                    }
+                }
+            }
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 24, t, s);
             tc_fence_after();
             pf_acc_to_image(t_acc, Lo, nullptr, q, half, lane);
@@ -287,6 +316,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
                 for (int kb = 0; kb < 4; ++kb) tma_load_2d(S0 + 3 * PT_IMG + kb * PT_CB, &a.tm_dgt, kb * 32, t * PT, &c.full[s]);
                 bulk_load(c.idx + s * 64, a.pair_c + (size_t)t * PT, 128u, &c.full[s]);
                 bulk_load(c.idx + s * 64 + 32, a.pair_j + (size_t)t * PT, 128u, &c.full[s]);
+                const int tp = t + PB_NS * (int)gridDim.x;            // L2 prefetch of the tile behind the ring
+                if (tp < nt) {
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        tma_prefetch_2d(&a.tm_pre, kb * 32, tp * PT); tma_prefetch_2d(&a.tm_g, kb * 32, tp * PT);
+                        tma_prefetch_2d(&a.tm_dgt, kb * 32, tp * PT);
+                    }
+                }
             }
         }
         __syncwarp();

@@ -53,6 +53,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const v
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
                  : "memory");
 }
+// L2 prefetch of a box (no shared-memory destination, no completion tracking): issued a few tiles ahead of the ring it
+// turns the HBM latency of the later tensor load into an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"((uint64_t)tm), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk groups of this thread have finished READING shared memory (the source may be overwritten)
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
