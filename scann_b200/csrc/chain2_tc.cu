@@ -612,7 +612,7 @@ static int chain2_launch(const C2Args& a, void* stream) {
     return scann_check_launch("scann_dense_chain2");
 }
 
-// Row capacity of the warp-specialised form: one CTA per SM with 64-row tiles at most.
+// Rows that one wave of the warp-specialised form covers (one CTA per SM, 64-row tiles); more rows run in several waves.
 extern "C" int scann_dense_chain2_max_rows(void) {
     static int sms = 0;
     if (sms == 0) sms = scann_device_sm_count();
@@ -620,11 +620,10 @@ extern "C" int scann_dense_chain2_max_rows(void) {
 }
 
 // Same contract as scann_dense_chain, except that W[kb] of every step points to the weight IMAGE of the block
-// (scann_weight_images; orientation 0 for x @ W, 1 for x @ W^T).  R must not exceed scann_dense_chain2_max_rows().
+// (scann_weight_images; orientation 0 for x @ W, 1 for x @ W^T).
 extern "C" int scann_dense_chain2(const void* steps_host, int nsteps, int R, void* stream) {
     if (nsteps < 1 || nsteps > C2_MAX_STEPS) { scann_set_error("dense_chain2: nsteps must be in 1..%d", C2_MAX_STEPS); return 1; }
     if (R <= 0) return 0;
-    if (R > scann_dense_chain2_max_rows()) { scann_set_error("dense_chain2: %d rows exceed the capacity %d", R, scann_dense_chain2_max_rows()); return 1; }
     static_assert(sizeof(C2Args) <= 4096, "kernel parameter space");
     C2Args a;
     memset(&a, 0, sizeof(a));

@@ -107,12 +107,15 @@ __device__ __forceinline__ void pf_issue_chain(int chain, uint32_t t_wraw, uint3
     }
 
 // Store warp (warp PF_CW + 1): when a consumer group has finished a tile in place (`done` = the ready[] barrier of the
-// stage), one lane issues the TMA stores of its images, and hands the stage back to the producer once the previous
-// tile's stores have finished reading shared memory -- the consumers never wait for the TMA unit.
+// stage), one lane issues the TMA stores of its images and hands the stage back to the producer as soon as THOSE stores
+// have finished reading shared memory (a few hundred cycles) -- the consumers never wait for the TMA unit.  (Round 2,
+// first form: the stage went back one tile later, behind the next tile's store issue; with the backward ring only
+// three stages deep that left the producer nothing to prefetch into, and 18 % of the consumers' samples sat in the
+// wait for a landed tile, profiles/r02_summary.md.)
 #define PF_STORE_LOOP(NSTAGES, STAGE_BYTES, CODE, STORE_STMTS)                                                                                 \
     {                                                                                                                    \
         if (lane == 0) {                                                                                                 \
-            int i = 0, prev = -1;                                                                                        \
+            int i = 0;                                                                                                   \
             for (int t = blockIdx.x; t < nt; t += gridDim.x, ++i) {                                                      \
                 const int s = i % NSTAGES;                                                                               \
                 const uint32_t ph = (uint32_t)(i / NSTAGES) & 1u;                                                        \
@@ -122,15 +125,8 @@ __device__ __forceinline__ void pf_issue_chain(int chain, uint32_t t_wraw, uint3
                 (void)Bm;                                                                                                \
                 STORE_STMTS                                                                                              \
                 tma_commit();                                                                                            \
-                if (prev >= 0) {                                                                                         \
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");                                       \
-                    mbar_arrive(&c.empty[prev]);                                                                         \
-                }                                                                                                        \
-                prev = s;                                                                                                \
-            }                                                                                                            \
-            if (prev >= 0) {                                                                                             \
                 tma_wait_read0();                                                                                        \
-                mbar_arrive(&c.empty[prev]);                                                                             \
+                mbar_arrive(&c.empty[s]);                                                                                \
             }                                                                                                            \
         }                                                                                                                \
         __syncwarp();                                                                                                    \

@@ -148,7 +148,9 @@ class Engine:
         # warp-specialised chained kernel (chain2_tc.cu): weight blocks as ready-made tcgen05 operand images, rebuilt
         # after every optimiser step / set_params and streamed into shared memory with cp.async.bulk
         self.use_chain2 = os.environ.get("SCANN_CHAIN2", "1") == "1" and self.use_chain
-        self.chain2_max_rows = lib.scann_dense_chain2_max_rows() if self.use_chain2 else 0
+        # up to this many rows (default: one wave of 64-row tiles) the warp-specialised form runs, above it the round-1 kernel
+        self.chain2_max_rows = (int(os.environ.get("SCANN_CHAIN2_MAX_ROWS", "0")) or lib.scann_dense_chain2_max_rows()) \
+            if self.use_chain2 else 0
         self._wimg_index = {int(o): i for i, o in enumerate(offs)}
         self._wimg_buf = torch.empty(len(offs) * 2 * 32768 + 256, dtype=torch.float32, device=dev) if self.use_chain2 else None
         self._wimg_base = ((self._wimg_buf.data_ptr() + 1023) // 1024 * 1024) if self.use_chain2 else 0

@@ -9,7 +9,10 @@ from scann_b200.configs import get_config
 from scann_b200.model import create_model
 from scann_b200.synth import make_batch
 wl, B = sys.argv[1], int(sys.argv[2])
-m = create_model(get_config(wl)); eng = m.engine
+cfg = get_config(wl)
+if wl == "ptgp":      # model_ptgp.yaml lacks these two keys (KeyError in the reference as shipped)
+    cfg["model"].update(g_update=False, gaussian_d=4.0)
+m = create_model(cfg); eng = m.engine
 inp, tgt = make_batch(wl, 0, B=B) if B else make_batch(wl, 0)
 b = eng.load_batch(inp, plan=False)
 t = torch.from_numpy(tgt).cuda()
