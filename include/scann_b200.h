@@ -380,6 +380,7 @@ int scann_debug_clocks_dense(long long* host_out16);
 int scann_debug_clocks_chain(long long* host_out64);
 int scann_debug_clocks_chain2(long long* host_out192);
 int scann_pipe_clocks(long long* host_out96);
+int scann_pipe_clocks_bwd(long long* host_out96);
 #endif
 
 #ifdef __cplusplus

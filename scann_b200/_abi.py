@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libscann_b200.so")
+# (development: SCANN_B200_LIB selects another build of the same library, e.g. an A/B variant)
+LIB_PATH = os.environ.get("SCANN_B200_LIB") or os.path.join(_HERE, "libscann_b200.so")
 
 vp = C.c_void_p
 ci = C.c_int
@@ -78,6 +79,7 @@ DEV_PROTOTYPES = {
     "scann_debug_clocks_chain": (ci, [vp]),
     "scann_debug_clocks_chain2": (ci, [vp]),
     "scann_pipe_clocks": (ci, [vp]),
+    "scann_pipe_clocks_bwd": (ci, [vp]),
 }
 
 

@@ -22,6 +22,19 @@ typedef PipeFrame<PB_NS, 4> BwdFrame;
 #define PB_STAGE (BwdFrame::STAGE)
 #define PB_SMEM (BwdFrame::SMEM)
 
+// phase timestamps of CTA 0, consumer group 0 (development builds: -DSCANN_DEV_PROBES): [kernel][tile ordinal][phase]
+#ifdef SCANN_DEV_PROBES
+__device__ long long g_pipe_clk_bwd[2][4][12];
+#define BCLK(k, ph) do { if (blockIdx.x == 0 && tid == 0 && (i / PF_NG) < 4) g_pipe_clk_bwd[k][i / PF_NG][ph] = clock64(); } while (0)
+extern "C" int scann_pipe_clocks_bwd(long long* host_out96) {
+    cudaError_t e = cudaMemcpyFromSymbol(host_out96, g_pipe_clk_bwd, sizeof(long long) * 96);
+    if (e != cudaSuccess) { scann_set_error("pipe_clocks_bwd: %s", cudaGetErrorString(e)); return 1; }
+    return 0;
+}
+#else
+#define BCLK(k, ph) do { } while (0)
+#endif
+
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
 
 // =============================================================================================
@@ -130,7 +143,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             const int32_t* sidx = c.idx + s * 64;
             float* Es = c.es + s * 2 * PT * 8;                  // [PT][8] e -> p
             float* Ds = Es + PT * 8;                            // [PT][8] dp -> de
+            BCLK(0, 0);
             pipe_wait(&c.full[s], ph, c.dead, a.status, 23, t, s);
+            BCLK(0, 1);
             int pc[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) pc[k] = sidx[wgl + PF_GW * k];
@@ -145,64 +160,83 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
                 if ((lane & 3) == 0) { Es[r * 8 + hl] = e; Ds[r * 8 + hl] = d; }
             }
             pf_group_sync(grp);
-            // ---- phase B (warp per atom): p, de ; dq = d_ctx + 0.25 sum_n de k
+            BCLK(0, 2);
+            // ---- phase B1 (warp per HEAD, lane per row): softmax over an atom's rows and its backward.  The rows of an
+            // atom are a contiguous run of lanes, so max / sums are segmented shuffle reductions: every warp is busy and
+            // the cost does not depend on the neighbour count (first form: one warp per atom looped over its rows --
+            // three or four of the eight warps worked, 24 % of the kernel's samples sat in the barrier behind them)
+            const int myc = sidx[lane];
+            const int prevc = __shfl_up_sync(0xffffffffu, myc, 1);
+            const uint32_t vmask = __ballot_sync(0xffffffffu, myc >= 0);
+            const uint32_t hmask = __ballot_sync(0xffffffffu, myc >= 0 && (lane == 0 || myc != prevc));
+            const int nvalid = __popc(vmask), natoms = __popc(hmask);
             {
-                const int myc = sidx[lane];
-                const int prevc = __shfl_up_sync(0xffffffffu, myc, 1);
-                const uint32_t vmask = __ballot_sync(0xffffffffu, myc >= 0);
-                const uint32_t hmask = __ballot_sync(0xffffffffu, myc >= 0 && (lane == 0 || myc != prevc));
-                const int nvalid = __popc(vmask), natoms = __popc(hmask);
-                uint32_t m = hmask;
-                for (int k = 0; k < wgl; ++k) m &= m - 1;
-                for (int k = wgl; k < natoms; k += PF_GW) {
-                    const int r0 = __ffs(m) - 1;
-                    uint32_t mn = m;
-                    mn &= mn - 1;
-                    const int n = (mn ? __ffs(mn) - 1 : nvalid) - r0;
-                    const int atom = sidx[r0];
-                    {
-                        const int h = lane & 7, rs = lane >> 3;
-                        float mx = -INFINITY;
-                        for (int r = rs; r < n; r += 4) mx = fmaxf(mx, Es[(r0 + r) * 8 + h]);
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-                        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-                        float sm = 0.f, dot = 0.f;
-                        for (int r = rs; r < n; r += 4) {
-                            const float p = __expf(Es[(r0 + r) * 8 + h] - mx);
-                            sm += p;
-                            // gradient w.r.t. the softmax output = (gradient w.r.t. the dropped probabilities) * mask
-                            const float dm = drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
-                            Ds[(r0 + r) * 8 + h] *= dm;
-                            dot = fmaf(p, Ds[(r0 + r) * 8 + h], dot);
-                        }
-                        sm += __shfl_xor_sync(0xffffffffu, sm, 8);   sm += __shfl_xor_sync(0xffffffffu, sm, 16);
-                        dot += __shfl_xor_sync(0xffffffffu, dot, 8); dot += __shfl_xor_sync(0xffffffffu, dot, 16);
-                        const float is = 1.0f / sm;
-                        dot *= is;
-                        for (int r = rs; r < n; r += 4) {
-                            const float p = __expf(Es[(r0 + r) * 8 + h] - mx) * is;
-                            const float dp = Ds[(r0 + r) * 8 + h];
-                            // d_k uses the dropped probabilities, the softmax backward the undropped ones
-                            Es[(r0 + r) * 8 + h] = p * drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + r) * 8u + h);
-                            Ds[(r0 + r) * 8 + h] = p * (dp - dot);
-                        }
-                    }
-                    __syncwarp();
-                    {
-                        float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                        for (int r = 0; r < n; ++r) {
-                            const float de = Ds[(r0 + r) * 8 + hl];
-                            const float4 kv = lds4(K + pt_off4(r0 + r, lane));
-                            c0 = fmaf(de, kv.x, c0); c1 = fmaf(de, kv.y, c1); c2 = fmaf(de, kv.z, c2); c3 = fmaf(de, kv.w, c3);
-                        }
-                        const float4 dca = ld4(a.d_ctx + (size_t)atom * SCANN_D + lane * 4);
-                        st4(a.dq + (size_t)atom * SCANN_D + lane * 4,
-                            make_float4(dca.x + 0.25f * c0, dca.y + 0.25f * c1, dca.z + 0.25f * c2, dca.w + 0.25f * c3));
-                    }
-                    for (int k2 = 0; k2 < PF_GW && m; ++k2) m &= m - 1;
+                const bool valid = myc >= 0;
+                const uint32_t below = hmask & ((2u << lane) - 1u);              // run starts at or below this lane
+                const uint32_t above = lane < 31 ? hmask & ~((2u << lane) - 1u) : 0u;
+                const int lo = valid ? 31 - __clz(below) : lane;                 // first / last lane of this lane's run
+                const int hi = valid ? (above ? __ffs(above) - 2 : nvalid - 1) : lane;
+                const int h = wgl;
+                const float e = valid ? Es[lane * 8 + h] : -INFINITY;
+                float mx = e;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_down_sync(0xffffffffu, mx, o);
+                    if (lane + o <= hi) mx = fmaxf(mx, v);
+                }
+                mx = __shfl_sync(0xffffffffu, mx, lo);
+                const float p = valid ? __expf(e - mx) : 0.f;
+                // gradient w.r.t. the softmax output = (gradient w.r.t. the dropped probabilities) * mask
+                const float dm = valid ? drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + lane) * 8u + h) : 0.f;
+                const float dp = valid ? Ds[lane * 8 + h] * dm : 0.f;
+                float sm = p, dot = p * dp;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v1 = __shfl_down_sync(0xffffffffu, sm, o), v2 = __shfl_down_sync(0xffffffffu, dot, o);
+                    if (lane + o <= hi) { sm += v1; dot += v2; }
+                }
+                sm = __shfl_sync(0xffffffffu, sm, lo);
+                dot = __shfl_sync(0xffffffffu, dot, lo);
+                if (valid) {
+                    const float is = 1.0f / sm;
+                    const float pn = p * is;
+                    // d_k uses the dropped probabilities, the softmax backward the undropped ones
+                    Es[lane * 8 + h] = pn * dm;
+                    Ds[lane * 8 + h] = pn * (dp - dot * is);
                 }
             }
             pf_group_sync(grp);
+            BCLK(0, 3);
+            // ---- phase B2: dq = d_ctx + 0.25 sum_n de k, by the warp that owns the atom's FIRST row (rows wgl + 8 k): its
+            // d_ctx row already sits in that warp's registers (dc[k]), and the atoms spread over all eight warps.  The row
+            // loop runs four rows per trip so that the shared-memory loads of a trip are in flight together.
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r0 = wgl + PF_GW * k;
+                if (!((hmask >> r0) & 1u)) continue;                      // (warp-uniform)
+                const uint32_t nxt = r0 < 31 ? hmask & ~((2u << r0) - 1u) : 0u;
+                const int n = (nxt ? __ffs(nxt) - 1 : nvalid) - r0;
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                for (int r = 0; r < n; r += 4) {
+                    float de[4];
+                    float4 kv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int rr = r0 + (r + u < n ? r + u : 0);
+                        de[u] = r + u < n ? Ds[rr * 8 + hl] : 0.f;
+                        kv[u] = lds4(K + pt_off4(rr, lane));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        c0 = fmaf(de[u], kv[u].x, c0); c1 = fmaf(de[u], kv[u].y, c1);
+                        c2 = fmaf(de[u], kv[u].z, c2); c3 = fmaf(de[u], kv[u].w, c3);
+                    }
+                }
+                st4(a.dq + (size_t)pc[k] * SCANN_D + lane * 4,
+                    make_float4(dc[k].x + 0.25f * c0, dc[k].y + 0.25f * c1, dc[k].z + 0.25f * c2, dc[k].w + 0.25f * c3));
+            }
+            pf_group_sync(grp);
+            BCLK(0, 4);
             // ---- phase C: dk = p d_ctx[c] + 0.25 de q[c] in place over k (hi operand), lo image, dbk
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -221,11 +255,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             fence_async_smem();
             tc_fence_before();
             pf_group_sync(grp);
+            BCLK(0, 5);
             if (wgl < 3) {                                      // d_a^T = Wk dk^T: one product chain per warp
                 tc_fence_after();
                 if (tc_elect_one()) pf_issue_chain(wgl, t_wraw, t_wlo, smem_u32(K), smem_u32(Lo), t_acc, &c.accf[s]);
                 __syncwarp();
             }
+            BCLK(0, 6);
             int jj[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) jj[k] = pc[k] >= 0 ? sidx[32 + wgl + PF_GW * k] : 0;
@@ -248,9 +284,11 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             }
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 24, t, s);
             tc_fence_after();
+            BCLK(0, 7);
             pf_acc_to_image(t_acc, Lo, nullptr, q, half, lane);
             tc_fence_before();
             pf_group_sync(grp);
+            BCLK(0, 8);
             // ---- phase D: d_nbr = d_a * g' -> dx[j] ; d_a * x[j] in place over x[j] (-> dg through the store warp)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -266,6 +304,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_bwd_pipe_kernel(const _
             }
             fence_async_smem();
             pf_group_sync(grp);
+            BCLK(0, 9);
             if (gtid == 0) mbar_arrive(&c.ready[s]);            // d_k and d_a * x[j]: over to the store warp
         }
         atomicAdd(&s_dbk[lane * 4 + 0], dbk.x); atomicAdd(&s_dbk[lane * 4 + 1], dbk.y);
@@ -296,6 +335,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
     __shared__ float s_acc[2 * SCANN_D];
     if (threadIdx.x < 2 * SCANN_D) s_acc[threadIdx.x] = 0.f;
     // stationary operand A[M = k][K = n] = W2[k][n]: (d_pre W2^T)^T = W2 d_pre^T
+    // (Tried in round 2: phase A in the forward kernels' row-group mapping -- four rows of a warp at once, three-step
+    // reductions, x_hat parked in the G image for a separate d_gamma / d_beta pass.  The phase itself got 30 % shorter
+    // (4 300 -> 2 950 cycles) but the step 0.7 % SLOWER: the extra image traffic (4 STS.128 + 8 LDS.128 per lane and tile)
+    // costs more than the shorter chain saves -- these kernels are bound by the shared-memory pipe, ~270 KB per tile.)
     PF_PROLOGUE(BwdFrame, PB_NS, a.W2T, 1)
     if (warp == PF_CW) {
         // ================= producer =================
@@ -347,7 +390,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
             uint8_t* G = P + 2 * PT_IMG;                        // layer input geometry g
             uint8_t* Dg = P + 3 * PT_IMG;                       // gradient w.r.t. g'
             const int32_t* sidx = c.idx + s * 64;
+            BCLK(1, 0);
             pipe_wait(&c.full[s], ph, c.dead, a.status, 33, t, s);
+            BCLK(1, 1);
             int pc[4];
             float4 dz[4];
 #pragma unroll
@@ -409,11 +454,13 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
             fence_async_smem();
             tc_fence_before();
             pf_group_sync(grp);
+            BCLK(1, 2);
             if (wgl < 3) {                                      // W2 d_pre^T: one product chain per warp
                 tc_fence_after();
                 if (tc_elect_one()) pf_issue_chain(wgl, t_wraw, t_wlo, smem_u32(P), smem_u32(Lo), t_acc, &c.accf[s]);
                 __syncwarp();
             }
+            BCLK(1, 3);
             // ---- phase B (warp per atom, overlaps the MMAs): s_pre[c] = sum_n d_pre
             {
                 const int myc = sidx[lane];
@@ -438,11 +485,14 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
                     for (int k2 = 0; k2 < PF_GW && m; ++k2) m &= m - 1;
                 }
             }
+            BCLK(1, 4);
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 34, t, s);
             tc_fence_after();
+            BCLK(1, 5);
             pf_acc_to_image(t_acc, Lo, nullptr, q, half, lane);
             tc_fence_before();
             pf_group_sync(grp);
+            BCLK(1, 6);
             // ---- phase C: dg = d_z + d_pre @ W2^T (in place)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -456,6 +506,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_geom_bwd_pipe_kernel(const _
             }
             fence_async_smem();
             pf_group_sync(grp);
+            BCLK(1, 7);
             if (gtid == 0) mbar_arrive(&c.ready[s]);            // d_pre and dg: over to the store warp
         }
         atomicAdd(&s_acc[lane * 4 + 0], dgam.x); atomicAdd(&s_acc[lane * 4 + 1], dgam.y);
