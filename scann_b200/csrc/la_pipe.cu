@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
             uint8_t* Bm = A + PT_IMG;                           // x[j] -> lo image
             const int32_t* sidx = c.idx + s * 64;
             float* Es = c.es + s * 2 * PT * 8;
+            PCLK(1, 0);
             pipe_wait(&c.full[s], ph, c.dead, a.status, 13, t, s);
+            PCLK(1, 1);
             const int pc = sidx[r];
             const bool ok = pc >= 0;
             float4 qv[4];
@@ -309,16 +311,20 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
             fence_async_smem();
             tc_fence_before();
             pf_group_sync(grp);
+            PCLK(1, 2);
             if (wgl < 3) {
                 tc_fence_after();
                 if (tc_elect_one()) pf_issue_chain(wgl, t_wraw, t_wlo, smem_u32(A), smem_u32(Bm), t_acc, &c.accf[s]);
                 __syncwarp();
             }
+            PCLK(1, 3);
             pipe_wait(&c.accf[s], ph, c.dead, a.status, 14, t, s);
             tc_fence_after();
+            PCLK(1, 4);
             pf_acc_to_image(t_acc, A, a.bk, q, half, lane);                  // keys k = a @ Wk + bk
             tc_fence_before();
             pf_group_sync(grp);
+            PCLK(1, 5);
             // ---- scores e[r][h] = 0.25 <q_h, k_h>  (head h = 16 columns = 4 adjacent lanes of the row)
             if (!__all_sync(0xffffffffu, !ok)) {
 #pragma unroll
@@ -329,52 +335,87 @@ __global__ void __launch_bounds__(PF_THREADS, 1) la_attn_fwd_pipe_kernel(const _
                 }
             }
             pf_group_sync(grp);
-            // ---- per atom (one warp each): softmax over its rows, context, residual q, LayerNorm.  The atoms of the
-            // tile are read off the centre indices: valid rows are a prefix, an atom's rows are contiguous
+            PCLK(1, 6);
+            // ---- softmax over an atom's rows, by HEAD-warps: lane = row, the rows of an atom are a contiguous run of lanes, so
+            // max and sum are segmented shuffle reductions -- every warp is busy and the cost does not depend on the
+            // neighbour count.  (First form: one warp per atom looped twice over its rows, three or four of the eight warps
+            // worked: 3 000 of the 6 600 cycles of a tile, gpurun_out/r02ap_pipe_clocks_fwd.log.)
+            const int myc = sidx[lane];
+            const int prevc = __shfl_up_sync(0xffffffffu, myc, 1);
+            const uint32_t vmask = __ballot_sync(0xffffffffu, myc >= 0);
+            const uint32_t hmask = __ballot_sync(0xffffffffu, myc >= 0 && (lane == 0 || myc != prevc));
+            const int nvalid = __popc(vmask);
             {
-                const int myc = sidx[lane];
-                const int prevc = __shfl_up_sync(0xffffffffu, myc, 1);
-                const uint32_t vmask = __ballot_sync(0xffffffffu, myc >= 0);
-                const uint32_t hmask = __ballot_sync(0xffffffffu, myc >= 0 && (lane == 0 || myc != prevc));
-                const int nvalid = __popc(vmask), natoms = __popc(hmask);
-                uint32_t m = hmask;
-                for (int k = 0; k < wgl; ++k) m &= m - 1;
-                for (int k = wgl; k < natoms; k += PF_GW) {
-                    const int r0 = __ffs(m) - 1;
-                    uint32_t mn = m;
-                    mn &= mn - 1;
-                    const int n = (mn ? __ffs(mn) - 1 : nvalid) - r0;
-                    const int atom = sidx[r0];
-                    const int h = lane >> 2;
-                    const float4 qa = ld4(a.proj + (size_t)atom * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
-                    float mx = -INFINITY;
-                    for (int rr = 0; rr < n; ++rr) mx = fmaxf(mx, Es[(r0 + rr) * 8 + h]);
-                    float sm = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-                    for (int rr = 0; rr < n; ++rr) {
-                        float p = __expf(Es[(r0 + rr) * 8 + h] - mx);
-                        const float4 kv = lds4(A + pt_off4(r0 + rr, lane));
-                        sm += p;                                        // the softmax is normalised before the dropout
-                        p *= drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + rr) * 8u + h);
-                        c0 = fmaf(p, kv.x, c0); c1 = fmaf(p, kv.y, c1); c2 = fmaf(p, kv.z, c2); c3 = fmaf(p, kv.w, c3);
-                    }
-                    const float is = 1.0f / sm;
-                    if (a.attn && (lane & 3) == 0)
-                        for (int rr = 0; rr < n; ++rr)
-                            a.attn[(rowbase + r0 + rr) * 8 + h] = __expf(Es[(r0 + rr) * 8 + h] - mx) * is *
-                                                                drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + r0 + rr) * 8u + h);
-                    c0 = c0 * is + qa.x; c1 = c1 * is + qa.y; c2 = c2 * is + qa.z; c3 = c3 * is + qa.w;
-                    if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
-                    const float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
-                    c0 -= mean; c1 -= mean; c2 -= mean; c3 -= mean;
-                    const float inv = rsqrtf(warp_sum(c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3) * (1.0f / SCANN_D) + SCANN_LN_EPS);
-                    st4(a.out + (size_t)atom * SCANN_D + lane * 4,
-                        make_float4(c0 * inv * gam.x + bet.x, c1 * inv * gam.y + bet.y, c2 * inv * gam.z + bet.z,
-                                    c3 * inv * gam.w + bet.w));
-                    for (int k2 = 0; k2 < PF_GW && m; ++k2) m &= m - 1;     // this warp's next atom
+                const bool valid = myc >= 0;
+                const uint32_t below = hmask & ((2u << lane) - 1u);
+                const uint32_t above = lane < 31 ? hmask & ~((2u << lane) - 1u) : 0u;
+                const int lo = valid ? 31 - __clz(below) : lane;
+                const int hi = valid ? (above ? __ffs(above) - 2 : nvalid - 1) : lane;
+                const int h = wgl;
+                const float e = valid ? Es[lane * 8 + h] : -INFINITY;
+                float mx = e;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_down_sync(0xffffffffu, mx, o);
+                    if (lane + o <= hi) mx = fmaxf(mx, v);
+                }
+                mx = __shfl_sync(0xffffffffu, mx, lo);
+                const float pe = valid ? __expf(e - mx) : 0.f;
+                float sm = pe;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float v = __shfl_down_sync(0xffffffffu, sm, o);
+                    if (lane + o <= hi) sm += v;
+                }
+                sm = __shfl_sync(0xffffffffu, sm, lo);
+                if (valid) {
+                    // the softmax is normalised before the dropout (attention.py:189-192)
+                    const float pn = pe * (1.0f / sm) * drop_mult(a.drop, a.drop_site, (uint32_t)(rowbase + lane) * 8u + h);
+                    Es[lane * 8 + h] = pn;
+                    if (a.attn) a.attn[(rowbase + lane) * 8 + h] = pn;
                 }
             }
+            pf_group_sync(grp);
+            // ---- context, residual q, LayerNorm: by the warp that owns the atom's first row (rows 4 wgl .. 4 wgl + 3), four
+            // rows per trip so that the shared-memory loads of a trip are in flight together
+#pragma unroll 1
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r0 = wgl * 4 + rr;
+                if (!((hmask >> r0) & 1u)) continue;                      // (warp-uniform)
+                const uint32_t nxt = r0 < 31 ? hmask & ~((2u << r0) - 1u) : 0u;
+                const int n = (nxt ? __ffs(nxt) - 1 : nvalid) - r0;
+                const int atom = sidx[r0];
+                const int h = lane >> 2;
+                const float4 qa = ld4(a.proj + (size_t)atom * 3 * SCANN_D + 2 * SCANN_D + lane * 4);
+                float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+                for (int r2 = 0; r2 < n; r2 += 4) {
+                    float pw[4];
+                    float4 kv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int row = r0 + (r2 + u < n ? r2 + u : 0);
+                        pw[u] = r2 + u < n ? Es[row * 8 + h] : 0.f;
+                        kv[u] = lds4(A + pt_off4(row, lane));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        c0 = fmaf(pw[u], kv[u].x, c0); c1 = fmaf(pw[u], kv[u].y, c1);
+                        c2 = fmaf(pw[u], kv[u].z, c2); c3 = fmaf(pw[u], kv[u].w, c3);
+                    }
+                }
+                c0 += qa.x; c1 += qa.y; c2 += qa.z; c3 += qa.w;
+                if (a.ctx_pre) st4(a.ctx_pre + (size_t)atom * SCANN_D + lane * 4, make_float4(c0, c1, c2, c3));
+                const float mean = warp_sum(c0 + c1 + c2 + c3) * (1.0f / SCANN_D);
+                c0 -= mean; c1 -= mean; c2 -= mean; c3 -= mean;
+                const float inv = rsqrtf(warp_sum(c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3) * (1.0f / SCANN_D) + SCANN_LN_EPS);
+                st4(a.out + (size_t)atom * SCANN_D + lane * 4,
+                    make_float4(c0 * inv * gam.x + bet.x, c1 * inv * gam.y + bet.y, c2 * inv * gam.z + bet.z,
+                                c3 * inv * gam.w + bet.w));
+            }
+            PCLK(1, 7);
             if (a.has_k) fence_async_smem();
             pf_group_sync(grp);
+            PCLK(1, 8);
             // training: the keys leave through the store warp; inference: the stage goes straight back to the producer
             if (gtid == 0) mbar_arrive(a.has_k ? &c.ready[s] : &c.empty[s]);
         }

@@ -864,3 +864,98 @@ def test_global_attention_and_residual_norm_layers():
     ref = O.residual_norm(w, "rn", torch.tensor(x, dtype=torch.float64))
     assert rel(out.cpu().numpy(), ref.numpy()) <= TOL_OUT
     assert rn.get_config() == {"dim": 128, "dropout": 0.1}
+
+
+def _weight_image_reference(W):
+    """Host restatement of weight_images_kernel (chain2_tc.cu): [2 orientations][4 K-blocks][raw | lo][128 rows x 128 B],
+    16-byte chunk i of row m at m * 128 + ((i ^ (m & 7)) << 4); raw = low 13 mantissa bits cleared, lo = w - raw."""
+    out = np.zeros((2, 4, 2, 128, 32), np.float32)
+    for orient, A in enumerate((W.T, W)):                       # A[m][k]: orientation 0 = W[k][m], 1 = W[m][k]
+        A = np.ascontiguousarray(A, np.float32)
+        raw = (A.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lo = A - raw
+        for kb in range(4):
+            for part, src in enumerate((raw, lo)):
+                blk = src[:, 32 * kb:32 * kb + 32].reshape(128, 8, 4)          # [m][logical chunk][4]
+                phys = np.empty_like(blk)
+                m = np.arange(128)
+                for i in range(8):
+                    phys[m, i ^ (m & 7)] = blk[m, i]
+                out[orient, kb, part] = phys.reshape(128, 32)
+    return out
+
+
+def test_weight_images_are_bit_exact():
+    """scann_weight_images: the tcgen05 operand images of the 128x128 weight blocks (byte layout and the tf32 split) against
+    a host restatement -- index / byte work, so bit for bit."""
+    from scann_b200 import _abi
+    _abi.require_gpu()
+    rng = np.random.default_rng(5)
+    nblk = 3
+    params = rng.standard_normal(nblk * 128 * 128 + 64).astype(np.float32)
+    offs = np.array([64 + b * 128 * 128 for b in range(nblk)], np.int32)
+    p_d, o_d = torch.from_numpy(params).cuda(), torch.from_numpy(offs).cuda()
+    buf = torch.zeros(nblk * 2 * 32768 + 256, dtype=torch.float32, device="cuda")
+    base = (buf.data_ptr() + 1023) // 1024 * 1024
+    _abi.check(_abi.lib.scann_weight_images(p_d.data_ptr(), o_d.data_ptr(), nblk, base, 0))
+    torch.cuda.synchronize()
+    skip = (base - buf.data_ptr()) // 4
+    got = buf.cpu().numpy()[skip:skip + nblk * 2 * 32768].reshape(nblk, 2, 4, 2, 128, 32)
+    for b in range(nblk):
+        W = params[offs[b]:offs[b] + 128 * 128].reshape(128, 128)
+        assert np.array_equal(got[b].view(np.uint32), _weight_image_reference(W).view(np.uint32))
+
+
+@pytest.mark.parametrize("R", [100, 3712, 5000, 10000])
+def test_chain2_matches_round1_chain_and_reference(R):
+    """scann_dense_chain2 (warp-specialised, weight images) against scann_dense_chain and an fp64 restatement on a
+    ResidualNorm-like step list (attention.py:25-40 + the next layer's projections): 32-row tiles (R <= 32 x SMs), 64-row
+    tiles, several waves, a ragged last tile."""
+    import ctypes
+    from scann_b200 import _abi
+    from scann_b200._abi import ChainStep, chain_step, check, lib
+    _abi.require_gpu()
+    rng = np.random.default_rng(R)
+    D = 128
+    Ws = [(rng.standard_normal((D, D)) / np.sqrt(D)).astype(np.float32) for _ in range(4)]
+    bs = [(0.1 * rng.standard_normal(D)).astype(np.float32) for _ in range(4)]
+    gamma, beta = (1 + 0.1 * rng.standard_normal(D)).astype(np.float32), (0.1 * rng.standard_normal(D)).astype(np.float32)
+    x = rng.standard_normal((R, D)).astype(np.float32)
+    params = np.concatenate([w.ravel() for w in Ws])
+    p_d = torch.from_numpy(params).cuda()
+    offs = torch.arange(4, dtype=torch.int32, device="cuda") * (D * D)
+    imgbuf = torch.zeros(4 * 2 * 32768 + 256, dtype=torch.float32, device="cuda")
+    ibase = (imgbuf.data_ptr() + 1023) // 1024 * 1024
+    check(lib.scann_weight_images(p_d.data_ptr(), offs.data_ptr(), 4, ibase, 0))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    x_d, b_d, g_d, be_d = dev(x), [dev(b) for b in bs], dev(gamma), dev(beta)
+
+    def run(new):
+        outs = {k: torch.zeros(R, D, device="cuda") for k in ("t1", "h1", "v2", "x1", "p0", "p1")}
+        wp = (lambda i: ibase + (i * 2) * 131072) if new else (lambda i: p_d.data_ptr() + i * D * D * 4)
+        steps = [
+            chain_step(A=[x_d.data_ptr()], W=[wp(0)], bias=b_d[0].data_ptr(), mode=1, pre_out=outs["t1"].data_ptr(),
+                       C_=outs["h1"].data_ptr(), to_image=True),
+            chain_step(W=[wp(1)], bias=b_d[1].data_ptr(), resid=x_d.data_ptr(), mode=3, pre_out=outs["v2"].data_ptr(),
+                       gamma=g_d.data_ptr(), beta=be_d.data_ptr(), C_=outs["x1"].data_ptr(), to_image=True),
+            chain_step(W=[wp(2)], bias=b_d[2].data_ptr(), C_=outs["p0"].data_ptr()),
+            chain_step(W=[wp(3)], C_=outs["p1"].data_ptr()),
+        ]
+        arr = (ChainStep * len(steps))(*steps)
+        fn = lib.scann_dense_chain2 if new else lib.scann_dense_chain
+        check(fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, 0))
+        torch.cuda.synchronize()
+        return {k: v.cpu().numpy() for k, v in outs.items()}
+
+    new, old = run(True), run(False)
+    X = torch.tensor(x, dtype=torch.float64)
+    W64 = [torch.tensor(w, dtype=torch.float64) for w in Ws]
+    B64 = [torch.tensor(b, dtype=torch.float64) for b in bs]
+    t1 = X @ W64[0] + B64[0]
+    h1 = t1 * torch.sigmoid(t1)
+    v2 = h1 @ W64[1] + B64[1] + X
+    x1 = torch.nn.functional.layer_norm(v2, (D,), torch.tensor(gamma, dtype=torch.float64), torch.tensor(beta, dtype=torch.float64), 1e-6)
+    ref = {"t1": t1, "h1": h1, "v2": v2, "x1": x1, "p0": x1 @ W64[2] + B64[2], "p1": x1 @ W64[3]}
+    for k, r in ref.items():
+        assert rel(new[k], r.numpy()) <= TOL_OUT, (k, rel(new[k], r.numpy()))
+        assert rel(old[k], r.numpy()) <= TOL_OUT, (k, rel(old[k], r.numpy()))

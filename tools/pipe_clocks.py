@@ -32,3 +32,11 @@ for k in range(4):
         parts.append(f"{names[p]} +{g[k][p] - prev}")
         prev = g[k][p]
     print(f"tile ordinal {k} (@{g[k][0] - t00}, total {g[k][8] - g[k][0]}): " + ", ".join(parts))
+
+names1 = ["loop top", "tile landed", "a = x[j] * g', lo, fence, sync", "MMA issued", "accumulators ready", "acc -> image (keys) + sync",
+          "scores + sync", "per-atom softmax / context / LayerNorm", "sync"]
+g = a[1]
+print("--- attention forward")
+for k in range(4):
+    if g[k][1] == 0: continue
+    print(f"tile ordinal {k} (total {g[k][8] - g[k][0]}): " + ", ".join(f"{names1[p]} +{g[k][p] - g[k][p-1]}" for p in range(1, 9)))
