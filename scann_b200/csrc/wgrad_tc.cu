@@ -258,6 +258,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
+        // (Round 2 experiments, both slower: the three products issued by three warps into three accumulators -- step
+        // +35 us, 122 -> 157 us for this launch; eight splitter warps + a dedicated MMA warp behind named barriers -- 168
+        // registers and 800 bytes of spills.  Kept: one issuing lane, two image sets.)
         if (warp == 0 && tc_elect_one()) {
             tc_fence_after();
             const uint64_t dxh = wg_mn_desc(smem_u32(sXh)), dxl = wg_mn_desc(smem_u32(sXl)), dyh = wg_mn_desc(smem_u32(sYh)),
