@@ -99,11 +99,16 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(float* __restrict__ p, fl
         float4* red = reinterpret_cast<float4*>(fl + P2P_FLAG_WORDS);
         const int lo = b.rank * per, hi = min(n4, lo + per);
         for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+            // all remote loads first (a loop over a runtime rank count issues them one NVLink round trip after the other),
+            // then the sum in rank order
+            float4 t[P2P_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r)
+                t[r] = r < b.world ? reinterpret_cast<const float4*>(b.arena[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 gi = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < b.world; ++r) {
-                const float4 t = reinterpret_cast<const float4*>(b.arena[r])[i];
-                gi.x += t.x; gi.y += t.y; gi.z += t.z; gi.w += t.w;
-            }
+#pragma unroll
+            for (int r = 0; r < P2P_MAX_RANKS; ++r)
+                if (r < b.world) { gi.x += t[r].x; gi.y += t[r].y; gi.z += t[r].z; gi.w += t[r].w; }
             red[i] = gi;
         }
         __syncthreads();
@@ -120,7 +125,13 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(float* __restrict__ p, fl
         __syncthreads();
     }
     float sse = 0.f, sabs = 0.f;
-    for (int r = 0; r < b.world; ++r) { sse += b.arena[r][n]; sabs += b.arena[r][n + 1]; }
+    {
+        float s0[P2P_MAX_RANKS], s1[P2P_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r) { s0[r] = r < b.world ? b.arena[r][n] : 0.f; s1[r] = r < b.world ? b.arena[r][n + 1] : 0.f; }
+#pragma unroll
+        for (int r = 0; r < P2P_MAX_RANKS; ++r) if (r < b.world) { sse += s0[r]; sabs += s1[r]; }
+    }
     const float rmse = sqrtf(sse / h.batch);
     const float scale = 1.0f / (h.batch * rmse);
     if (blockIdx.x == 0 && threadIdx.x == 0) { sums[0] = sse; sums[1] = sabs; }
@@ -138,10 +149,13 @@ __global__ void __launch_bounds__(256) adam_p2p_kernel(float* __restrict__ p, fl
         if (two_shot) {                         // all-gather: the reduced slice of its owner
             gi = reinterpret_cast<const float4*>(b.flags[i / per] + P2P_FLAG_WORDS)[i];
         } else {
-            for (int r = 0; r < b.world; ++r) {
-                const float4 t = reinterpret_cast<const float4*>(b.arena[r])[i];
-                gi.x += t.x; gi.y += t.y; gi.z += t.z; gi.w += t.w;
-            }
+            float4 t[P2P_TWO_SHOT_MIN_RANKS - 1];                  // one-shot form: at most three ranks
+#pragma unroll
+            for (int r = 0; r < P2P_TWO_SHOT_MIN_RANKS - 1; ++r)
+                t[r] = r < b.world ? reinterpret_cast<const float4*>(b.arena[r])[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < P2P_TWO_SHOT_MIN_RANKS - 1; ++r)
+                if (r < b.world) { gi.x += t[r].x; gi.y += t[r].y; gi.z += t[r].z; gi.w += t[r].w; }
         }
         const float4 w = reinterpret_cast<const float4*>(p)[i], lm = reinterpret_cast<const float4*>(l2mask)[i];
         float4 mi = make_float4(0.f, 0.f, 0.f, 0.f), vi = mi, gr, o;
