@@ -413,13 +413,13 @@ def run_ours(args):
             "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
             "share_of_step": n_bwd * ms_bwd / args.steps / (dev_ms / args.steps),
             "algorithmic_bytes_per_launch": bytes_bwd,
-            # measured kind::tf32 rate of one SM (profiles/r02_tf32_peak.md: 46.4 cycles per 128x128x8 tcgen05.mma from
-            # one issuing thread = 5 650 flop/clk/SM), times the SMs and the SM clock seen during this run
+            # measured kind::tf32 rate of one SM (profiles/r02_tf32_peak.md: 64.5 cycles per 128x128x8 tcgen05.mma, the math
+            # floor of the N = 128 form = 4 064 flop/clk/SM), times the SMs and the SM clock seen during this run
             "tensor_view": (lambda tf, pk: {"tf32_tflops_issued": tf, "tf32_peak_measured_tflops": pk, "frac": tf / pk,
-                                            "note": "3 tf32 products per fp32 product; peak = 5650 flop/clk/SM (measured "
-                                                    "tcgen05 kind::tf32 issue rate) x SMs x SM clock"})(
+                                            "note": "3 tf32 products per fp32 product; peak = 4064 flop/clk/SM (measured "
+                                                    "tcgen05 kind::tf32 rate, M = N = 128) x SMs x SM clock"})(
                 flops_bwd / (ms_bwd * 1e-3) / 1e12,
-                5650.0 * eng.sm_count * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e12),
+                4064.0 * eng.sm_count * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e12),
             "la_forward": {"achieved": bytes_fwd / (ms_fwd * 1e-3) / 1e9, "ms_per_launch": ms_fwd,
                            "frac": bytes_fwd / (ms_fwd * 1e-3) / 1e9 / peaks["hbm_gbs"]}}
     if n_wg:

@@ -6,7 +6,7 @@ from scann_b200._abi import lib, check, require_gpu
 require_gpu()
 out = torch.zeros(4, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-for ncols in (32, 64):
+for ncols in (32, 64, 128):
     for nacc in (1, 2, 3, 4, 6, 8):
         if nacc * ncols > 256:
             continue
