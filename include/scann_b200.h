@@ -196,9 +196,11 @@ int scann_dense_chain(const ScannChainStep* steps, int nsteps, int R, void* stre
  * ([nblocks][2][32768] floats, 1024-byte aligned): orientation 0 is the operand of x @ W, orientation 1 of x @ W^T
  * (what the backward pass multiplies with) -- four K-blocks of [tf32-truncated | remainder] chunk blocks in the
  * 128-byte-swizzled K-major tcgen05 layout, streamed into shared memory with cp.async.bulk.  Call it after every change
- * of the parameters.  scann_dense_chain2_max_rows() = the rows one wave covers (64 per SM); more rows run in several waves. */
+ * of the parameters.  scann_dense_chain2_max_rows() = the rows one wave covers (64 per SM); more rows run in several waves.
+ * status (nullable): 8 device ints; a bounded wait that gives up ORs 16 into word 0 and leaves {site 41..47, CTA, step / block,
+ * buffer} in words 1..4, as the pipelined local-attention kernels do. */
 int scann_weight_images(const float* params, const int32_t* offsets, int nblocks, float* images, void* stream);
-int scann_dense_chain2(const ScannChainStep* steps, int nsteps, int R, void* stream);
+int scann_dense_chain2(const ScannChainStep* steps, int nsteps, int R, int32_t* status, void* stream);
 int scann_dense_chain2_max_rows(void);
 
 /* ---- local attention (the hot kernel) ---------------------------------------------------------

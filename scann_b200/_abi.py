@@ -36,7 +36,7 @@ PROTOTYPES = {
     "scann_dense_forward": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_forward_tc": (ci, [vp, ci, vp, vp, ci, ci, ci, vp, ci, ci, vp, ci, vp, vp, vp, vp, vp]),
     "scann_dense_chain": (ci, [vp, ci, ci, vp]),
-    "scann_dense_chain2": (ci, [vp, ci, ci, vp]),
+    "scann_dense_chain2": (ci, [vp, ci, ci, vp, vp]),
     "scann_dense_chain2_max_rows": (ci, []),
     "scann_weight_images": (ci, [vp, vp, ci, vp, vp]),
     "scann_dense_wgrad": (ci, [vp, ci, vp, ci, ci, ci, ci, vp, vp, vp]),

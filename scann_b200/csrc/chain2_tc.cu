@@ -19,7 +19,8 @@
 //     the next one.  Steps that share their input image (W1 | W3 | Wq) overlap: the tensor core works on the next
 //     product while the epilogue of the previous one drains.
 //
-// Every mbarrier wait is bounded (pipe_common.cuh: pipe_wait); a protocol error ends with wrong numbers, not a hang.
+// Every mbarrier wait is bounded (pipe_common.cuh: pipe_wait): a protocol error ends with SCANN_ERR_PIPE_TIMEOUT and the wait
+// site in the caller's status words (the engine raises on it), not with a hang.
 #include <string.h>
 
 #include "pipe_common.cuh"
@@ -82,6 +83,7 @@ struct C2Step {
 struct C2Block { const float* wimg; uint32_t flags; uint32_t pad; };
 struct C2Args {
     int nsteps, R, nblocks, pad;
+    int32_t* status;        // engine status words (nullable): a wait that gives up sets SCANN_ERR_PIPE_TIMEOUT + its site (41..47)
     C2Step s[C2_MAX_STEPS];
     C2Block b[C2_MAX_BLOCKS];
 };
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(a.b[bi].wimg);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
-                    pipe_wait(&w_empty[kb], ((uint32_t)bi & 1u) ^ 1u, dead, nullptr, 1, bi, kb);
+                    pipe_wait(&w_empty[kb], ((uint32_t)bi & 1u) ^ 1u, dead, a.status, 41, bi, kb);
                     mbar_expect_tx(&w_full[kb], C2_SLOT_BYTES);
                     bulk_load(ring + (size_t)kb * C2_SLOT_BYTES, src + (size_t)kb * C2_SLOT_BYTES, C2_SLOT_BYTES, &w_full[kb]);
                 }
@@ -236,9 +238,9 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                 const uint32_t fl = a.b[bi].flags;
                 if (fl & C2_FRESH) {
                     ++xi;
-                    pipe_wait(&x_full[xi % K::NXBUF], ((uint32_t)(xi / K::NXBUF)) & 1u, dead, nullptr, 2, bi, xi);
+                    pipe_wait(&x_full[xi % K::NXBUF], ((uint32_t)(xi / K::NXBUF)) & 1u, dead, a.status, 42, bi, xi);
                 }
-                if (fl & C2_FIRST) pipe_wait(&acc_empty[ai & 1], (((uint32_t)(ai >> 1)) & 1u) ^ 1u, dead, nullptr, 3, bi, ai);
+                if (fl & C2_FIRST) pipe_wait(&acc_empty[ai & 1], (((uint32_t)(ai >> 1)) & 1u) ^ 1u, dead, a.status, 43, bi, ai);
                 if (chain == 2) C2CLK(1, bi * 3);
                 // accumulator set: [W_lo X_raw | W_raw X_lo | main, K-blocks 0-1 | main, K-blocks 2-3].  The tensor core's
                 // accumulate loses low-order bits of what it adds to a large accumulator (profiles/r01_tcgen05_probe.md);
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                 const uint32_t ximg = smem_u32(sX + (size_t)(xi % K::NXBUF) * 2u * K::IMG) + (chain == 1 ? K::IMG : 0u);
 #pragma unroll
                 for (int kb = 0; kb < 4; ++kb) {
-                    pipe_wait(&w_full[kb], (uint32_t)bi & 1u, dead, nullptr, 4, bi, kb);
+                    pipe_wait(&w_full[kb], (uint32_t)bi & 1u, dead, a.status, 44, bi, kb);
                     tc_fence_after();
                     if (kb == 3 && chain == 2) C2CLK(1, bi * 3 + 1);
                     const uint64_t da = pt_desc(ring_a + kb * C2_SLOT_BYTES), db = pt_desc(ximg + kb * K::CB);
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                     xv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r0 + r < a.R) xv[it] = ld4(A + (size_t)(r0 + r) * st.lda + c4 * 4);
                 }
-                pipe_wait(&x_empty[xi % K::NXBUF], (((uint32_t)(xi / K::NXBUF)) & 1u) ^ 1u, dead, nullptr, 5, si, xi);
+                pipe_wait(&x_empty[xi % K::NXBUF], (((uint32_t)(xi / K::NXBUF)) & 1u) ^ 1u, dead, a.status, 45, si, xi);
                 uint8_t* Xr = sX + (size_t)(xi % K::NXBUF) * 2u * K::IMG;
 #pragma unroll
                 for (int it = 0; it < K::XIT; ++it) {
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
                     }
                 }
             }
-            pipe_wait(&acc_full[ai & 1], ((uint32_t)(ai >> 1)) & 1u, dead, nullptr, 6, si, ai);
+            pipe_wait(&acc_full[ai & 1], ((uint32_t)(ai >> 1)) & 1u, dead, a.status, 46, si, ai);
             tc_fence_after();
             if (tid == 0) C2CLK(0, 2 + si * 4);
             if (si == a.nsteps - 1) pdl_trigger();      // only the last epilogue is left
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(C2_THREADS, 1) dense_chain2_kernel(const __gri
             uint8_t* Xn = nullptr;
             if (to_image) {
                 ++xi;
-                pipe_wait(&x_empty[xi % K::NXBUF], (((uint32_t)(xi / K::NXBUF)) & 1u) ^ 1u, dead, nullptr, 7, si, xi);
+                pipe_wait(&x_empty[xi % K::NXBUF], (((uint32_t)(xi / K::NXBUF)) & 1u) ^ 1u, dead, a.status, 47, si, xi);
                 Xn = sX + (size_t)(xi % K::NXBUF) * 2u * K::IMG;
             }
             float dgam[2][4], dbet[2][4];
@@ -621,7 +623,7 @@ extern "C" int scann_dense_chain2_max_rows(void) {
 
 // Same contract as scann_dense_chain, except that W[kb] of every step points to the weight IMAGE of the block
 // (scann_weight_images; orientation 0 for x @ W, 1 for x @ W^T).
-extern "C" int scann_dense_chain2(const void* steps_host, int nsteps, int R, void* stream) {
+extern "C" int scann_dense_chain2(const void* steps_host, int nsteps, int R, int32_t* status, void* stream) {
     if (nsteps < 1 || nsteps > C2_MAX_STEPS) { scann_set_error("dense_chain2: nsteps must be in 1..%d", C2_MAX_STEPS); return 1; }
     if (R <= 0) return 0;
     static_assert(sizeof(C2Args) <= 4096, "kernel parameter space");
@@ -629,6 +631,7 @@ extern "C" int scann_dense_chain2(const void* steps_host, int nsteps, int R, voi
     memset(&a, 0, sizeof(a));
     a.nsteps = nsteps;
     a.R = R;
+    a.status = status;
     const C2Step* s = (const C2Step*)steps_host;
     int nb = 0;
     for (int i = 0; i < nsteps; ++i) {

@@ -27,7 +27,7 @@ L2_COEF = 1e-4
 
 ERR_BITS = {1: "plan tile capacity exceeded", 2: "an atom has more than 128 valid neighbours",
             4: "atomic number outside the embedding table", 8: "neighbour index outside [0, M)",
-            16: "a bounded mbarrier wait of a pipelined local-attention kernel gave up"}
+            16: "a bounded mbarrier wait of a pipelined kernel (local attention, chained Dense) gave up"}
 
 
 def _p(t: Optional[torch.Tensor], off_elems: int = 0) -> int:
@@ -608,7 +608,8 @@ class Engine:
                 for kb in range(s.kblk):
                     s.W[kb] = self._wimg_ptr(s.W[kb])
             arr = (ChainStep * len(steps))(*steps)
-            check(lib.scann_dense_chain2(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, self._stream()), "dense_chain2")
+            check(lib.scann_dense_chain2(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, _p(self.status), self._stream()),
+                  "dense_chain2")
             self.launches += 1
             return
         arr = (ChainStep * len(steps))(*steps)

@@ -943,7 +943,7 @@ def test_chain2_matches_round1_chain_and_reference(R):
         ]
         arr = (ChainStep * len(steps))(*steps)
         fn = lib.scann_dense_chain2 if new else lib.scann_dense_chain
-        check(fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, 0))
+        check(fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, 0, 0) if new else fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, 0))
         torch.cuda.synchronize()
         return {k: v.cpu().numpy() for k, v in outs.items()}
 

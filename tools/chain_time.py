@@ -39,7 +39,7 @@ def launch(steps, R, new):
                 s.W[kb] = eng._wimg_ptr(s.W[kb])
     arr = (ChainStep * len(steps))(*steps)
     fn = lib.scann_dense_chain2 if new else lib.scann_dense_chain
-    check(fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, st))
+    check(fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, 0, st) if new else fn(ctypes.cast(arr, ctypes.c_void_p), len(steps), R, st))
 
 def timeit(fn, n=50):
     for _ in range(5): fn()
