@@ -16,8 +16,9 @@
  *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous and re-entrant across
  *    streams; the only global state is the per-thread error string and two per-thread launch switches
  *    (scann_set_pdl, scann_set_la_groups4: scheduling choices, never numerics);
- *  - there is no scann_allreduce_*: the data-parallel exchange is either torch.distributed (NCCL) on the host side
- *    or the peer-memory form fused into the optimiser kernel (scann_p2p_*, scann_adam_p2p_step);
+ *  - the data-parallel exchange is either an NCCL all-reduce of the gradient arena (scann_allreduce_*, NCCL bound at run
+ *    time; torch.distributed's own all_reduce works as well) or the peer-memory form fused into the optimiser kernel
+ *    (scann_p2p_*, scann_adam_p2p_step); the NCCL communicator is the one piece of process-wide state;
  *  - per-atom tensors are [R,128] fp32 row-major with R = B*M (row r = b*M + m);
  *    per-pair tensors use the tile-padded packed layout built by scann_plan_build:
  *    tile t owns rows [S t, S t + S) with S = tile_stride (32 for the pipelined local-attention kernels,
@@ -344,6 +345,19 @@ int scann_adam_step(float* params, const float* grads, float* m, float* v, const
                     float* sse, const void* scalars_dev, float* grad_out, int apply, void* stream);
 int scann_loss_value(const float* params, const float* l2mask, int n, const float* sse, float batch, float l2,
                      float* out3, void* stream);
+
+/* ---- NCCL gradient all-reduce ---------------------------------------------------------------
+ * One process per GPU, one communicator per process.  Rank 0: scann_allreduce_unique_id(out128) -> 128 HOST bytes
+ * (ncclUniqueId) that the caller sends to the other ranks; every rank, with its device current:
+ * scann_allreduce_init(id128, rank, world) (collective); per step scann_allreduce_sum(arena, n + 4, stream) between the
+ * backward pass and scann_adam_step (in place, asynchronous, capturable into the step's CUDA graph);
+ * scann_allreduce_destroy at the end.  libnccl.so.2 is dlopen'ed on first use (the copy already loaded in the process,
+ * e.g. PyTorch's, else the system one): the library itself does not link against NCCL. */
+int scann_allreduce_unique_id(void* out128);
+int scann_allreduce_init(const void* id128, int rank, int world);
+int scann_allreduce_sum(float* buf, long long count, void* stream);
+int scann_allreduce_world(void);
+int scann_allreduce_destroy(void);
 
 /* ---- gradient exchange over NVLink peer memory, fused into the optimiser -------------------------------------
  * Data-parallel training (one process per GPU; the reference trains on one device, scann_model.py:232-241): instead of

@@ -61,6 +61,11 @@ PROTOTYPES = {
     "scann_rmse_prepare": (ci, [vp, vp, ci, vp, vp, vp]),
     "scann_adam_step": (ci, [vp, vp, vp, vp, vp, ci, vp, vp, vp, ci, vp]),
     "scann_loss_value": (ci, [vp, vp, ci, vp, C.c_float, C.c_float, vp, vp]),
+    "scann_allreduce_unique_id": (ci, [vp]),
+    "scann_allreduce_init": (ci, [vp, ci, ci]),
+    "scann_allreduce_sum": (ci, [vp, C.c_longlong, vp]),
+    "scann_allreduce_world": (ci, []),
+    "scann_allreduce_destroy": (ci, []),
     "scann_p2p_alloc": (ci, [C.c_longlong, C.POINTER(vp)]),
     "scann_p2p_free": (ci, [vp]),
     "scann_p2p_export": (ci, [vp, vp]),

@@ -40,6 +40,37 @@ def allreduce_sum(t: torch.Tensor) -> None:
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
 
+_native_world = 0
+
+
+def native_allreduce_init(rank: int, world: int) -> None:
+    """Communicator of the library's own NCCL entry points (``scann_allreduce_*``, include/scann_b200.h): rank 0 creates
+    the unique id, torch.distributed carries its 128 bytes to the other ranks (any host channel would do), every rank
+    joins with its CUDA device current.  One communicator per process."""
+    global _native_world
+    import ctypes as C
+    from ._abi import check, lib
+    if _native_world:
+        if _native_world != world:
+            raise RuntimeError("the native NCCL communicator was created for another world size")
+        return
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(lib.scann_allreduce_unique_id(C.cast(buf, C.c_void_p)), "allreduce_unique_id")
+    box = [bytes(buf)]
+    dist.broadcast_object_list(box, src=0)
+    buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+    check(lib.scann_allreduce_init(C.cast(buf, C.c_void_p), rank, world), "allreduce_init")
+    _native_world = world
+
+
+def native_allreduce_sum(t: torch.Tensor) -> None:
+    """In-place fp32 sum over the ranks through ``scann_allreduce_sum`` on the current stream (capturable)."""
+    from ._abi import check, lib
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    check(lib.scann_allreduce_sum(t.data_ptr(), t.numel(), torch.cuda.current_stream(t.device).cuda_stream), "allreduce_sum")
+
+
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard [lo, hi) of n structures for this rank (SURVEY.md 8e partitioning)."""
     per = (n + world - 1) // world
@@ -134,6 +165,11 @@ def attach(model, world: int) -> None:
     if world > 1:
         model.allreduce = allreduce_sum
         model.world_size = world
+        # SCANN_NCCL=native: the all-reduce goes through the library's own scann_allreduce_* entry points (NCCL bound at
+        # run time) instead of torch.distributed's all_reduce -- same collective, same place in the captured graph
+        if os.environ.get("SCANN_NCCL", "torch") == "native" and torch.cuda.is_available():
+            native_allreduce_init(env_world()[0], world)
+            model.allreduce = native_allreduce_sum
         # default on one node: the peer-memory exchange (validated against the single-GPU full-batch run on 2, 4 and 8
         # GPUs, tools/dp_check.py); SCANN_P2P_REDUCE=0 selects the NCCL all-reduce, which is also the multi-node path
         one_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) == world and world <= P2PExchange.MAX_RANKS

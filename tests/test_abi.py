@@ -69,3 +69,16 @@ def test_no_gpu_means_loud_failure():
     from scann_b200.model import create_model
     with pytest.raises(Exception):
         create_model(get_config("qm9"))
+
+
+def test_allreduce_entry_points_refuse_to_run_without_a_communicator():
+    """scann_allreduce_* (NCCL bound at run time): without scann_allreduce_init the sum must fail loudly, and the library
+    itself must not depend on NCCL at load time."""
+    from scann_b200 import _abi
+    assert _abi.lib.scann_allreduce_world() == 0
+    assert _abi.lib.scann_allreduce_sum(None, 16, None) != 0
+    assert "no communicator" in _abi.last_error()
+    assert _abi.lib.scann_allreduce_destroy() == 0
+    import subprocess
+    deps = subprocess.run(["ldd", _abi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in deps.lower()

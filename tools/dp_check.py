@@ -3,7 +3,8 @@ device, the whole batch, loss = sqrt(mean_B err^2), scann/layers/losses.py:5-6).
 
 Run under torchrun with WORLD_SIZE ranks.  Every step, rank r trains on its shard of a 2*8*WORLD_SIZE... batch whose
 shards have DIFFERENT pair counts (so the ranks' shape-class / CUDA-graph caches miss at different steps), once with
-the NCCL all-reduce and once with the peer-memory exchange (SCANN_P2P_REDUCE=1); rank 0 also trains a single-GPU model
+torch.distributed's NCCL all-reduce, once with the library's own scann_allreduce_* entry points (SCANN_NCCL=native) and once
+with the peer-memory exchange (SCANN_P2P_REDUCE=1); rank 0 also trains a single-GPU model
 on the concatenated batches.  Parameters after the steps must agree and be bit-identical across ranks."""
 import os
 import sys
@@ -42,6 +43,7 @@ def batches():
 
 def run(mode: str):
     os.environ["SCANN_P2P_REDUCE"] = "1" if mode == "p2p" else "0"
+    os.environ["SCANN_NCCL"] = "native" if mode == "nccl-native" else "torch"
     m = create_model(cfg, seed=3)
     m.dropout = False
     if mode != "single":
@@ -59,7 +61,7 @@ ok = True
 ref = None
 if rank == 0:
     ref, lref, p0 = run("single")
-for mode in ("nccl", "p2p"):
+for mode in ("nccl", "nccl-native", "p2p"):
     dist.barrier()
     p, losses, p0 = run(mode)
     mine = torch.from_numpy(p).cuda()
