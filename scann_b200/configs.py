@@ -1,7 +1,8 @@
 """The hyper-parameters of the reference's shipped yaml files as Python dicts.
 
-Values restate configs/model_qm9.yaml, model_mp2018.yaml, model_fullerene.yaml and
-model_ptgp.yaml of the reference (model section only; dataset paths are not reproduced).
+Values restate configs/model_qm9.yaml, model_qm9_std.yaml, model_mp2018.yaml, model_smfe.yaml,
+model_fullerene.yaml and model_ptgp.yaml of the reference -- every yaml it ships (model section and the
+hyper-parameters the training shell reads; dataset paths are not reproduced).
 A user's own yaml loads unchanged through ``scann_b200.config.load_yaml``.
 """
 from __future__ import annotations
@@ -16,10 +17,18 @@ CONFIGS = {
     "qm9": {"model": dict(_COMMON, n_atoms=10, embedding_dim=48, n_attention=7, use_ga_norm=True, use_ring=False,
                           g_update=True, gaussian_d=4.0),
             "hyper": {"batch_size": 128, "scaler": True, "scheduler": "sgdr", "lr": 0.0005, "min_lr": 0.0001}},
+    # configs/model_qm9_std.yaml (the JCTC split: eight layers, cosine schedule, no scaler key)
+    "qm9_std": {"model": dict(_COMMON, n_atoms=10, embedding_dim=48, n_attention=8, use_ga_norm=True, use_ring=False,
+                              g_update=True, gaussian_d=4.0),
+                "hyper": {"batch_size": 128, "scheduler": "cosine", "lr": 0.0006, "min_lr": 0.00008}},
     # configs/model_mp2018.yaml
     "mp2018": {"model": dict(_COMMON, n_atoms=95, embedding_dim=128, n_attention=9, use_ga_norm=True, use_ring=False,
                              g_update=True, gaussian_d=6.0),
                "hyper": {"batch_size": 64, "scaler": False, "scheduler": "cosine", "lr": 0.0001, "min_lr": 0.00005}},
+    # configs/model_smfe.yaml (SmFe12 crystals)
+    "smfe": {"model": dict(_COMMON, n_atoms=70, embedding_dim=48, n_attention=9, use_ga_norm=True, use_ring=False,
+                           g_update=True, gaussian_d=6.0),
+             "hyper": {"batch_size": 128, "scaler": False, "scheduler": "cosine", "lr": 0.0005, "min_lr": 0.0001}},
     # configs/model_fullerene.yaml
     "fullerene": {"model": dict(_COMMON, n_atoms=10, embedding_dim=48, n_attention=7, use_ga_norm=False,
                                 use_ring=False, g_update=True, gaussian_d=4.0),

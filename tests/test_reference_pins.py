@@ -130,6 +130,8 @@ def test_shipped_yaml_configs_equal_the_restated_dicts():
     from scann_b200.config import load_yaml
     from scann_b200.configs import CONFIGS
     cdir = os.path.join(ref_stubs.REFERENCE_ROOT, "configs")
+    shipped = sorted(f[len("model_"):-len(".yaml")] for f in os.listdir(cdir) if f.startswith("model_") and f.endswith(".yaml"))
+    assert shipped == sorted(CONFIGS), (shipped, sorted(CONFIGS))           # every yaml the reference ships is restated
     for name, mine in CONFIGS.items():
         theirs = load_yaml(os.path.join(cdir, f"model_{name}.yaml"))
         for section in ("model", "hyper"):
