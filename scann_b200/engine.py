@@ -18,6 +18,7 @@ import torch
 from . import _abi
 from ._abi import ChainStep, WgradProblem, chain_step, check, lib, ptr_array
 from .config import ModelSpec, N_RBF, check_kernel_support
+from .dlpack import import_tensor
 from .params import ParamLayout, layer_name
 
 TILE = 128
@@ -231,6 +232,7 @@ class Engine:
         pinned staging buffers; CUDA tensors / ``__dlpack__`` objects are copied device-to-device.
         Buffers are persistent per (B, M, N, tile capacity) so that a captured CUDA graph can be
         replayed on every batch of that shape."""
+        inputs = {k: import_tensor(v) for k, v in inputs.items()}     # DLPack capsules / exporters -> torch views
         nb = inputs["neighbors"]
         B, M, N = (int(s) for s in nb.shape)
         nmask_in = inputs["neighbor_mask"]
@@ -246,8 +248,6 @@ class Engine:
         def put(dst: torch.Tensor, x, name):
             if isinstance(x, torch.Tensor):
                 t = x
-            elif hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
-                t = torch.from_dlpack(x)
             else:
                 a = np.ascontiguousarray(x)
                 if a.dtype == np.bool_:

@@ -21,6 +21,7 @@ import torch
 
 from . import _abi
 from ._abi import check, lib, ptr_array
+from .dlpack import import_tensor
 
 D = 128
 TILE = 128
@@ -33,12 +34,8 @@ def _dev() -> torch.device:
 
 
 def _t(x, dtype=torch.float32) -> torch.Tensor:
-    if isinstance(x, torch.Tensor):
-        t = x
-    elif hasattr(x, "__dlpack__") and not isinstance(x, np.ndarray):
-        t = torch.from_dlpack(x)
-    else:
-        t = torch.from_numpy(np.ascontiguousarray(x))
+    x = import_tensor(x)                         # DLPack capsule / __dlpack__ exporter -> torch view (zero-copy)
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
     t = t.to(_dev())
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)

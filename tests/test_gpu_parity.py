@@ -694,6 +694,52 @@ def test_public_api_predict_and_train(tmp_path):
     assert np.array_equal(infer_h5.model.engine.get_params(), trainer.model.engine.get_params())
 
 
+def test_dlpack_producers_are_accepted_on_the_boundary():
+    """north_star: tensors are exchanged with the TF / Keras graph via DLPack.  TensorFlow is absent, so the producer
+    here is torch (same capsule type as tf.experimental.dlpack.to_dlpack) and a foreign ``__dlpack__`` exporter:
+    device-resident inputs handed over as capsules give the outputs of host numpy inputs, for the facade
+    and (bit for bit) for a layer mirror, and an output exported as a capsule is re-imported without a copy."""
+    from scann.layers import LocalAttention, gather_shape
+    from scann.models import SCANN
+    from scann_b200.dlpack import export_capsule, import_tensor
+
+    class Foreign:
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, **kw): return self.t.__dlpack__(**kw)
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+
+    cfg = get_config("qm9")
+    cfg["model"]["n_attention"] = 2
+    model = SCANN(cfg, mode="infer").model
+    inputs, _ = make_batch("qm9", 5, B=6)
+    y0, ga0 = model.predict(inputs)
+    dev = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in inputs.items()}
+    y1, ga1 = model.predict({k: export_capsule(v) for k, v in dev.items()})
+    y2, ga2 = model.predict({k: Foreign(v) for k, v in dev.items()})
+    # (the pair count of a device-resident batch is not known on the host: its shape class, hence its tile layout,
+    # may differ from the host-array batch -- same values up to the summation order inside GlobalAttention)
+    assert np.array_equal(y1, y2) and np.array_equal(ga1, ga2)
+    assert rel(y1, y0) <= 1e-6 and rel(ga1, ga0) <= 1e-6
+
+    rng = np.random.default_rng(3)
+    B, M, N = 2, 9, 5
+    x = rng.standard_normal((B, M, 128)).astype(np.float32)
+    geom = rng.standard_normal((B, M, N, 128)).astype(np.float32)
+    nbrs = rng.integers(0, M, (B, M, N)).astype(np.int32)
+    mask = (rng.random((B, M, N)) > 0.3).astype(np.float32)
+    layer = LocalAttention(v_proj=False, kq_proj=True, dim=128, num_head=8, activation="swish", dropout=False,
+                           g_update=True)
+    shapes = [(128, 128), (128,), (128, 128), (128,), (384, 128), (128,), (128,), (128,), (128,), (128,)]
+    layer.set_weights([(0.1 * rng.standard_normal(s)).astype(np.float32) for s in shapes])
+    ref = layer(x, gather_shape(nbrs), geom, mask)
+    cap = lambda a: export_capsule(torch.as_tensor(a).cuda())
+    got = layer(cap(x), gather_shape(cap(nbrs)), cap(geom), cap(mask))
+    for r, g in zip(ref, got):
+        assert torch.equal(r, g)
+    back = import_tensor(export_capsule(got[1]))            # what tf.experimental.dlpack.from_dlpack would take
+    assert back.data_ptr() == got[1].data_ptr() and torch.equal(back, got[1])
+
+
 def test_training_shell_fit_checkpoint_evaluate(tmp_path):
     """SCANN.train / evaluate (scann_model.py:199-313) on attached iterators: fit with the reference's callbacks
     (best-val_mae ModelCheckpoint to Keras HDF5, EarlyStopping, SGDRC), then evaluate from the checkpoint."""

@@ -137,3 +137,23 @@ def test_balanced_shards_equal_counts_and_nearly_equal_pair_counts():
         assert naive.max() - naive.min() > 4 * (loads.max() - loads.min())
     with pytest.raises(ValueError):
         balanced_shards(np.ones(10), 4)
+
+
+def test_dlpack_import_accepts_capsules_and_exporters():
+    """scann_b200.dlpack: the two DLPack producer forms (capsule = what tf.experimental.dlpack.to_dlpack returns,
+    ``__dlpack__`` exporter) come back as zero-copy torch views; numpy arrays and tensors pass through untouched."""
+    import torch
+    from scann_b200.dlpack import export_capsule, import_tensor, is_capsule
+
+    class Foreign:                                   # an exporter that is neither numpy nor torch
+        def __init__(self, t): self.t = t
+        def __dlpack__(self, **kw): return self.t.__dlpack__(**kw)
+        def __dlpack_device__(self): return self.t.__dlpack_device__()
+
+    src = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+    cap = export_capsule(src)
+    assert is_capsule(cap)
+    for got in (import_tensor(cap), import_tensor(Foreign(src))):
+        assert isinstance(got, torch.Tensor) and got.shape == src.shape and got.data_ptr() == src.data_ptr()
+    a = np.zeros(3, np.float32)
+    assert import_tensor(a) is a and import_tensor(src) is src and import_tensor(None) is None
