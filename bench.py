@@ -439,7 +439,8 @@ def run_ours(args):
     if n_gaf:
         bytes_ga = 2 * 516.0 * A_valid + 512.0 * B
         roof["global_attention"] = {
-            "kernel": "ga_head_fwd_kernel / ga_head_bwd_kernel (GlobalAttention + property head, one CTA per structure)",
+            "kernel": "ga_head_fwd_staged_kernel / ga_head_bwd_staged_kernel (GlobalAttention + property head, one CTA per "
+                      "structure, its query | key block staged in shared memory; ga.cu)",
             "forward": {"achieved": bytes_ga / (ms_gaf * 1e-3) / 1e9, "ms_per_launch": ms_gaf,
                         "frac": bytes_ga / (ms_gaf * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_ga},
             "backward": (None if not n_gab else

@@ -76,6 +76,9 @@ __device__ __forceinline__ void pf_issue_chain(int chain, uint32_t t_wraw, uint3
     tc_commit(bar);
 }
 
+// (Round 2, measured: reading the tile count BEFORE griddepcontrol.wait -- legal, the pair plan is never the direct
+// predecessor of these kernels -- made the QM9 train step 0.8 % SLOWER (0.976 -> 0.984 ms, two runs each, one box,
+// gpurun_out/r02ca_ab.log) and left MP2018 unchanged; the count is read behind the wait.)
 // prologue shared by both kernels: tensor-memory allocation, barrier init, the stationary weight
 #define PF_PROLOGUE(FRAME, NSTAGES, W_PTR, FULL_COUNT)                                                                   \
     extern __shared__ uint8_t smem_raw[];                                                                                \

@@ -694,7 +694,7 @@ def test_public_api_predict_and_train(tmp_path):
     assert np.array_equal(infer_h5.model.engine.get_params(), trainer.model.engine.get_params())
 
 
-def test_dlpack_producers_are_accepted_on_the_boundary():
+def test_dlpack_producers_are_accepted_on_the_boundary(tmp_path):
     """north_star: tensors are exchanged with the TF / Keras graph via DLPack.  TensorFlow is absent, so the producer
     here is torch (same capsule type as tf.experimental.dlpack.to_dlpack) and a foreign ``__dlpack__`` exporter:
     device-resident inputs handed over as capsules give the outputs of host numpy inputs, for the facade
@@ -710,7 +710,9 @@ def test_dlpack_producers_are_accepted_on_the_boundary():
 
     cfg = get_config("qm9")
     cfg["model"]["n_attention"] = 2
-    model = SCANN(cfg, mode="infer").model
+    path = str(tmp_path / "weights.npz")
+    SCANN(cfg, mode="train").model.save_weights(path)
+    model = SCANN(cfg, pretrained=path, mode="infer").model
     inputs, _ = make_batch("qm9", 5, B=6)
     y0, ga0 = model.predict(inputs)
     dev = {k: torch.as_tensor(np.ascontiguousarray(v)).cuda() for k, v in inputs.items()}
