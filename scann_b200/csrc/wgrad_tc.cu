@@ -260,7 +260,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_batch_tc_kernel(const WgA
         __syncthreads();
         // (Round 2 experiments, both slower: the three products issued by three warps into three accumulators -- step
         // +35 us, 122 -> 157 us for this launch; eight splitter warps + a dedicated MMA warp behind named barriers -- 168
-        // registers and 800 bytes of spills.  Kept: one issuing lane, two image sets.)
+        // registers and 800 bytes of spills.  Kept: one issuing lane, two image sets.
+        // Second session: the __syncthreads replaced by an mbarrier hand-over (every warp arrives on ready[set] and goes
+        // on, warp 0 waits for the 16 arrives and issues; no CTA-wide barrier in the unit loop although the ncu source
+        // page has 13.5 % of the samples there, gpurun_out/r02cb_prof.ncu-rep): 132 -> 157 us for this launch, QM9 step
+        // 0.977 -> 0.999 ms, MP2018 1.752 -> 1.80 ms (profiles/r02_ab_wgrad_handover.log) -- the same 157 us as the
+        // three-warp form: warps that drift apart cost more than the barrier.  A 17th, dedicated MMA warp leaves 96
+        // registers per thread (five warps on one scheduler): 1 182 bytes of spills, not measured.  The kernel executes
+        // 289 warp-instructions per warp and unit (cursor / index bookkeeping around 12 loads and 16 split stores) at
+        // 48 % issue-slot use with shared memory at 26 % and DRAM at 44 %: instruction latency, not a pipe, bounds it.)
         if (warp == 0 && tc_elect_one()) {
             tc_fence_after();
             const uint64_t dxh = wg_mn_desc(smem_u32(sXh)), dxl = wg_mn_desc(smem_u32(sXl)), dyh = wg_mn_desc(smem_u32(sYh)),
