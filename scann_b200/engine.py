@@ -109,6 +109,8 @@ class Engine:
         self.tc_la_fwd = eng != "simt" and os.environ.get("SCANN_LA_FWD", "tc") == "tc"
         self.tc_la_bwd = self.tc_la_fwd and os.environ.get("SCANN_LA_BWD", "tc") == "tc"
         self.use_side_stream = os.environ.get("SCANN_SIDE_STREAM", "1") == "1"
+        # geometry-initialisation backward beside the embedding backward at the end of the step (_backward_tail)
+        self.tail_fork = os.environ.get("SCANN_TAIL_FORK", "1") == "1"
         # Wave-balanced tiles: rows per tile chosen so that the tile count is a whole number of rounds over the
         # SMs' warp groups (QM9/128: 592 tiles of ~40 rows instead of 388 of 64: every group runs two short
         # tiles instead of some running two long ones).  Local-attention backward 74 -> 64 us per layer; the
@@ -1046,14 +1048,22 @@ class Engine:
         sp, st = self.spec, self._stream()
         R = b.R
         dx = ws["dx"]
-        if sp.g_update and "geom_init" not in self._skip:
-          check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid * self.gi_bwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
-                                           _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
-                                           self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
-                                           self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),
-                                           self.gw("neighbor_d/bias"), self.gw("neighbor_w/kernel"),
-                                           self.gw("neighbor_w/bias"), st), "geom_init_backward")
         self._pdl(False)
+        if sp.g_update and "geom_init" not in self._skip:
+            # geometry-initialisation backward (a full-grid FP32 kernel, ~25 us) and the embedding backward (two small
+            # latency-bound launches, ~17 us) only meet in the optimiser: the former goes to the side stream
+            gst = st
+            if side is not main and self.tail_fork:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                gst = side.cuda_stream
+            check(lib.scann_geom_init_backward(_p(b.ntiles), self.la_grid * self.gi_bwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+                                               _p(self.centers_d), _p(self.centers_w), self.w("neighbor_d/kernel"),
+                                               self.w("neighbor_d/bias"), self.w("neighbor_w/kernel"),
+                                               self.w("neighbor_w/bias"), _p(dg_up), self.gw("neighbor_d/kernel"),
+                                               self.gw("neighbor_d/bias"), self.gw("neighbor_w/kernel"),
+                                               self.gw("neighbor_w/bias"), gst), "geom_init_backward")
         E = sp.embedding_dim
         ring = sp.use_ring
         if sp.feature == "cgcnn":
