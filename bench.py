@@ -395,8 +395,12 @@ def run_ours(args):
     ach = bytes_bwd / (ms_bwd * 1e-3) / 1e9
     pipe_bwd = eng.tc_la_bwd and (eng.la_pipe & 12) == 12 and int(inputs["neighbors"].shape[2]) <= 32 and \
         bool(CFG["model"].get("g_update", True))
+    noup_pipe = eng.tc_la_bwd and getattr(eng, "noup_pipe", False) and int(inputs["neighbors"].shape[2]) <= 32 and \
+        not bool(CFG["model"].get("g_update", True))
     kern = ("la_attn_bwd_pipe_kernel + la_geom_bwd_pipe_kernel (one layer of local-attention backward: warp-specialised "
             "TMA pipelines, la_pipe_bwd.cu)" if pipe_bwd else
+            "la_attn_bwd_pipe_kernel + noupdate_geom_bwd_kernel (one layer of local-attention backward of a g_update = "
+            "False model: pipelined attention kernel, la_pipe_bwd.cu, + filter gradient)" if noup_pipe else
             "la_attn_bwd_tc_kernel + la_geom_bwd_tc_kernel (one scann_la_backward_tc call = one layer of "
             "local-attention backward)" if eng.tc_la_bwd else "la_bwd_simt_kernel")
     # DRAM traffic of the same kernels from the committed `ncu --set full` capture (dram__bytes_read.sum +

@@ -253,6 +253,12 @@ int scann_la_backward_noupdate_tc(int grid, int tile_stride, int mma_rows, const
                                   const int32_t* pair_j, const float* x, const float* proj, const float* g_new,
                                   float* kbuf, const float* WkT, const float* d_ctx, float* dg, float* dq,
                                   float* dx_scatter, float* dbk, const void* attn_drop, int drop_site, void* stream);
+/* g' = swish(rbf(d) @ Wf + bf) * w of a g_update=False layer (attention.py:155) written out as a
+ * [tile_cap * tile_stride, 128] tensor (padding rows zero): the geometry operand of scann_la_forward_pipe (which = 2)
+ * and scann_la_backward_pipe (which = 1) when such a layer runs on the pipelined attention kernels. */
+int scann_noupdate_geom_forward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
+                                const float* pair_d, const float* pair_w, const float* centers_d, const float* Wf,
+                                const float* bf, float* g_out, void* stream);
 /* ... and the gradient of its geometry filter g' = swish(rbf(d) @ Wf + bf) * w: dWf [20,128], dbf accumulated. */
 int scann_noupdate_geom_backward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
                                  const float* pair_d, const float* pair_w, const float* centers_d, const float* Wf,

@@ -48,6 +48,7 @@ PROTOTYPES = {
     "scann_la_forward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 23 + [vp, ci, vp]),
     "scann_la_forward_pipe": (ci, [ci, C.c_longlong, ci] + [vp] * 19 + [vp, ci, vp, vp]),
     "scann_la_backward_noupdate_tc": (ci, [ci, ci, ci] + [vp] * 17 + [vp, ci, vp]),
+    "scann_noupdate_geom_forward": (ci, [vp, ci, ci] + [vp] * 7 + [vp]),
     "scann_noupdate_geom_backward": (ci, [vp, ci, ci] + [vp] * 9 + [vp]),
     "scann_la_backward": (ci, [ci] + [vp] * 28 + [vp]),
     "scann_la_backward_tc": (ci, [ci, ci, ci] + [vp] * 18 + [ci] + [vp] * 9 + [vp, ci, vp]),

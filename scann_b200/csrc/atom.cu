@@ -258,32 +258,46 @@ __global__ void __launch_bounds__(128) embed_bwd_cols_kernel(const float* __rest
 // ---------------------------------------------------------------------------------------------
 // Geometry initialisation (g_update): g0 = swish(rbf_d Wd + bd) * swish(rbf_w Ww + bw)
 // rbf_x[k] = exp(-(x - c_k)^2 / 0.25)                 (scann_model.py:378-389, custom_layers.py:55-65)
+// and the geometry filter of a g_update = False layer: g' = swish(rbf_d Wf + bf) * w   (attention.py:155)
 // ---------------------------------------------------------------------------------------------
-// returns the tile's fill (valid rows are a prefix of the tile slot; wave-balanced plans leave the tail empty)
-__device__ __forceinline__ int geom_stage_rbf(float (*s_rbf)[2 * SCANN_RBF], int* s_c, float* s_d, float* s_w,
-                                               const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
-                                               const float* __restrict__ pair_w, const float* __restrict__ cd,
-                                               const float* __restrict__ cw, size_t base, int stride) {
-    // per-tile pair data -> smem (one coalesced pass), then the 2 x 20 Gaussians of every row
-    int valid = 0;
-    if ((int)threadIdx.x < stride) {
-        const int c = pair_c[base + threadIdx.x];
-        s_c[threadIdx.x] = c;
-        s_d[threadIdx.x] = c >= 0 ? pair_d[base + threadIdx.x] : 0.f;
-        s_w[threadIdx.x] = c >= 0 ? pair_w[base + threadIdx.x] : 0.f;
-        valid = c >= 0;
-    }
-    const int fill = __syncthreads_count(valid);
-    for (int i = threadIdx.x; i < fill * 2 * SCANN_RBF; i += blockDim.x) {
-        const int row = i / (2 * SCANN_RBF), k = i % (2 * SCANN_RBF);
-        const float x = (k < SCANN_RBF) ? s_d[row] : s_w[row];
-        const float c = (k < SCANN_RBF) ? cd[k] : cw[k - SCANN_RBF];
-        const float df = x - c;
-        s_rbf[row][k] = s_c[row] >= 0 ? expf(-(df * df) / 0.25f) : 0.f;
+// The four kernels below walk the pair rows in CHUNKS of GEOM_CR = 64 rows, whatever the tile stride of the plan
+// (rows = ntiles * stride, a multiple of 32; padding rows have pair_c < 0 and may sit anywhere in a chunk).  Per chunk:
+// four threads per row fetch the row's (centre, distance, weight) with unconditional loads -- one round trip -- and
+// write its Gaussians as 16-byte vectors; after ONE barrier thread (n = tid % 128, half = tid / 128) runs over the rows
+// half, half + 2, ... with its weight column in registers and the Gaussians read as LDS.128 broadcasts.
+// (Round 2, first form: one 32-row tile per round, 32 threads fetching centre -> distance / weight as two dependent
+// round trips, three barriers per tile, an integer division per Gaussian: noupdate_geom_fwd 72 us and noupdate_geom_bwd
+// 194 us per layer on the PtGP shape (132 031 pairs), a third of that train step -- gpurun_out/r02ch_launches.csv.)
+#define GEOM_CR 64
+
+template <int NC>   // 20: Gaussians of the distance; 40: distance | Voronoi weight
+__device__ __forceinline__ void geom_stage_chunk(float (*s_rbf)[2 * SCANN_RBF], int* s_c, float* s_w,
+                                                 const int32_t* __restrict__ pair_c, const float* __restrict__ pair_d,
+                                                 const float* __restrict__ pair_w, const float* __restrict__ cd,
+                                                 const float* __restrict__ cw, size_t base, int nrows) {
+    const int row = threadIdx.x & (GEOM_CR - 1), part = threadIdx.x >> 6;
+    int c = -1;
+    float d = 0.f, w = 0.f;
+    if (row < nrows) { c = pair_c[base + row]; d = pair_d[base + row]; w = pair_w[base + row]; }
+    if (part == 0) { s_c[row] = c; s_w[row] = c >= 0 ? w : 0.f; }
+    for (int j = part; j < NC / 4; j += 4) {                 // 16-byte vector j of the row: Gaussians 4j .. 4j + 3
+        const bool dist = 4 * j < SCANN_RBF;
+        const float x = dist ? d : w;
+        const float* cc = dist ? cd + 4 * j : cw + (4 * j - SCANN_RBF);
+        const float d0 = x - cc[0], d1 = x - cc[1], d2 = x - cc[2], d3 = x - cc[3];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c >= 0) v = make_float4(expf(-(d0 * d0) / 0.25f), expf(-(d1 * d1) / 0.25f), expf(-(d2 * d2) / 0.25f),
+                                    expf(-(d3 * d3) / 0.25f));
+        *reinterpret_cast<float4*>(&s_rbf[row][4 * j]) = v;
     }
     __syncthreads();
-    return fill;
 }
+// rows of chunk ch and its first row
+#define GEOM_CHUNK_LOOP(NT, STRIDE)                                                                       \
+    const long long total_rows = (long long)(NT) * (STRIDE);                                              \
+    const int nchunks = (int)((total_rows + GEOM_CR - 1) / GEOM_CR);                                      \
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+#define GEOM_CHUNK_ROWS(ch) ((int)(total_rows - (long long)(ch) * GEOM_CR < GEOM_CR ? total_rows - (long long)(ch) * GEOM_CR : GEOM_CR))
 
 __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __restrict__ ntiles, int stride,
                                                             const int32_t* __restrict__ pair_c,
@@ -293,9 +307,9 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
                                                             const float* __restrict__ Wd, const float* __restrict__ bd,
                                                             const float* __restrict__ Ww, const float* __restrict__ bw,
                                                             float* __restrict__ g0) {
-    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
-    __shared__ int s_c[SCANN_TILE];
-    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
+    __shared__ __align__(16) float s_rbf[GEOM_CR][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
+    __shared__ int s_c[GEOM_CR];
+    __shared__ float s_w[GEOM_CR];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
     float wd[SCANN_RBF], ww[SCANN_RBF];
 #pragma unroll
@@ -306,14 +320,14 @@ __global__ void __launch_bounds__(256) geom_init_fwd_kernel(const int32_t* __res
     const float bdn = bd[n], bwn = bw[n];
     pdl_wait();                                   // weights above are parameters; the plan is a predecessor's output
     const int nt = *ntiles;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t base = (size_t)t * stride;
+    GEOM_CHUNK_LOOP(nt, stride) {
+        const size_t base = (size_t)ch * GEOM_CR;
+        const int nrows = GEOM_CHUNK_ROWS(ch);
         __syncthreads();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
-        for (int row = fill + half; row < stride; row += 2) g0[(base + row) * SCANN_D + n] = 0.f;   // empty tail
+        if (ch + (int)gridDim.x >= nchunks) pdl_trigger();          // last chunk of this CTA: let the next kernel set up
+        geom_stage_chunk<2 * SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cw, base, nrows);
 #pragma unroll 4
-        for (int row = half; row < fill; row += 2) {
+        for (int row = half; row < nrows; row += 2) {                // padding rows: Gaussians are zero, result selected away
             float a = bdn, b = bwn;
             const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
 #pragma unroll
@@ -341,9 +355,9 @@ __global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __
                                                             const float* __restrict__ dg0, float* __restrict__ dWd,
                                                             float* __restrict__ dbd, float* __restrict__ dWw,
                                                             float* __restrict__ dbw) {
-    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
-    __shared__ int s_c[SCANN_TILE];
-    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
+    __shared__ __align__(16) float s_rbf[GEOM_CR][2 * SCANN_RBF];    // rows read as LDS.128 broadcasts
+    __shared__ int s_c[GEOM_CR];
+    __shared__ float s_w[GEOM_CR];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
     float wd[SCANN_RBF], ww[SCANN_RBF], gd[SCANN_RBF], gw[SCANN_RBF];
 #pragma unroll
@@ -357,20 +371,21 @@ __global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __
     float gbd = 0.f, gbw = 0.f;
     pdl_wait();
     const int nt = *ntiles;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t base = (size_t)t * stride;
+    GEOM_CHUNK_LOOP(nt, stride) {
+        const size_t base = (size_t)ch * GEOM_CR;
+        const int nrows = GEOM_CHUNK_ROWS(ch);
         __syncthreads();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();          // last tile of this CTA: let the next kernel set up
-        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cw, base, stride);
+        if (ch + (int)gridDim.x >= nchunks) pdl_trigger();          // last chunk of this CTA: let the next kernel set up
+        geom_stage_chunk<2 * SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cw, base, nrows);
         // the gradient rows of this thread's half are independent loads: keep 8 in flight
-        for (int r8 = half; r8 < fill; r8 += 16) {
+        for (int r8 = half; r8 < nrows; r8 += 16) {
             float dv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dv[q] = dg0[(base + r8 + 2 * q) * SCANN_D + n];
+            for (int q = 0; q < 8; ++q) dv[q] = r8 + 2 * q < nrows ? dg0[(base + r8 + 2 * q) * SCANN_D + n] : 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int row = r8 + 2 * q;
-                if (s_c[row] < 0) continue;
+                if (row >= nrows || s_c[row] < 0) continue;
                 float a = bdn, b = bwn;
                 const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
 #pragma unroll
@@ -400,7 +415,7 @@ __global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __
         }
     }
     pdl_trigger();
-    if ((int)blockIdx.x < nt) {
+    if ((long long)blockIdx.x * GEOM_CR < (long long)nt * stride) {
 #pragma unroll
         for (int k = 0; k < SCANN_RBF; ++k) {
             atomicAdd(dWd + k * SCANN_D + n, gd[k]);
@@ -411,10 +426,54 @@ __global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __
     }
 }
 
+// g_update = False, forward (attention.py:155): g' = swish(rbf(d) @ Wf + bf) * w  as a [rows,128] tensor -- the geometry
+// operand of the pipelined attention kernels (la_pipe.cu / la_pipe_bwd.cu), which take it tile by tile through TMA.
+// (The round-1 attention kernel la_attn_fwd_tc computes the same expression on the fly inside its tile loop; the
+// pipelined kernels' consumers have no issue slots left for 20 more fused multiply-adds per element, profiles/r02_summary.md.)
+// Padding rows of a tile are written as zeros.
+__global__ void __launch_bounds__(256) noupdate_geom_fwd_kernel(const int32_t* __restrict__ ntiles, int stride,
+                                                                const int32_t* __restrict__ pair_c,
+                                                                const float* __restrict__ pair_d,
+                                                                const float* __restrict__ pair_w,
+                                                                const float* __restrict__ cd,
+                                                                const float* __restrict__ Wf, const float* __restrict__ bf,
+                                                                float* __restrict__ g) {
+    __shared__ __align__(16) float s_rbf[GEOM_CR][2 * SCANN_RBF];
+    __shared__ int s_c[GEOM_CR];
+    __shared__ float s_w[GEOM_CR];
+    const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
+    float wf[SCANN_RBF];
+#pragma unroll
+    for (int k = 0; k < SCANN_RBF; ++k) wf[k] = Wf[k * SCANN_D + n];
+    const float bfn = bf[n];
+    pdl_wait();                                   // weights above are parameters; the plan is a predecessor's output
+    const int nt = *ntiles;
+    GEOM_CHUNK_LOOP(nt, stride) {
+        const size_t base = (size_t)ch * GEOM_CR;
+        const int nrows = GEOM_CHUNK_ROWS(ch);
+        __syncthreads();
+        if (ch + (int)gridDim.x >= nchunks) pdl_trigger();
+        geom_stage_chunk<SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cd, base, nrows);
+#pragma unroll 4
+        for (int row = half; row < nrows; row += 2) {
+            float a = bfn;
+            const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
+#pragma unroll
+            for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
+                const float4 rd = rb[k4];
+                a = fmaf(rd.x, wf[4 * k4], a); a = fmaf(rd.y, wf[4 * k4 + 1], a);
+                a = fmaf(rd.z, wf[4 * k4 + 2], a); a = fmaf(rd.w, wf[4 * k4 + 3], a);
+            }
+            g[(base + row) * SCANN_D + n] = s_c[row] >= 0 ? swish_fast(a) * s_w[row] : 0.f;
+        }
+    }
+    pdl_trigger();
+}
+
 // g_update = False (attention.py:155): g' = swish(rbf(d) @ Wf + bf) * w is recomputed in every layer; its only
 // trainable inputs are Wf [20,128] and bf.  dWf += rbf^T d_pre, dbf += sum d_pre with
 // d_pre = dg' * w * swish'(pre), pre = rbf @ Wf + bf (recomputed here from the 8 bytes/pair of raw geometry).
-__global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
+__global__ void __launch_bounds__(256, 2) noupdate_geom_bwd_kernel(const int32_t* __restrict__ ntiles, int stride,
                                                                 const int32_t* __restrict__ pair_c,
                                                                 const float* __restrict__ pair_d,
                                                                 const float* __restrict__ pair_w,
@@ -422,9 +481,9 @@ __global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* _
                                                                 const float* __restrict__ Wf, const float* __restrict__ bf,
                                                                 const float* __restrict__ dg, float* __restrict__ dWf,
                                                                 float* __restrict__ dbf) {
-    __shared__ __align__(16) float s_rbf[SCANN_TILE][2 * SCANN_RBF];
-    __shared__ int s_c[SCANN_TILE];
-    __shared__ float s_d[SCANN_TILE], s_w[SCANN_TILE];
+    __shared__ __align__(16) float s_rbf[GEOM_CR][2 * SCANN_RBF];
+    __shared__ int s_c[GEOM_CR];
+    __shared__ float s_w[GEOM_CR];
     const int n = threadIdx.x & 127, half = threadIdx.x >> 7;
     float wf[SCANN_RBF], gf[SCANN_RBF];
 #pragma unroll
@@ -433,19 +492,20 @@ __global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* _
     float gb = 0.f;
     pdl_wait();
     const int nt = *ntiles;
-    for (int t = blockIdx.x; t < nt; t += gridDim.x) {
-        const size_t base = (size_t)t * stride;
+    GEOM_CHUNK_LOOP(nt, stride) {
+        const size_t base = (size_t)ch * GEOM_CR;
+        const int nrows = GEOM_CHUNK_ROWS(ch);
         __syncthreads();
-        if (t + (int)gridDim.x >= nt) pdl_trigger();
-        const int fill = geom_stage_rbf(s_rbf, s_c, s_d, s_w, pair_c, pair_d, pair_w, cd, cd, base, stride);   // columns 20..39 unused
-        for (int r8 = half; r8 < fill; r8 += 16) {
+        if (ch + (int)gridDim.x >= nchunks) pdl_trigger();
+        geom_stage_chunk<SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cd, base, nrows);
+        for (int r8 = half; r8 < nrows; r8 += 16) {
             float dv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dv[q] = dg[(base + r8 + 2 * q) * SCANN_D + n];
+            for (int q = 0; q < 8; ++q) dv[q] = r8 + 2 * q < nrows ? dg[(base + r8 + 2 * q) * SCANN_D + n] : 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int row = r8 + 2 * q;
-                if (s_c[row] < 0) continue;
+                if (row >= nrows || s_c[row] < 0) continue;
                 float a = bfn;
                 const float4* rb = reinterpret_cast<const float4*>(s_rbf[row]);
                 float4 rd[SCANN_RBF / 4];
@@ -455,7 +515,7 @@ __global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* _
                     a = fmaf(rd[k4].x, wf[4 * k4], a); a = fmaf(rd[k4].y, wf[4 * k4 + 1], a);
                     a = fmaf(rd[k4].z, wf[4 * k4 + 2], a); a = fmaf(rd[k4].w, wf[4 * k4 + 3], a);
                 }
-                const float da = dv[q] * s_w[row] * swish_grad_f(a);
+                const float da = dv[q] * s_w[row] * swish_grad_fast(a);
                 gb += da;
 #pragma unroll
                 for (int k4 = 0; k4 < SCANN_RBF / 4; ++k4) {
@@ -466,7 +526,7 @@ __global__ void __launch_bounds__(256) noupdate_geom_bwd_kernel(const int32_t* _
         }
     }
     pdl_trigger();
-    if ((int)blockIdx.x < nt) {
+    if ((long long)blockIdx.x * GEOM_CR < (long long)nt * stride) {
 #pragma unroll
         for (int k = 0; k < SCANN_RBF; ++k) atomicAdd(dWf + k * SCANN_D + n, gf[k]);
         atomicAdd(dbf + n, gb);
@@ -803,6 +863,18 @@ extern "C" int scann_geom_init_backward(const int32_t* ntiles, int grid, int til
     scann_launch(geom_init_bwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w, centers_d, centers_w,
                  Wd, bd, Ww, bw, dg0, dWd, dbd, dWw, dbw);
     return scann_check_launch("scann_geom_init_backward");
+}
+
+// g' = swish(rbf(d) @ Wf + bf) * w of a g_update = False layer as a [tile_cap * tile_stride, 128] tensor (see
+// noupdate_geom_fwd_kernel): the geometry input of scann_la_forward_pipe / scann_la_backward_pipe for such a layer.
+extern "C" int scann_noupdate_geom_forward(const int32_t* ntiles, int grid, int tile_stride, const int32_t* pair_c,
+                                           const float* pair_d, const float* pair_w, const float* centers_d,
+                                           const float* Wf, const float* bf, float* g_out, void* stream) {
+    if (tile_stride != 32 && tile_stride != 64 && tile_stride != 128) { scann_set_error("noupdate_geom_forward: tile_stride must be 32, 64 or 128"); return 1; }
+    if (grid <= 0) return 0;
+    scann_launch(noupdate_geom_fwd_kernel, dim3(grid), dim3(256), 0, stream, ntiles, tile_stride, pair_c, pair_d, pair_w,
+                 centers_d, Wf, bf, g_out);
+    return scann_check_launch("scann_noupdate_geom_forward");
 }
 
 // Weight gradient of the g_update = False geometry (see noupdate_geom_bwd_kernel): dWf [20,128], dbf [128]

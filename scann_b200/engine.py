@@ -127,6 +127,10 @@ class Engine:
         self.la_pipe_built = 15
         self.la_pipe = (int(os.environ.get("SCANN_LA_PIPE", str(self.la_pipe_built))) & self.la_pipe_built
                         if (self.tc_la_fwd and self.tc_la_bwd) else 0)
+        # g_update = False layers (model_ptgp.yaml) on the pipelined ATTENTION kernels: their geometry operand
+        # g' = swish(rbf(d) Wf + bf) * w is written out per layer by scann_noupdate_geom_forward (training saves it anyway)
+        # and read through TMA like the updated geometry of a g_update = True layer.  Needs both attention bits of la_pipe.
+        self.noup_pipe = os.environ.get("SCANN_NOUP_PIPE", "1") == "1" and (self.la_pipe & 6) == 6
         self.side_stream = torch.cuda.Stream(device=self.device)
         self._prep_event = None
         # local-attention kernels with four warp groups per CTA where the plan's tiles hold <= 48 rows (bit mask:
@@ -314,7 +318,7 @@ class Engine:
         # (32-row slots need the batched weight-gradient launch: the per-layer la_wgrad_tc kernels of the unbatched
         # variant only know 64 / 128-row slots)
         if N <= 32 and tc and self.use_chain and self.use_wgrad_batch and (
-                pref == 32 or (pref == 0 and self.la_pipe and self.spec.g_update)):
+                pref == 32 or (pref == 0 and self.la_pipe and (self.spec.g_update or self.noup_pipe))):
             stride = 32
         tile_rows = stride
         # (the pipelined kernels on 32-row slots keep six tiles in flight per SM: full tiles, no wave balancing)
@@ -534,6 +538,8 @@ class Engine:
         ws = {}
         nsave = L + 1 if training else 2
         ws["g"] = [torch.empty(rows, D, **f) for _ in range(nsave)] if self.spec.g_update else []
+        if not self.spec.g_update and not training and self.noup_pipe and b.stride == 32:
+            ws["gsave"] = [torch.empty(rows, D, **f)]         # g' of the current layer (pipelined attention kernel)
         ws["x"] = [torch.empty(R, D, **f) for _ in range(L + 1 if training else 2)]
         nl = L if training else 1
         ws["proj"] = [torch.empty(R, 3 * D, **f) for _ in range(nl)]
@@ -859,6 +865,19 @@ class Engine:
                     self.w(f"{la}/layer_norm/beta"), _p(g_out), _p(ctxpre), _p(out), _p(attn)),
                     _p(ws["pre"][l]) if save else 0, _p(ws["kk"][l]) if save else 0, self._adrop(training, l), st)
                 self.launches += 2
+            elif self.noup_pipe and b.stride == 32 and "gsave" in ws:
+                # g_update = False on the pipelined attention kernel: g' written out, then read by TMA
+                gbuf = ws["gsave"][l if training else 0]
+                check(lib.scann_noupdate_geom_forward(
+                    _p(b.ntiles), self.la_grid * self.gi_fwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w),
+                    _p(self.centers_d), self.w(fg), self.w(f"{la}/filter_geo/bias"), _p(gbuf), st), "noupdate_geom_forward")
+                check(lib.scann_la_forward_pipe(
+                    self.la_grid, b.rows, 2, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(x_in), _p(proj), 0, 0,
+                    self.w(f"{la}/key/kernel"), self.w(f"{la}/key/bias"), 0, 0, self.w(f"{la}/layer_norm/gamma"),
+                    self.w(f"{la}/layer_norm/beta"), _p(gbuf), _p(ctxpre), _p(out), _p(attn), 0,
+                    _p(ws["kk"][l]) if training else 0, *self._adrop(training, l), _p(self.status), st),
+                    "la_forward_pipe")
+                self.launches += 2
             else:
                 check(lib.scann_la_forward_noupdate_tc(
                     self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
@@ -1152,13 +1171,20 @@ class Engine:
             self._ev("la_backward", True)
             if not sp.g_update:
                 # SCANN without geometry update: attention part only, then the filter_geo [20,128] gradient
-                check(lib.scann_la_backward_noupdate_tc(
-                    self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
-                    _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["gsave"][l]), _p(ws["kk"][l]),
-                    self.wT(f"{la}/key/kernel"), _p(ws["d_ctx"]), _p(ws["dg"][0]), _p(dq), _p(dx_sc),
-                    self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_noupdate_tc")
+                if self.noup_pipe and b.stride == 32:
+                    check(lib.scann_la_backward_pipe(
+                        self.la_grid, b.rows, 1, _p(b.ntiles), _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]),
+                        0, _p(ws["gsave"][l]), _p(ws["kk"][l]), 0, 0, self.wT(f"{la}/key/kernel"), 0, _p(ws["d_ctx"]),
+                        _p(ws["dg"][0]), 0, 0, _p(dq), 0, 0, _p(dx_sc), 0, 0, self.gw(f"{la}/key/bias"),
+                        *self._adrop(True, l), _p(self.status), st), "la_backward_pipe")
+                else:
+                    check(lib.scann_la_backward_noupdate_tc(
+                        self.la_grid, b.stride, b.mma_rows, _p(b.ntiles), _p(b.tile_a0), _p(b.tile_a1), _p(b.cnt), _p(b.rowptr),
+                        _p(b.pair_c), _p(b.pair_j), _p(ws["x"][l]), _p(ws["proj"][l]), _p(ws["gsave"][l]), _p(ws["kk"][l]),
+                        self.wT(f"{la}/key/kernel"), _p(ws["d_ctx"]), _p(ws["dg"][0]), _p(dq), _p(dx_sc),
+                        self.gw(f"{la}/key/bias"), *self._adrop(True, l), st), "la_backward_noupdate_tc")
                 check(lib.scann_noupdate_geom_backward(
-                    _p(b.ntiles), self.la_grid, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
+                    _p(b.ntiles), self.la_grid * self.gi_bwd_mult, b.stride, _p(b.pair_c), _p(b.pair_d), _p(b.pair_w), _p(self.centers_d),
                     self.w(fg), self.w(f"{la}/filter_geo/bias"), _p(ws["dg"][0]), self.gw(fg),
                     self.gw(f"{la}/filter_geo/bias"), st), "noupdate_geom_backward")
                 self.launches += 2

@@ -407,9 +407,13 @@ def test_ga_norm_false_fullerene_config():
     assert rel(y, y_ref.ravel()) <= TOL_OUT and rel(ga, ga_ref[..., 0]) <= ga_tolerance(spec, lay, arena, inputs)
 
 
-def test_scann_without_geometry_update_and_ring_features():
+@pytest.mark.parametrize("noup_pipe", ["1", "0"])
+def test_scann_without_geometry_update_and_ring_features(monkeypatch, noup_pipe):
     """model_ptgp.yaml family: g_update=False (attention.py:155) + use_ring=True (scann_model.py:367-371).
-    The yaml lacks g_update / gaussian_d (KeyError in the reference as shipped), so they are supplied."""
+    The yaml lacks g_update / gaussian_d (KeyError in the reference as shipped), so they are supplied.
+    Both implementations: the pipelined attention kernels fed by scann_noupdate_geom_forward (default) and the
+    round-1 kernels that expand the geometry inside their tile loop (SCANN_NOUP_PIPE=0)."""
+    monkeypatch.setenv("SCANN_NOUP_PIPE", noup_pipe)
     cfg = get_config("ptgp")
     cfg["model"].update(g_update=False, gaussian_d=4.0, n_attention=3)
     spec = model_spec(cfg)
@@ -422,6 +426,7 @@ def test_scann_without_geometry_update_and_ring_features():
     assert rel(y, y_ref.ravel()) <= TOL_OUT
     assert rel(ga, ga_ref[..., 0]) <= TOL_OUT
     needs_default_engine(eng)
+    assert b.stride == (32 if noup_pipe == "1" else 64) and eng.noup_pipe == (noup_pipe == "1")
     # train step of the same variant: every gradient against the oracle's reverse-mode autodiff
     w = lay.to_dict(arena)
     l2n = [e.name for e in lay if e.l2]

@@ -13,7 +13,8 @@ cfg = get_config(wl)
 if wl == "ptgp":      # model_ptgp.yaml lacks these two keys (KeyError in the reference as shipped)
     cfg["model"].update(g_update=False, gaussian_d=4.0)
 m = create_model(cfg); eng = m.engine
-inp, tgt = make_batch(wl, 0, B=B) if B else make_batch(wl, 0)
+ring = bool(cfg["model"].get("use_ring"))
+inp, tgt = make_batch(wl, 0, B=B, use_ring=ring) if B else make_batch(wl, 0, use_ring=ring)
 b = eng.load_batch(inp, plan=False)
 t = torch.from_numpy(tgt).cuda()
 for _ in range(4): eng.train_step(b, t, 5e-4, replan=True)
