@@ -389,6 +389,14 @@ def run_ours(args):
     # algorithmic bytes per launch: valid pairs P and atoms A only
     bytes_bwd = 1540.0 * P_valid + 1028.0 * A_valid
     bytes_fwd = 1028.0 * P_valid + 1028.0 * A_valid
+    if not bool(CFG["model"].get("g_update", True)):
+        # g_update = False (attention.py:155): no per-pair geometry tensor exists algorithmically -- a pair is its distance,
+        # weight, neighbour index and mask (16 bytes, BASELINE.md section 3: 21 MB per layer on the full PtGP shape); the
+        # per-atom rows are x, q, out forward and d_ctx, dq, dx backward.  This implementation materialises g' (512 bytes
+        # per pair written and read back), so its fraction of THIS roofline is small by construction: the layer is bound
+        # by the 3xTF32 key projection (550 flop per byte), see tensor_view.
+        bytes_fwd = 16.0 * P_valid + 1028.0 * A_valid
+        bytes_bwd = 16.0 * P_valid + 1540.0 * A_valid
     n_bwd, ms_bwd = prof.get("la_backward", (0, float("nan")))
     n_fwd, ms_fwd = prof.get("la_forward", (0, float("nan")))
     n_wg, ms_wg = prof.get("wgrad_batch", (0, float("nan")))
@@ -447,8 +455,11 @@ def run_ours(args):
     if n_gaf:
         bytes_ga = 2 * 516.0 * A_valid + 512.0 * B
         roof["global_attention"] = {
-            "kernel": "ga_head_fwd_staged_kernel / ga_head_bwd_staged_kernel (GlobalAttention + property head, one CTA per "
-                      "structure, its query | key block staged in shared memory; ga.cu)",
+            "kernel": ("ga_head_fwd_staged_kernel / ga_head_bwd_staged_kernel (GlobalAttention + property head, one CTA per "
+                       "structure, its query | key block staged in shared memory; ga.cu)"
+                       if int(inputs["neighbors"].shape[1]) * 1024 + 8192 <= 200 * 1024 else
+                       "ga_head_fwd_kernel / ga_head_bwd_kernel (GlobalAttention + property head, one CTA per structure; the "
+                       "query | key block of a structure this large does not fit shared memory)"),
             "forward": {"achieved": bytes_ga / (ms_gaf * 1e-3) / 1e9, "ms_per_launch": ms_gaf,
                         "frac": bytes_ga / (ms_gaf * 1e-3) / 1e9 / peaks["hbm_gbs"], "algorithmic_bytes": bytes_ga},
             "backward": (None if not n_gab else
