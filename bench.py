@@ -423,7 +423,7 @@ def run_ours(args):
     # tensor-core view of the same kernels: 3xTF32 = 3 tensor-core products per algorithmic product
     # (two [P,128]x[128,128] input-gradient GEMMs per layer = 65 536 flops per valid pair; the weight
     # gradients are a separate launch)
-    flops_bwd = 3.0 * 65536.0 * P_valid
+    flops_bwd = 3.0 * (65536.0 if bool(CFG["model"].get("g_update", True)) else 32768.0) * P_valid    # one GEMM without geometry update
     roof = {"bound": "hbm", "kernel": kern, "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": ach / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
             "launches_timed": n_bwd, "ms_per_launch": ms_bwd,
