@@ -15,3 +15,6 @@ timeout 400 python tools/skip_time.py > $O/${TAG}_skip_time.log 2>&1; cat $O/${T
 python tools/infer_loop.py 128 3 train > $O/${TAG}_plain.log 2>&1 && \
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches.csv python tools/infer_loop.py 128 3 train > $O/${TAG}_ncu1.log 2>&1
 echo "launch list rc=$?"; python tools/launch_summary.py $O/${TAG}_launches.csv 3 > $O/${TAG}_launches.md; head -24 $O/${TAG}_launches.md
+python tools/wl_loop.py ptgp 2 train > $O/${TAG}_ptgp_plain.log 2>&1 && \
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${TAG}_launches_ptgp.csv python tools/wl_loop.py ptgp 2 train > $O/${TAG}_ncu_ptgp.log 2>&1
+python tools/launch_summary.py $O/${TAG}_launches_ptgp.csv 2 > $O/${TAG}_launches_ptgp.md; head -14 $O/${TAG}_launches_ptgp.md
