@@ -377,7 +377,9 @@ __global__ void __launch_bounds__(256, 2) geom_init_bwd_kernel(const int32_t* __
         __syncthreads();
         if (ch + (int)gridDim.x >= nchunks) pdl_trigger();          // last chunk of this CTA: let the next kernel set up
         geom_stage_chunk<2 * SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cw, base, nrows);
-        // the gradient rows of this thread's half are independent loads: keep 8 in flight
+        // the gradient rows of this thread's half are independent loads: keep 8 in flight.  (Batches of 4 with the next
+        // batch prefetched -- the form that pays in noupdate_geom_bwd_kernel -- are neutral here: 128 registers either way,
+        // gpurun_out/r02da_ab.log.)
         for (int r8 = half; r8 < nrows; r8 += 16) {
             float dv[8];
 #pragma unroll
@@ -498,10 +500,17 @@ __global__ void __launch_bounds__(256, 2) noupdate_geom_bwd_kernel(const int32_t
         __syncthreads();
         if (ch + (int)gridDim.x >= nchunks) pdl_trigger();
         geom_stage_chunk<SCANN_RBF>(s_rbf, s_c, s_w, pair_c, pair_d, pair_w, cd, cd, base, nrows);
+        // gradient rows in batches of 8, the NEXT batch's loads issued before the current one is consumed (they were one
+        // exposed HBM round trip per batch: 4 of the ~10 us a chunk took, gpurun_out/r02cz_launches_ptgp.csv)
+        float nx[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) nx[q] = half + 2 * q < nrows ? dg[(base + half + 2 * q) * SCANN_D + n] : 0.f;
         for (int r8 = half; r8 < nrows; r8 += 16) {
             float dv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) dv[q] = r8 + 2 * q < nrows ? dg[(base + r8 + 2 * q) * SCANN_D + n] : 0.f;
+            for (int q = 0; q < 8; ++q) dv[q] = nx[q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nx[q] = r8 + 16 + 2 * q < nrows ? dg[(base + r8 + 16 + 2 * q) * SCANN_D + n] : 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int row = r8 + 2 * q;
