@@ -1,8 +1,10 @@
 """Generates tests/golden/*.npz from the fp64 oracle (oracle/scann_oracle.py).
 
-The reference itself cannot run here (TensorFlow absent) and ships no golden
-vectors (F8), so these fixtures pin the ORACLE against accidental change and give the GPU
-tests committed expected values; they do not pin the oracle to TensorFlow ("parity unpinned").
+TensorFlow is absent and the reference ships no golden vectors (F8).  The fixtures are written by
+the oracle; ``tests/test_reference_graph.py::test_golden_vectors_equal_the_reference_graph`` then runs the
+reference's OWN ``create_model`` graph (imported from /root/reference on the functional TensorFlow stand-in
+``tests/tf_shim.py``) on the same seeded cases and requires equality at fp64 round-off, so the committed values are
+pinned to reference-run code at the graph level (TensorFlow's own primitive kernels stay unpinned).
 
     python tests/golden/make_golden.py
 """

@@ -127,3 +127,56 @@ def load_reference():
             del sys.modules[k]
         sys.modules.update(saved)
     return _cache
+
+
+_graph_cache = None
+
+
+def load_reference_graph():
+    """The reference's own GRAPH code on the functional TensorFlow stand-in ``tests/tf_shim.py`` (PyTorch-CPU
+    primitives; pymatgen / openbabel / ase ... stay inert stubs).  -> dict with the reference's ``create_model``
+    (scann/models/scann_model.py:329-453), ``LocalAttention`` / ``GlobalAttention`` / ``ResidualNorm``
+    (scann/layers/attention.py), ``GaussianExpansion`` / ``gather_shape`` / ``mrelu`` (scann/layers/custom_layers.py),
+    ``root_mean_squared_error`` (scann/layers/losses.py) and the shim module (``shim.session(...)`` runs them)."""
+    global _graph_cache
+    if _graph_cache is not None:
+        return _graph_cache
+    if not reference_available():
+        raise FileNotFoundError(REFERENCE_ROOT)
+    from tests import tf_shim
+    saved = {k: v for k, v in sys.modules.items()
+             if k == "scann" or k.startswith("scann.") or k == "tensorflow" or k.startswith("tensorflow.")}
+    for k in saved:
+        del sys.modules[k]
+    finder = _StubFinder()
+    really_missing = []
+    for root in STUB_ROOTS:
+        if root == "tensorflow":
+            continue
+        try:
+            importlib.import_module(root)
+        except Exception:
+            really_missing.append(root)
+    sys.modules.update(tf_shim.build_modules())
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        sm = importlib.import_module("scann.models.scann_model")
+        att = importlib.import_module("scann.layers.attention")
+        cl = importlib.import_module("scann.layers.custom_layers")
+        ls = importlib.import_module("scann.layers.losses")
+        for m in (sm, att, cl, ls):
+            assert os.path.realpath(m.__file__).startswith(os.path.realpath(REFERENCE_ROOT))
+        _graph_cache = {"create_model": sm.create_model, "scann_model": sm, "attention": att, "custom_layers": cl,
+                        "LocalAttention": att.LocalAttention, "GlobalAttention": att.GlobalAttention,
+                        "ResidualNorm": att.ResidualNorm, "GaussianExpansion": cl.GaussianExpansion,
+                        "gather_shape": cl.gather_shape, "mrelu": cl.mrelu,
+                        "root_mean_squared_error": ls.root_mean_squared_error, "shim": tf_shim}
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        sys.meta_path.remove(finder)
+        for k in [k for k in sys.modules if k == "scann" or k.startswith("scann.") or k == "tensorflow"
+                  or k.startswith("tensorflow.") or k.split(".")[0] in really_missing]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return _graph_cache

