@@ -247,3 +247,71 @@ def test_reference_graph_in_fp32_sets_the_noise_floor(ref):
     e_ref, e_orc = relerr(r32["y"], y64), relerr(y32, y64)
     assert 1e-8 < e_ref <= 2e-5 and e_ref <= 3 * e_orc + 1e-6 and e_orc <= 3 * e_ref + 1e-6
     assert relerr(r32["ga"], ga64) <= 1e-5
+
+
+def _graph_layers(ref, cfg, spec, lay, w, inputs):
+    """Top-level layers of the reference's create_model run, in graph (call) order."""
+    r = run_reference_graph(ref, cfg, w, inputs, None, grads=False)
+    return list(r["session"].top_layers.items())
+
+
+@pytest.mark.parametrize("name", ["qm9_l2", "ptgp_noupdate_ring", "qm9_cgcnn", "qm9_mrelu_head", "qm9_no_attn_norm"])
+def test_arena_order_and_model_config_follow_the_reference_graph(ref, name):
+    """(1) ``ParamLayout`` lists the tensors in the reference's Keras order: layers in graph order, inside a layer its
+    own variables, then its sub-layers in attribute-assignment order (attention.py:25-35,95-113,260-262) -- the
+    ``weight_names`` order of a Keras HDF5 file.  (2) The ``model_config`` JSON that ``model.save`` writes names the
+    same layers (class, name) in the same order, and carries every key / value of the reference layers' OWN
+    ``get_config()`` (attention.py:42-50,218-231,320-331; custom_layers.py:67-75)."""
+    import json
+    from scann_b200.model import keras_model_config, spec_from_model_config
+    cfg, spec, lay, w, inputs, target = case(**GRAPH_CASES[name])
+    with ref["shim"].session(inputs, {k: torch.tensor(v, dtype=torch.float64) for k, v in w.items()}) as s:
+        ref["create_model"](cfg)
+        layers = list(s.top_layers.items())
+        order = [n for _, l in layers for n in l.weights_order()]
+        ref_cfg = {n: (type(l).__name__, l.get_config()) for n, l in layers}
+    assert order == [e.name for e in lay]
+    mc = json.loads(keras_model_config(spec))["config"]["layers"]
+    skip = {"Lambda", "Multiply"}                              # wiring-only layers are not in the written config
+    assert [(c, n) for n, (c, _) in ref_cfg.items() if c not in skip] == [(l["class_name"], l["name"]) for l in mc]
+    for l in mc:
+        cls, rc = ref_cfg[l["name"]]
+        for k, v in rc.items():
+            if k == "activation" and callable(v):
+                v = v.__name__
+            got = l["config"][k]
+            if k == "centers":
+                np.testing.assert_allclose(np.asarray(got), np.asarray(v, np.float64), rtol=1e-6)
+            else:
+                assert got == v, (l["name"], k, got, v)
+    import dataclasses
+    want = dataclasses.replace(spec, n_atoms=0) if spec.feature == "cgcnn" else spec     # cgcnn graphs have no vocabulary
+    assert spec_from_model_config(json.dumps({"config": {"layers": mc}})) == want
+
+
+def test_layer_mirrors_keep_the_reference_constructor_config_and_weight_order(ref):
+    """scann_b200.layers.{LocalAttention, ResidualNorm, GlobalAttention, GaussianExpansion}: same constructor
+    arguments, same ``get_config`` items and the same ``set_weights`` order as the reference's own classes."""
+    from scann_b200 import layers as mine
+    shim = ref["shim"]
+    spec = model_spec(get_config("qm9"))
+    lay = ParamLayout(spec)
+    wt = {k: torch.tensor(v, dtype=torch.float64) for k, v in lay.to_dict(lay.randomize_arena(1)).items()}
+    la_kw = dict(v_proj=False, kq_proj=True, dim=128, num_head=8, activation="swish", dropout=False, g_update=True)
+    ga_kw = dict(v_proj=False, kq_proj=True, dim=128, norm=False)
+    centers = np.linspace(0, 4.0, 20, dtype="float32")
+    with shim.session({}, wt):
+        pairs = [(ref["LocalAttention"](**la_kw), mine.LocalAttention(**la_kw)),
+                 (ref["ResidualNorm"](128), mine.ResidualNorm(128)),
+                 (ref["GlobalAttention"](**ga_kw), mine.GlobalAttention(**ga_kw)),
+                 (ref["GaussianExpansion"](centers), mine.GaussianExpansion(centers))]
+        for theirs, ours in pairs:
+            a = {k: v for k, v in theirs.get_config().items() if k != "name"}
+            b = {k: v for k, v in ours.get_config().items() if k != "name"}
+            assert set(a) == set(b), type(theirs).__name__
+            for k in a:
+                assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), (type(theirs).__name__, k)
+            if hasattr(ours, "weight_names"):
+                p = theirs.path()
+                assert [n[len(p) + 1:] for n in theirs.weights_order()] == list(ours.weight_names)
+        assert pairs[3][0].width == pairs[3][1].width == 0.25

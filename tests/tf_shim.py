@@ -284,7 +284,19 @@ class Layer:
         if isinstance(value, Layer) and not key.startswith("_") and value.__dict__.get("_parent") is None:
             value.__dict__["_parent"] = self
             value.__dict__["_attr"] = key
+            self.__dict__.setdefault("_tracked", []).append(value)      # Keras tracks sub-layers in assignment order
         object.__setattr__(self, key, value)
+
+    OWN_WEIGHTS: tuple = ()
+
+    def weights_order(self) -> List[str]:
+        """Names (full paths) of ``layer.weights`` in Keras order: the layer's own variables, then those of its
+        tracked sub-layers in attribute-assignment order -- the order of ``weight_names`` in a Keras HDF5 file."""
+        p = self.path()
+        out = [f"{p}/{w}" for w in self.OWN_WEIGHTS]
+        for sub in self.__dict__.get("_tracked", []):
+            out += sub.weights_order()
+        return out
 
     # -- naming
     def _own_name(self) -> str:
@@ -333,6 +345,13 @@ def _activation(act):
 
 
 class Dense(Layer):
+    OWN_WEIGHTS = ("kernel", "bias")
+
+    def get_config(self):
+        act = self.activation
+        return {"name": self.name, "units": self.units,
+                "activation": "linear" if act is None else act if isinstance(act, str) else getattr(act, "__name__", "?")}
+
     def __init__(self, units, activation=None, kernel_regularizer=None, **kwargs):
         super().__init__(**kwargs)
         self.units = int(units)
@@ -350,6 +369,11 @@ class Dense(Layer):
 
 
 class Embedding(Layer):
+    OWN_WEIGHTS = ("embeddings",)
+
+    def get_config(self):
+        return {"name": self.name, "input_dim": self.input_dim, "output_dim": self.output_dim}
+
     def __init__(self, input_dim, output_dim, **kwargs):
         super().__init__(**kwargs)
         self.input_dim, self.output_dim = int(input_dim), int(output_dim)
@@ -365,6 +389,9 @@ class Dropout(Layer):
         super().__init__(**kwargs)
         self.rate = float(rate)
 
+    def get_config(self):
+        return {"name": self.name, "rate": self.rate}
+
     def call(self, x):
         p = self.path()
         _S().dropout_sites.append(p)
@@ -373,6 +400,8 @@ class Dropout(Layer):
 
 
 class LayerNormalization(Layer):
+    OWN_WEIGHTS = ("gamma", "beta")
+
     def __init__(self, epsilon=1e-3, **kwargs):
         super().__init__(**kwargs)
         self.epsilon = float(epsilon)
@@ -426,6 +455,7 @@ class Sequential(Layer):
             counters[base] = i + 1
             l.__dict__["_parent"] = self
             l.__dict__["_seq_name"] = base if i == 0 else f"{base}_{i}"
+            self.__dict__.setdefault("_tracked", []).append(l)
 
     def path(self) -> str:
         parent = self.__dict__.get("_parent")
