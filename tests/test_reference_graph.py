@@ -315,3 +315,127 @@ def test_layer_mirrors_keep_the_reference_constructor_config_and_weight_order(re
                 p = theirs.path()
                 assert [n[len(p) + 1:] for n in theirs.weights_order()] == list(ours.weight_names)
         assert pairs[3][0].width == pairs[3][1].width == 0.25
+
+
+# ------------------------------------------------------------------------------------------------ training shell
+class _FakeHistory:
+    def __init__(self):
+        self.history = {"loss": [0.9, 0.5, 0.4], "mae": [0.7, 0.31, 0.33], "val_mae": [0.8, 0.45, 0.41]}
+
+
+class _FakeModel:
+    """Stands in for the compiled Keras model / the accelerated model: records what the shell asks of it."""
+
+    def __init__(self, log):
+        self.log = log
+
+    def compile(self, **kw):
+        self.log["compile"] = kw
+
+    def fit(self, x, **kw):
+        self.log["fit"] = (x, kw)
+        return _FakeHistory()
+
+    def load_weights(self, path):
+        self.log["loaded"] = path
+
+    def predict(self, inputs):
+        return (inputs["neighbor_distance"].sum((1, 2)) * 0.01 - inputs["atomic"].sum(1) * 0.003).reshape(-1, 1)
+
+
+class _Iter:
+    def __init__(self, n_batches, seed):
+        self.b = [make_batch("qm9", seed + i, B=3) for i in range(n_batches)]
+
+    def __len__(self):
+        return len(self.b)
+
+    def __getitem__(self, i):
+        return self.b[i]
+
+
+def _numbers(obj):
+    return {k: v for k, v in vars(obj).items() if isinstance(v, (int, float, str, bool)) and not k.startswith("_")}
+
+
+@pytest.mark.parametrize("scheduler", ["sgdr", "cosine"])
+def test_training_shell_follows_the_reference_train_and_evaluate(ref, scheduler, tmp_path, monkeypatch):
+    """The reference's own ``SCANN.create_callbacks`` / ``train`` / ``evaluate`` (scann_model.py:163-313) executed
+    with recording stand-ins for Keras' compile / fit / callbacks / optimisers, beside ``scann_b200.model.SCANN``'s:
+    same callbacks with the same arguments, same learning-rate schedule arguments, same ``config.yaml``, the best
+    checkpoint reloaded from the same path before evaluation (the reference deletes its model after fit), same
+    ``report.txt`` and ``hist_data.npy``."""
+    import yaml
+    from scann_b200 import callbacks as C
+    from scann_b200 import model as mine
+    epochs = 40
+
+    def config(root):
+        cfg = get_config("qm9")
+        cfg["hyper"].update(save_path=str(root / "run"), scheduler=scheduler, lr=5e-4, min_lr=1e-4)
+        return cfg
+
+    runs = {}
+    for who in ("reference", "mine"):
+        root = tmp_path / who
+        root.mkdir()
+        log = {}
+        cls = ref["SCANN"] if who == "reference" else mine.SCANN
+        obj = object.__new__(cls)
+        obj.config, obj.mean, obj.std = config(root), 0.25, 1.5
+        obj.model = _FakeModel(log)
+        obj.trainIter, obj.validIter, obj.testIter = _Iter(5, 100), _Iter(2, 200), _Iter(3, 300)
+        best = root / "run_homo" / "models" / "model_homo.h5"
+        if who == "reference":
+            with ref["shim"].session({}, {}):
+                obj.train(epochs=epochs)
+                assert not hasattr(obj, "model")                       # scann_model.py:243-245
+                monkeypatch.setattr(ref["scann_model"], "load_model",
+                                    lambda path, custom_objects=None: (log.__setitem__("loaded", path), _FakeModel(log))[1])
+                obj.evaluate()
+        else:
+            obj.train(epochs=epochs)
+            best.write_bytes(b"")                                      # what ModelCheckpoint would have left
+            obj.evaluate()
+        runs[who] = dict(log=log, root=root, cfg=yaml.safe_load(open(root / "run_homo" / "config.yaml")),
+                         report=open(root / "run_homo" / "report.txt").read(),
+                         hist=np.load(root / "run_homo" / "hist_data.npy", allow_pickle=True))
+    r, m = runs["reference"], runs["mine"]
+    # config.yaml: same content up to the run directory
+    for d in (r, m):
+        d["cfg"]["hyper"].pop("save_path")
+    assert r["cfg"] == m["cfg"]
+    # best checkpoint path relative to the run root
+    assert os.path.relpath(r["log"]["loaded"], r["root"]) == os.path.relpath(m["log"]["loaded"], m["root"]) \
+        == os.path.join("run_homo", "models", "model_homo.h5")
+    # learning rate: a float under SGDR (the callback drives it), CosineDecay(lr, 0.5 * steps * epochs, alpha) otherwise
+    adam = r["log"]["compile"]["optimizer"]
+    assert type(adam).__name__ == "Adam" and adam.kwargs == {"decay": 1e-5}
+    assert r["log"]["compile"]["loss"] is ref["scann_model"].root_mean_squared_error
+    lr_ref, lr_mine = adam.args[0], m["log"]["compile"]["optimizer"]
+    if scheduler == "sgdr":
+        assert lr_ref == lr_mine == 5e-4
+    else:
+        assert type(lr_ref).__name__ == "CosineDecay" and isinstance(lr_mine, mine.CosineDecay)
+        assert lr_ref.args == (lr_mine.lr0, lr_mine.decay_steps) == (5e-4, 0.5 * 5 * epochs)
+        assert lr_ref.kwargs["alpha"] == lr_mine.alpha == 1e-4 / 5e-4
+    # fit: same iterators, epochs, callbacks
+    (xr, kr), (xm, km) = r["log"]["fit"], m["log"]["fit"]
+    assert len(xr) == len(xm) == 5 and kr["epochs"] == km["epochs"] == epochs
+    assert len(kr["validation_data"]) == len(km["validation_data"]) == 2 and kr["shuffle"] is False
+    cr, cm = kr["callbacks"], km["callbacks"]
+    assert [type(c).__name__ for c in cr] == [type(c).__name__ for c in cm]
+    ck_r, ck_m = cr[0].kwargs, cm[0]
+    assert os.path.relpath(ck_r["filepath"], r["root"]) == os.path.relpath(ck_m.filepath, m["root"])
+    assert (ck_r["monitor"], ck_r["save_weights_only"], ck_r["save_best_only"]) == \
+        (ck_m.monitor, ck_m.save_weights_only, ck_m.save_best_only) == ("val_mae", False, True)
+    assert cr[1].kwargs == {"monitor": "val_mae", "patience": 200} and (cm[1].monitor, cm[1].patience) == ("val_mae", 200)
+    if scheduler == "sgdr":
+        assert isinstance(cr[2], ref["SGDRC"]) and isinstance(cm[2], C.SGDRC)
+        assert _numbers(cr[2]) == _numbers(cm[2])
+        assert cr[3].args[0].__self__ is cr[2] and cm[3].schedule.__self__ is cm[2]          # lr.lr_scheduler
+    # evaluation: same report, same saved history
+    assert r["report"] == m["report"]
+    np.testing.assert_allclose(np.asarray(r["hist"][0], np.float64), np.asarray(m["hist"][0], np.float64), rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(r["hist"][1], np.float64), np.asarray(m["hist"][1], np.float64), rtol=0)
+    assert r["hist"][2] == m["hist"][2]

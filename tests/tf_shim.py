@@ -502,8 +502,22 @@ class L2:
 
 
 class Callback:
-    def __init__(self, *a, **k):
+    """Base of the reference's own callbacks (SGDRC, LearningRateLoggingCallback) and of the RECORDING stand-ins for
+    the stock Keras callbacks / optimisers below: those keep their constructor arguments for the shell-level tests
+    (what the reference's ``create_callbacks`` / ``train`` asks Keras for); none of them trains anything."""
+
+    def __init__(self, *args, **kwargs):
         self.model = None
+        self.args, self.kwargs = args, kwargs
+
+
+def _recording(name):
+    return type(name, (Callback,), {})
+
+
+class _Recorder:
+    def __init__(self, *args, **kwargs):
+        self.args, self.kwargs = args, kwargs
 
 
 # ----------------------------------------------------------------------------------------------- module tree
@@ -526,9 +540,13 @@ def build_modules() -> Dict[str, types.ModuleType]:
                    if axis is None else _t(x).mean(axis), square=lambda x: _t(x) ** 2,
                    sum=lambda x, axis=None: reduce_sum(x, axis), epsilon=lambda: 1e-7)
     regularizers = _mod("tensorflow.keras.regularizers", l2=L2, L2=L2)
-    callbacks = _mod("tensorflow.keras.callbacks", Callback=Callback, ModelCheckpoint=type("ModelCheckpoint", (Callback,), {}),
-                     EarlyStopping=type("EarlyStopping", (Callback,), {}), CSVLogger=type("CSVLogger", (Callback,), {}),
-                     ReduceLROnPlateau=type("ReduceLROnPlateau", (Callback,), {}))
+    callbacks = _mod("tensorflow.keras.callbacks", Callback=Callback, ModelCheckpoint=_recording("ModelCheckpoint"),
+                     EarlyStopping=_recording("EarlyStopping"), CSVLogger=_recording("CSVLogger"),
+                     ReduceLROnPlateau=_recording("ReduceLROnPlateau"),
+                     LearningRateScheduler=_recording("LearningRateScheduler"))
+    schedules = _mod("tensorflow.keras.optimizers.schedules", CosineDecay=type("CosineDecay", (_Recorder,), {}))
+    optimizers = _mod("tensorflow.keras.optimizers", Adam=type("Adam", (_Recorder,), {}), schedules=schedules)
+    backend_extra = dict(clear_session=lambda: None)
     layers = _mod("tensorflow.keras.layers", Layer=Layer, Dense=Dense, Dropout=Dropout, Embedding=Embedding, Input=Input,
                   Lambda=Lambda, Multiply=Multiply, Add=Add, LayerNormalization=LayerNormalization)
 
@@ -536,8 +554,9 @@ def build_modules() -> Dict[str, types.ModuleType]:
         raise NotImplementedError("tf_shim: load_model (Keras HDF5) is outside the shim; see scann_b200/h5lite.py")
 
     models = _mod("tensorflow.keras.models", load_model=load_model, Model=Model, Sequential=Sequential)
+    backend.__dict__.update(backend_extra)
     keras = _mod("tensorflow.keras", backend=backend, regularizers=regularizers, callbacks=callbacks, layers=layers,
-                 models=models, Model=Model, Sequential=Sequential, Input=Input)
+                 models=models, optimizers=optimizers, Model=Model, Sequential=Sequential, Input=Input)
     math = _mod("tensorflow.math", exp=_exp, logical_not=_logical_not)
     nn = _mod("tensorflow.nn", softmax=_softmax)
     linalg = _mod("tensorflow.linalg", normalize=_normalize)
@@ -546,5 +565,6 @@ def build_modules() -> Dict[str, types.ModuleType]:
               maximum=maximum, einsum=einsum, reduce_sum=reduce_sum, eye=eye, range=range_, broadcast_to=broadcast_to,
               ones=ones, Variable=Variable, custom_gradient=custom_gradient, float32=float32, float64=float64,
               int32=int32, int64=int64, bool=bool_, __version__="2.10.0-shim")
-    _modules = {m.__name__: m for m in (tf, keras, backend, regularizers, callbacks, layers, models, math, nn, linalg)}
+    _modules = {m.__name__: m for m in (tf, keras, backend, regularizers, callbacks, layers, models, optimizers, schedules, math, nn,
+                                       linalg)}
     return _modules
