@@ -153,6 +153,9 @@ def cpu_train_step_fn():
                 state["w"][k], g[k].astype(np.float32), state["m"][k], state["v"][k], state["t"], 5e-4)
         return 128
 
+    step.workload = {"structures_per_gpu": 128, "M": int(M_), "N": int(inp["neighbors"].shape[2]),
+                     "layers": int(spec.n_attention), "valid_atoms_per_gpu": int(inp["atom_mask"].sum()),
+                     "valid_pairs_per_gpu": int(inp["neighbor_mask"].sum()), "dropout": 0.1}
     return step, cores
 
 
@@ -178,8 +181,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "qm9_train_step_b128", "note": "reference graph restated on CPU in PyTorch "
-                   "(TensorFlow 2.10 is not installable in this image); rank 0 only"},
+        # the same seeded batch, model depth and Dropout sites as the sm_100a arm's N = 1 workload (same keys, same values)
+        "config": dict({"workload": "qm9_train_step_b128"}, **step.workload,
+                       note="reference graph restated on CPU in PyTorch (TensorFlow 2.10 is not installable in this "
+                            "image; the restatement equals the reference's own create_model code run on a TensorFlow "
+                            "stand-in, tests/test_reference_graph.py); rank 0 only"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
