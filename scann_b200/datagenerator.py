@@ -22,11 +22,46 @@ from typing import Dict, Tuple
 import numpy as np
 
 
+ATOMIC_FEATURES = None      # [Z + 1, 92] float32 table for feature='cgcnn' (set_atomic_features / load_atomic_features)
+
+
+def set_atomic_features(table) -> np.ndarray:
+    """Install the per-element feature vectors ``feature='cgcnn'`` batches are built from -- the reference keeps them
+    as ``atomic_features`` (scann/utils/dataset/atomic_data.py: CGCNN's ``atom_init.json``, one 92-vector per atomic
+    number, keys are strings, key "0" is the padding atom).  ``table``: such a dict, or an array ``[Z + 1, 92]``.
+    The table itself is data of the CGCNN project and is not shipped with this package."""
+    global ATOMIC_FEATURES
+    if isinstance(table, dict):
+        zmax = max(int(k) for k in table)
+        width = len(next(iter(table.values())))
+        arr = np.zeros((zmax + 1, width), np.float32)
+        for k, v in table.items():
+            arr[int(k)] = np.asarray(v, np.float32)
+    else:
+        arr = np.ascontiguousarray(table, np.float32)
+    if arr.ndim != 2:
+        raise ValueError("atomic feature table must be [Z + 1, features]")
+    ATOMIC_FEATURES = arr
+    return arr
+
+
+def load_atomic_features(path: str) -> np.ndarray:
+    """``set_atomic_features`` from a JSON file in CGCNN's ``atom_init.json`` format ({"1": [...], "2": [...], ...})."""
+    import json
+    with open(path) as f:
+        return set_atomic_features(json.load(f))
+
+
 class DataIterator:
     def __init__(self, data_energy, data_neighbor, batch_size=32, converter=False, use_ring=False, shuffle=False,
-                 feature="atomic", g_update=False):
-        if feature != "atomic":
-            raise NotImplementedError("feature='cgcnn' is not on the accelerated path")
+                 feature="atomic", g_update=False, atomic_features=None):
+        if feature not in ("atomic", "cgcnn"):
+            raise ValueError(f"feature must be 'atomic' or 'cgcnn', got {feature!r}")
+        if atomic_features is not None:
+            set_atomic_features(atomic_features)
+        if feature == "cgcnn" and ATOMIC_FEATURES is None:
+            raise NotImplementedError("feature='cgcnn' needs the per-element feature table: pass atomic_features= or call "
+                                      "scann_b200.datagenerator.load_atomic_features(<atom_init.json>)")
         self.batch_size, self.shuffle, self.use_ring, self.feature = batch_size, shuffle, use_ring, feature
         self.weight_index = 2 if g_update else 3                       # datagenerator.py:48-50
         self.converter = 1000 if converter else 1.0                    # :54-57
@@ -79,7 +114,10 @@ class DataIterator:
     # ------------------------------------------------------------------ padded batch, as the reference returns it
     def __getitem__(self, idx: int):
         csr, energy = self.csr_item(idx)
-        return pack_padded(csr), energy
+        inputs = pack_padded(csr)
+        if self.feature == "cgcnn":        # datagenerator.py:107-110: the mask comes from the atomic numbers, then the
+            inputs["atomic"] = ATOMIC_FEATURES[inputs["atomic"]]      # numbers are replaced by their feature vectors
+        return inputs, energy
 
 
 def pack_padded(csr: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
@@ -110,6 +148,71 @@ def pack_padded(csr: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
         ring[b_of_atom, m_of_atom] = csr["ring"]
         out["ring_aromatic"] = ring
     return out
+
+
+def pad_sequence(sequences, maxlen=None, dtype="int32", value=0, padding="post"):
+    """``pad_sequence`` (scann/utils/general.py:14-32): ``[n, maxlen, ...]`` array filled with ``value``, sequence ``i``
+    at the front of row ``i``; a sequence longer than ``maxlen`` keeps its LAST ``maxlen`` items.  ``padding`` is
+    accepted and, as in the reference, always behaves as "post"."""
+    if maxlen is None:
+        maxlen = max(len(seq) for seq in sequences)
+    out = np.full((len(sequences), maxlen) + np.asarray(sequences[0]).shape[1:], value, dtype=dtype)
+    for row, seq in zip(out, sequences):
+        kept = np.asarray(seq[-maxlen:], dtype=dtype)
+        row[:len(kept)] = kept
+    return out
+
+
+def pad_nested_sequences(sequences, max_len_1, max_len_2, dtype="int32", value=0):
+    """``pad_nested_sequences`` (scann/utils/general.py:35-50): ragged ``[structure][atom][neighbour]`` lists ->
+    ``[n, max_len_2 atoms, max_len_1 neighbours]`` filled with ``value``."""
+    out = np.full((len(sequences), max_len_2, max_len_1), value, dtype=dtype)
+    for block, atoms in zip(out, sequences):
+        for row, items in zip(block, atoms[-max_len_2:]):
+            kept = np.asarray(items[-max_len_1:], dtype=dtype)
+            row[:len(kept)] = kept
+    return out
+
+
+def split_data(len_data, test_percent=0.1, train_size=None, test_size=None):
+    """``split_data`` (scann/utils/general.py:79-101): ONE permutation of the global numpy generator (the same
+    ``np.random.seed`` gives the reference's split) cut into train | valid | test | extra.  Sizes: the given
+    ``train_size`` / ``test_size``, else ``int(len * (1 - 2 * test_percent))`` / ``int(len * test_percent)``; the
+    validation set takes what is left."""
+    if train_size:
+        n_train, n_test = train_size, test_size
+    else:
+        n_train, n_test = int(len_data * (1 - test_percent * 2)), int(len_data * test_percent)
+    n_valid = len_data - n_train - n_test
+    order = np.random.permutation(len_data)
+    train, valid, test, extra = np.split(order, np.cumsum([n_train, n_valid, n_test]))
+    return train, valid, test, extra
+
+
+def load_dataset(dataset, dataset_neighbor, target_prop, use_ref=False, use_ring=True):
+    """``load_dataset`` (scann/utils/general.py:104-144): the pickled object arrays the reference's preprocessing
+    writes.  ``dataset``: records ``{"Atomic": [...], "Properties": {name: value, ...}, "Features": {name: per-atom
+    flags}}``; ``dataset_neighbor``: the per-structure neighbour lists.  Returns ``(data_energy, data_neighbor)`` as
+    object arrays: rows ``[atomic numbers, target, ring/aromatic flags [atoms, n_features]]`` with ``use_ring``
+    (which takes precedence), ``[atomic numbers, target - Ref_energy]`` with ``use_ref``, else
+    ``[atomic numbers, target]``."""
+    records = np.load(dataset, allow_pickle=True)
+    if use_ref:
+        print("Using reference energy optimization", "\n")
+    if use_ring:
+        print("Using ring aromatic information", "\n")
+    rows = []
+    for rec in records:
+        value = float(rec["Properties"][target_prop])
+        if use_ring:
+            rows.append([rec["Atomic"], value, np.stack([rec["Features"][k] for k in rec["Features"]], -1)])
+        elif use_ref:
+            rows.append([rec["Atomic"], value - float(rec["Properties"]["Ref_energy"])])
+        else:
+            rows.append([rec["Atomic"], value])
+    data_energy = np.array(rows, dtype="object")
+    data_neighbor = np.array(np.load(dataset_neighbor, allow_pickle=True), dtype="object")
+    return data_energy, data_neighbor
 
 
 def prepare_input_from_neighbors(atomic_numbers, neighbors, angle: bool = True) -> Dict[str, np.ndarray]:

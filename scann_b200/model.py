@@ -41,6 +41,12 @@ class History:
         self.history.setdefault(key, []).append(float(v))
 
 
+def _ragged_capable(seq) -> bool:
+    """A Sequence whose batches may travel as CSR slices: this package's DataIterator on atomic-number features
+    (cgcnn batches carry per-atom feature vectors and go the padded way)."""
+    return hasattr(seq, "csr_item") and getattr(seq, "feature", "atomic") == "atomic"
+
+
 # --------------------------------------------------------------------------- model_config of the HDF5 files
 def keras_model_config(spec: ModelSpec) -> str:
     """The ``model_config`` attribute of a full-model HDF5 file (scann_model.py:165-177 saves the whole model): the
@@ -251,7 +257,7 @@ class ScannKerasModel:
             try:
                 for i in range(len(x)):
                     # iterators that can hand out the ragged CSR form skip the host-side padding altogether
-                    inputs, target = x.csr_item(i) if hasattr(x, "csr_item") else x[i]
+                    inputs, target = x.csr_item(i) if _ragged_capable(x) else x[i]
                     pending.append(self._train_on_batch_async(inputs, target))
                     harvest(4)                    # results older than 4 steps (long finished; ring of 8 slots)
                 harvest(0)
@@ -432,6 +438,42 @@ class SCANN:
         hy = self.config["hyper"]
         return "{}_{}".format(hy["save_path"], hy["target"])
 
+    def prepare_dataset(self, split: bool = True):
+        """``SCANN.prepare_dataset`` (scann_model.py:98-161): load the pickled data set (``hyper.data_energy_path`` /
+        ``hyper.data_nei_path``, written by the reference's preprocessing), standardise the target when
+        ``hyper.scaler`` is set (float32 mean / std, recorded in the config as strings like the reference), split it
+        with the global numpy generator and attach ``trainIter`` / ``validIter`` / ``testIter`` (or ``dataIter``)."""
+        from .datagenerator import DataIterator, load_dataset, split_data
+        hy, cm = self.config["hyper"], self.config["model"]
+        data_energy, data_neighbor = load_dataset(hy["data_energy_path"], hy["data_nei_path"], hy["target"],
+                                                  use_ref=hy["use_ref"], use_ring=cm["use_ring"])
+        if hy["scaler"]:
+            values = [row[1] for row in data_energy]
+            self.mean, self.std = np.mean(values, dtype="float32"), np.std(values, dtype="float32")
+            print("Normalize dataset property with mean: ", self.mean, " , std: ", self.std, "\n")
+            data_energy[:, 1] = (data_energy[:, 1] - self.mean) / self.std
+        hy["target_mean"], hy["target_std"] = str(self.mean), str(self.std)
+        hy["data_size"] = len(data_energy)
+
+        def iterator(indices=None, shuffle=False):
+            return DataIterator(batch_size=hy["batch_size"], use_ring=cm["use_ring"], shuffle=shuffle,
+                                feature=cm["feature"], g_update=cm["g_update"],
+                                data_neighbor=data_neighbor if indices is None else data_neighbor[indices],
+                                data_energy=data_energy if indices is None else data_energy[indices])
+
+        if not split:
+            self.dataIter = iterator()
+            return None
+        train, valid, test, extra = split_data(len_data=len(data_energy), test_percent=hy["test_percent"],
+                                               train_size=hy["train_size"], test_size=hy["test_size"])
+        assert len(extra) == 0, "Split was inexact {} {} {} {}".format(len(train), len(valid), len(test), len(extra))
+        print("Number of train data : ", len(train), " , Number of valid data: ", len(valid),
+              " , Number of test data: ", len(test), "\n")
+        # the reference shuffles every subset that is as long as the training subset (scann_model.py:146)
+        self.trainIter, self.validIter, self.testIter = [iterator(ix, shuffle=(len(ix) == len(train)))
+                                                         for ix in (train, valid, test)]
+        return train, valid, test
+
     def create_callbacks(self):
         """ModelCheckpoint(best val_mae) + EarlyStopping(patience 200) + SGDRC / lr logging (scann_model.py:163-197)."""
         from . import callbacks as C
@@ -448,7 +490,7 @@ class SCANN:
 
     def train(self, epochs: int = 1000):
         """``SCANN.train`` (scann_model.py:199-245) for iterators attached as ``self.trainIter`` / ``self.validIter``
-        (``prepare_dataset`` needs pymatgen / the datasets and is outside the accelerated path)."""
+        or by ``prepare_dataset``)."""
         import yaml
         if not hasattr(self, "trainIter"):
             raise RuntimeError("attach trainIter / validIter (DataIterator-like sequences) before train()")

@@ -439,3 +439,44 @@ def test_training_shell_follows_the_reference_train_and_evaluate(ref, scheduler,
     np.testing.assert_allclose(np.asarray(r["hist"][0], np.float64), np.asarray(m["hist"][0], np.float64), rtol=1e-12)
     np.testing.assert_allclose(np.asarray(r["hist"][1], np.float64), np.asarray(m["hist"][1], np.float64), rtol=0)
     assert r["hist"][2] == m["hist"][2]
+
+
+@pytest.mark.parametrize("split,scaler,use_ring", [(True, True, False), (True, False, True), (False, True, True)])
+def test_prepare_dataset_follows_the_reference(ref, tmp_path, split, scaler, use_ring):
+    """``SCANN.prepare_dataset`` (scann_model.py:98-161) of the reference -- load_dataset, float32 mean / std target
+    scaling, split_data, the three DataIterators -- beside ``scann_b200.model.SCANN.prepare_dataset`` on the same
+    pickled data set and the same numpy seed: same split, same recorded config entries, bit-identical batches."""
+    from scann_b200 import model as mine
+    from tests.test_reference_pins import _write_dataset
+    p_e, p_n = _write_dataset(tmp_path, n=61)
+    out = {}
+    for who, cls in (("reference", ref["SCANN"]), ("mine", mine.SCANN)):
+        cfg = get_config("qm9")
+        cfg["model"]["use_ring"] = use_ring
+        cfg["hyper"].update(data_energy_path=p_e, data_nei_path=p_n, scaler=scaler, batch_size=8, test_percent=0.1,
+                            train_size=None, test_size=None)
+        obj = object.__new__(cls)
+        obj.config, obj.mean, obj.std = cfg, 0, 1
+        np.random.seed(23)
+        with ref["shim"].session({}, {}):
+            res = obj.prepare_dataset(split=split)
+        out[who] = (obj, res)
+    (r, r_res), (m, m_res) = out["reference"], out["mine"]
+    assert r.mean == m.mean and r.std == m.std and type(r.mean) is type(m.mean)
+    for k in ("target_mean", "target_std", "data_size"):
+        assert r.config["hyper"][k] == m.config["hyper"][k], k
+    if split:
+        for a, b in zip(r_res, m_res):
+            assert np.array_equal(a, b)
+        names = ("trainIter", "validIter", "testIter")
+    else:
+        assert r_res is None and m_res is None
+        names = ("dataIter",)
+    for n in names:
+        a, b = getattr(r, n), getattr(m, n)
+        assert len(a) == len(b) and a.shuffle == b.shuffle and a.batch_size == b.batch_size
+        for i in range(len(a)):
+            (ai, ae), (bi, be) = a[i], b[i]
+            assert np.array_equal(ae, be) and ae.dtype == be.dtype and set(ai) == set(bi)
+            for k in ai:
+                assert ai[k].dtype == bi[k].dtype and np.array_equal(ai[k], bi[k]), (n, i, k)

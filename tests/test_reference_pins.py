@@ -143,3 +143,86 @@ def test_shipped_yaml_configs_equal_the_restated_dicts():
                   "use_ga_norm", "dense_out", "use_ring"):
             assert theirs["model"][k] == mine["model"][k], (name, k)
         assert ("g_update" in theirs["model"]) == ("g_update" in mine["model"]), name     # model_ptgp.yaml lacks it
+
+
+def test_cgcnn_dataiterator_matches_the_reference_class(ref):
+    """feature='cgcnn' (datagenerator.py:107-110): the atom mask comes from the atomic numbers, then the numbers are
+    replaced by the 92-vectors of the reference's own ``atomic_features`` table (handed over at run time: the table is
+    data of the CGCNN project and is not shipped here)."""
+    from scann_b200.datagenerator import DataIterator, synthetic_ragged
+    de, dn = synthetic_ragged(21, seed=3)
+    theirs = ref["DataIterator"](de, dn, batch_size=8, feature="cgcnn", g_update=True)
+    ours = DataIterator(de, dn, batch_size=8, feature="cgcnn", g_update=True, atomic_features=ref["atomic_features"])
+    for i in range(len(theirs)):
+        (r_in, r_e), (o_in, o_e) = theirs[i], ours[i]
+        assert np.array_equal(r_e, o_e) and set(r_in) == set(o_in)
+        assert o_in["atomic"].shape[-1] == 92
+        for k in r_in:
+            assert o_in[k].dtype == r_in[k].dtype and np.array_equal(o_in[k], r_in[k]), k
+    assert not hasattr(ours, "feature") or ours.feature == "cgcnn"
+
+
+@pytest.mark.parametrize("kw", [dict(len_data=1000), dict(len_data=1003, test_percent=0.15),
+                                dict(len_data=500, train_size=400, test_size=60), dict(len_data=17, test_percent=0.2)])
+def test_split_data_matches_the_reference_function(ref, kw):
+    from scann_b200.datagenerator import split_data
+    np.random.seed(11)
+    theirs = ref["general"].split_data(**kw)
+    np.random.seed(11)
+    ours = split_data(**kw)
+    assert len(theirs) == len(ours) == 4
+    for a, b in zip(theirs, ours):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+
+
+def _write_dataset(tmp_path, n=37, ring=True, seed=5):
+    """A data set in the format the reference's preprocessing writes (scann/utils/dataset/qm9.py): records with
+    Atomic / Properties / Features, and the per-structure neighbour lists."""
+    from scann_b200.datagenerator import synthetic_ragged
+    rng = np.random.default_rng(seed)
+    de, dn = synthetic_ragged(n, seed=seed, use_ring=True)
+    records = []
+    for z, _, flags in de:
+        flags = np.asarray(flags)
+        records.append({"Atomic": list(z), "Properties": {"homo": float(rng.normal(-6.5, 0.6)), "u0": float(rng.normal(-400, 40)),
+                                                          "Ref_energy": float(rng.normal(-399, 40))},
+                        "Features": {"Ring": flags[:, 0], "Aromatic": flags[:, 1]}})
+    p_e, p_n = str(tmp_path / "data_energy.npy"), str(tmp_path / "data_neighbor.npy")
+    np.save(p_e, np.array(records, dtype=object), allow_pickle=True)
+    np.save(p_n, np.array(dn, dtype=object), allow_pickle=True)
+    return p_e, p_n
+
+
+@pytest.mark.parametrize("use_ref,use_ring,target", [(False, True, "homo"), (True, False, "u0"), (False, False, "homo"),
+                                                      (True, True, "u0")])
+def test_load_dataset_matches_the_reference_function(ref, tmp_path, use_ref, use_ring, target):
+    from scann_b200.datagenerator import load_dataset
+    p_e, p_n = _write_dataset(tmp_path)
+    te, tn = ref["general"].load_dataset(p_e, p_n, target, use_ref=use_ref, use_ring=use_ring)
+    oe, on = load_dataset(p_e, p_n, target, use_ref=use_ref, use_ring=use_ring)
+    assert te.shape == oe.shape and te.dtype == oe.dtype == object and tn.shape == on.shape
+    for a, b in zip(te, oe):
+        assert list(a[0]) == list(b[0]) and a[1] == b[1]
+        if use_ring:
+            assert np.array_equal(a[2], b[2])
+    for a, b in zip(tn, on):
+        assert a == b
+
+
+def test_pad_helpers_of_the_package_match_the_reference_functions(ref):
+    from scann.utils import pad_nested_sequences, pad_sequence          # the reference's import path, this repo's code
+    from scann_b200 import datagenerator as dg
+    assert pad_sequence is dg.pad_sequence
+    rng = np.random.default_rng(9)
+    seqs = [list(rng.integers(1, 50, size=int(n))) for n in rng.integers(1, 12, size=9)]
+    for kw in (dict(), dict(maxlen=15, value=1000), dict(maxlen=4), dict(dtype="float32", value=-1.5)):
+        a, b = ref["pad_sequence"](seqs, **kw), pad_sequence(seqs, **kw)
+        assert a.dtype == b.dtype and np.array_equal(a, b), kw
+    feats = [rng.integers(0, 2, size=(int(n), 2)) for n in rng.integers(1, 8, size=5)]      # ring flags: [atoms, 2]
+    a, b = ref["pad_sequence"](feats, maxlen=9), pad_sequence(feats, maxlen=9)
+    assert a.shape == b.shape == (5, 9, 2) and np.array_equal(a, b)
+    nested = [[list(rng.random(int(k))) for k in rng.integers(0, 7, size=int(n))] for n in rng.integers(1, 6, size=7)]
+    for kw in (dict(max_len_1=7, max_len_2=6, dtype="float32"), dict(max_len_1=9, max_len_2=8, dtype="float32", value=3.0),
+               dict(max_len_1=3, max_len_2=2, dtype="float32")):
+        a, b = ref["pad_nested_sequences"](nested, **kw), pad_nested_sequences(nested, **kw)
+        assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), kw
