@@ -480,3 +480,36 @@ def test_prepare_dataset_follows_the_reference(ref, tmp_path, split, scaler, use
             assert np.array_equal(ae, be) and ae.dtype == be.dtype and set(ai) == set(bi)
             for k in ai:
                 assert ai[k].dtype == bi[k].dtype and np.array_equal(ai[k], bi[k]), (n, i, k)
+
+
+def test_public_surface_matches_the_reference(ref):
+    """Every public method of the reference's ``SCANN`` exists here with the same parameter names and defaults (extra
+    optional parameters allowed), ``scann.layers`` exports the reference's ``__all__``, and the module-level helpers a
+    reference user imports (``create_model``, ``DataIterator``, ``split_data`` ...) resolve under the same paths."""
+    import importlib
+    import inspect
+    from scann_b200 import model as mine
+    for name, f in inspect.getmembers(ref["SCANN"], predicate=lambda x: inspect.isfunction(x) or inspect.ismethod(x)):
+        if name.startswith("__") and name != "__init__":
+            continue
+        assert hasattr(mine.SCANN, name), name
+        theirs = inspect.signature(f).parameters
+        ours = inspect.signature(getattr(mine.SCANN, name)).parameters
+        assert list(ours)[:len(theirs)] == list(theirs), name
+        for p in theirs:
+            assert ours[p].default == theirs[p].default or theirs[p].default is inspect.Parameter.empty, (name, p)
+        for p in list(ours)[len(theirs):]:
+            assert ours[p].default is not inspect.Parameter.empty, (name, p)       # extras must be optional
+    ref_all = ["GlobalAttention", "LocalAttention", "ResidualNorm", "GaussianExpansion", "SGDRC",
+               "root_mean_squared_error", "r2_square", "gather_shape", "mrelu"]      # scann/layers/__init__.py:7-17
+    import scann.layers
+    assert sorted(scann.layers.__all__) == sorted(ref_all)
+    assert all(k in scann.layers._CUSTOM_OBJECTS for k in ref_all)
+    for mod, names in {"scann.models": ["SCANN"], "scann.utils": ["DataIterator", "pad_sequence", "pad_nested_sequences",
+                                                                 "split_data", "load_dataset"],
+                       "scann.utils.general": ["pad_sequence", "pad_nested_sequences", "split_data", "load_dataset"],
+                       "scann.utils.datagenerator": ["DataIterator"]}.items():
+        m = importlib.import_module(mod)
+        for n in names:
+            assert hasattr(m, n), (mod, n)
+    assert callable(mine.create_model)
