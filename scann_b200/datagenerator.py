@@ -244,6 +244,18 @@ def prepare_input_from_neighbors(atomic_numbers, neighbors, angle: bool = True) 
             "neighbor_weight": w, "neighbor_distance": d}
 
 
+def prepare_input_pmt(struct, d_t=4.0, w_t=0.4, angle=True, neighbors=None) -> Dict[str, np.ndarray]:
+    """``prepare_input_pmt`` (scann/utils/general.py:206-246) with the reference's signature.  The Voronoi neighbour
+    search behind it (``compute_voronoi_neighbor``: pymatgen + Qhull) is outside this package, so the caller hands the
+    neighbour lists over as ``neighbors`` (what ``compute_voronoi_neighbor(struct, d_thresh=d_t, w_thresh=w_t)`` of the
+    reference returns); ``struct`` only has to offer ``atomic_numbers``.  Without ``neighbors`` the call fails loudly."""
+    if neighbors is None:
+        raise NotImplementedError("prepare_input_pmt: the Voronoi neighbour search (pymatgen / Qhull) is not part of the "
+                                  "accelerated package; pass neighbors=compute_voronoi_neighbor(struct, d_thresh=d_t, "
+                                  "w_thresh=w_t) or call prepare_input_from_neighbors(atomic_numbers, neighbors)")
+    return prepare_input_from_neighbors(list(struct.atomic_numbers), neighbors, angle=angle)
+
+
 def padded_to_csr(inputs: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
     """Inverse of ``pack_padded`` for batches whose valid atoms / neighbour slots are prefixes (what
     DataIterator.__getitem__ produces): padded dict -> CSR batch for ``Engine.load_batch_csr``."""

@@ -226,3 +226,28 @@ def test_pad_helpers_of_the_package_match_the_reference_functions(ref):
                dict(max_len_1=3, max_len_2=2, dtype="float32")):
         a, b = ref["pad_nested_sequences"](nested, **kw), pad_nested_sequences(nested, **kw)
         assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), kw
+
+
+def test_prepare_input_pmt_matches_the_reference_function(ref, monkeypatch):
+    """The reference's OWN ``prepare_input_pmt`` (general.py:206-246) with its Voronoi search replaced by given
+    neighbour lists, beside ``scann.utils.prepare_input_pmt(struct, ..., neighbors=...)``: identical input dicts
+    (README.md:102-120 inference flow); without neighbours ours refuses loudly."""
+    import types
+    from scann.utils import prepare_input_pmt
+    rng = np.random.default_rng(4)
+    na = 14
+    neighbors = [[(0, int(rng.integers(0, na)), float(rng.uniform(0.4, 3)), float(rng.uniform(0.2, 1)), float(rng.uniform(1, 4)))
+                  for _ in range(int(rng.integers(1, 12)))] for _ in range(na)]
+    struct = types.SimpleNamespace(atomic_numbers=tuple(int(z) for z in rng.choice([1, 6, 7, 8, 26], size=na)))
+    seen = {}
+    monkeypatch.setattr(ref["general"], "compute_voronoi_neighbor",
+                        lambda s, d_thresh, w_thresh: (seen.update(d=d_thresh, w=w_thresh), neighbors)[1])
+    for angle in (True, False):
+        want = ref["general"].prepare_input_pmt(struct, d_t=3.5, w_t=0.3, angle=angle)
+        assert seen == {"d": 3.5, "w": 0.3}
+        got = prepare_input_pmt(struct, d_t=3.5, w_t=0.3, angle=angle, neighbors=neighbors)
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].dtype == want[k].dtype and got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), k
+    with pytest.raises(NotImplementedError):
+        prepare_input_pmt(struct)
