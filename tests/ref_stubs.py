@@ -171,7 +171,7 @@ def load_reference_graph():
                         "LocalAttention": att.LocalAttention, "GlobalAttention": att.GlobalAttention,
                         "ResidualNorm": att.ResidualNorm, "GaussianExpansion": cl.GaussianExpansion,
                         "gather_shape": cl.gather_shape, "mrelu": cl.mrelu,
-                        "root_mean_squared_error": ls.root_mean_squared_error, "SCANN": sm.SCANN, "SGDRC": cl.SGDRC,
+                        "root_mean_squared_error": ls.root_mean_squared_error, "r2_square": ls.r2_square, "SCANN": sm.SCANN, "SGDRC": cl.SGDRC,
                         "shim": tf_shim}
     finally:
         sys.path.remove(REFERENCE_ROOT)

@@ -513,3 +513,17 @@ def test_public_surface_matches_the_reference(ref):
         for n in names:
             assert hasattr(m, n), (mod, n)
     assert callable(mine.create_model)
+
+
+def test_loss_and_metric_functions_match_the_reference(ref):
+    """``root_mean_squared_error`` / ``r2_square`` (scann/layers/losses.py:5-16, the compile() loss and metric) of the
+    reference against the host functions ``scann.layers`` exports here."""
+    import scann.layers as L
+    rng = np.random.default_rng(2)
+    for n in (1, 7, 128):
+        yt, yp = rng.standard_normal((n, 1)), rng.standard_normal((n, 1))
+        with ref["shim"].session({}, {}):
+            want_rmse = float(ref["root_mean_squared_error"](torch.tensor(yt), torch.tensor(yp)))
+            want_r2 = float(ref["r2_square"](torch.tensor(yt), torch.tensor(yp)))
+        assert abs(L.root_mean_squared_error(yt, yp) - want_rmse) <= 1e-14 * max(1.0, want_rmse)
+        assert abs(L.r2_square(yt, yp) - want_r2) <= 1e-12 * max(1.0, abs(want_r2))
